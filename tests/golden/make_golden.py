@@ -1,0 +1,196 @@
+"""Generate the committed golden fixtures by RUNNING THE UNMODIFIED REFERENCE (CPU, fp32).
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py [--full]
+
+Everything here goes through oracle/refshim.py (SURVEY.md Appendix C recipe: 4 module stubs,
+`.cuda()` -> identity, conjugate-symmetric Cauchy fallback).  Outputs are small .npz files in
+this directory; `-m gpu` tests and the oracle tests read them, never /root/reference.
+
+Fixture families
+  schedule_*.npz      utils.calc_diffusion_hyperparams                      (utils.py:121-151)
+  embed.npz           models.utils.calc_diffusion_step_embedding            (models/utils.py:4-29)
+  cauchy.npz          extensions/cauchy/cauchy.py:cauchy_mult_torch in complex128 on the inputs of
+                      extensions/cauchy/test_cauchy.py:11-23,53-66 (seed 2357, batch 4)
+  s4kernel_*.npz      models.s4.S4(...).kernel(L) before/after _setup_C      (s4.py:525-551,674-807)
+  tiny_*.npz          full state_dict + (x, t, mel) -> eps for tiny WaveNet / SaShiMi models
+  traj_*.npz          generate.sampling() on a tiny model, seeded            (generate.py:23-55)
+  full_*.npz (--full) eps of the reference at BASELINE sizes for weights created by OUR
+                      package's seeded initialiser (only the 64 KB outputs are stored)
+"""
+import argparse
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings("ignore")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import refshim  # noqa: E402
+
+SMALL_EMB = dict(diffusion_step_embed_dim_in=16, diffusion_step_embed_dim_mid=32,
+                 diffusion_step_embed_dim_out=32)
+# Sashimi's DiffWaveBlock ignores the config and hard-wires fc_t to 512 inputs (sashimi.py:116)
+SMALL_EMB_S = dict(diffusion_step_embed_dim_in=16, diffusion_step_embed_dim_mid=32,
+                   diffusion_step_embed_dim_out=512)
+
+TINY = {
+    "tiny_unet": dict(base="unet_d64", over=dict(d_model=8, n_layers=2, L=256, **SMALL_EMB_S), B=2, L=256),
+    "tiny_snet": dict(base="unet_d64", over=dict(d_model=8, n_layers=2, L=320, unet=False, pool=[4, 2], **SMALL_EMB_S), B=1, L=320),
+    "tiny_unet_e128": dict(base="unet_d64", over=dict(d_model=4, n_layers=1, L=64, pool=[2, 2]), B=3, L=64),
+    "tiny_unet_cond": dict(base="unet_d32_cond", over=dict(d_model=8, n_layers=1, L=512, **SMALL_EMB_S), B=2, L=512, mel=(1, 80, 3)),
+    "tiny_unet_condB": dict(base="unet_d32_cond", over=dict(d_model=8, n_layers=1, L=512, **SMALL_EMB_S), B=2, L=512, mel=(2, 80, 2)),
+    "tiny_wnet": dict(base="wnet_h128_d30", over=dict(res_channels=16, skip_channels=8, num_res_layers=7, dilation_cycle=5, **SMALL_EMB), B=2, L=300),
+    "tiny_wnet_cond": dict(base="wnet_h128_d30", over=dict(res_channels=8, skip_channels=16, num_res_layers=3, dilation_cycle=2, unconditional=False, mel_upsample=[16, 16], **SMALL_EMB), B=2, L=512, mel=(1, 80, 2)),
+}
+
+
+def np_sd(sd):
+    return {"sd/" + k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def nonzero_final(net):
+    """ZeroConv1d makes a fresh model output exactly 0 (SURVEY finding 5)."""
+    with torch.no_grad():
+        w = net.final_conv[2].conv.weight
+        w.normal_(0, (1.0 / w.shape[1]) ** 0.5)
+        net.final_conv[2].conv.bias.fill_(0.05)
+
+
+def build(ns, base, over, seed=0):
+    cfg = refshim.Cfg(refshim.MODEL_CFGS[base])
+    cfg.update(over)
+    torch.manual_seed(seed)
+    net = ns.models.construct_model(cfg).eval()
+    nonzero_final(net)
+    return cfg, net
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"{name}.npz  {os.path.getsize(path) / 1024:.1f} KB")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    args = ap.parse_args()
+    ns = refshim.load(parity=True)
+
+    # --- schedule ---------------------------------------------------------------------
+    for tag, kw in (("T200", dict(T=200, beta_0=1e-4, beta_T=0.02)), ("T50", dict(T=50, beta_0=1e-4, beta_T=0.05)),
+                    ("fast6", dict(T=6, beta_0=1e-4, beta_T=0.02, beta=[0.0001, 0.001, 0.01, 0.05, 0.2, 0.5], fast=True))):
+        dh = ns.utils.calc_diffusion_hyperparams(**kw)
+        save("schedule_" + tag, T=dh["T"], **{k: dh[k].numpy() for k in ("Beta", "Alpha", "Alpha_bar", "Sigma")},
+             kw=np.array(repr(kw)))
+
+    # --- step embedding ---------------------------------------------------------------
+    import models.utils as ref_mu  # imported by refshim under the reference's package name
+    t = torch.tensor([[0.], [1.], [2.5], [49.], [100.], [199.]])
+    save("embed", t=t.numpy(), e128=ref_mu.calc_diffusion_step_embedding(t, 128).numpy(),
+         e16=ref_mu.calc_diffusion_step_embedding(t, 16).numpy())
+
+    # --- Cauchy op (reference's own test recipe) --------------------------------------
+    sys.modules["cauchy_mult"] = types.SimpleNamespace(cauchy_mult_fwd=None, cauchy_mult_bwd=None,
+                                                       cauchy_mult_sym_fwd=None, cauchy_mult_sym_bwd=None)
+    sys.path.insert(0, os.path.join(refshim.REF_ROOT, "extensions", "cauchy"))
+    import cauchy as ref_cauchy
+    sys.path.pop(0)
+    out = {}
+    for N in (4, 8, 64, 256):            # full-spectrum sizes as in test_cauchy.py:54 (kernel sees N/2)
+        for L in (3, 17, 489, 1024, 1047):
+            torch.random.manual_seed(2357)
+            v_half = torch.randn(4, N // 2, dtype=torch.complex64)
+            v = torch.cat([v_half, v_half.conj()], dim=-1)
+            w_half = torch.randn(4, N // 2, dtype=torch.complex64)
+            w = torch.cat([w_half, w_half.conj()], dim=-1)
+            z = torch.exp(1j * torch.randn(L, dtype=torch.float32))
+            ref = ref_cauchy.cauchy_mult_torch(v.cdouble(), z.cdouble(), w.cdouble(), symmetric=True)
+            out[f"v_{N}_{L}"], out[f"w_{N}_{L}"], out[f"z_{N}_{L}"] = v_half.numpy(), w_half.numpy(), z.numpy()
+            out[f"out_{N}_{L}"] = ref.numpy()
+    save("cauchy", **out)
+
+    # --- S4 kernel generation ---------------------------------------------------------
+    for H, L in ((4, 64), (3, 100), (2, 250), (2, 1000)):
+        torch.manual_seed(3)
+        s4 = ns.s4.S4(H, l_max=L, bidirectional=True).eval()
+        sd0 = {k: v.clone() for k, v in s4.state_dict().items()}
+        with torch.no_grad():
+            k, _ = s4.kernel(L=L, rate=1.0)
+        sd1 = s4.state_dict()
+        omega = s4.kernel.kernel.omega
+        save(f"s4kernel_H{H}_L{L}", k=k.numpy(), omega=omega.numpy(),
+             **{"sd0/" + kk: v.numpy() for kk, v in sd0.items()}, **{"sd1/" + kk: v.numpy() for kk, v in sd1.items()})
+
+    # --- tiny models: weights + io ----------------------------------------------------
+    for name, spec in TINY.items():
+        cfg, net = build(ns, spec["base"], spec["over"])
+        B, L = spec["B"], spec["L"]
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(B, 1, L, generator=g)
+        t = torch.tensor([[3.], [17.], [0.]])[:B]
+        mel = torch.randn(*spec["mel"], generator=g) if "mel" in spec else None
+        sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+        with torch.no_grad():
+            eps = net((x, t), mel_spec=mel)
+        arrs = dict(cfg=np.array(repr(dict(cfg))), x=x.numpy(), t=t.numpy(), eps=eps.numpy(), **np_sd(net.state_dict()))
+        if mel is not None:
+            arrs["mel"] = mel.numpy()
+        if cfg["_name_"] == "sashimi":   # also keep the fresh (kernel.L == 0) C tensors to pin _setup_C
+            arrs.update({"sd0/" + k: v.numpy() for k, v in sd0.items() if k.endswith("kernel.kernel.C") or k.endswith("kernel.kernel.L")})
+        save(name, **arrs)
+
+    # --- sampler trajectories on tiny models -----------------------------------------
+    for name in ("tiny_unet", "tiny_wnet"):
+        spec = TINY[name]
+        cfg, net = build(ns, spec["base"], spec["over"])
+        with torch.no_grad():
+            net.final_conv[2].conv.weight.mul_(8.0)  # make eps matter against the injected noise
+        B, L, T = 2, spec["L"], 12
+        dh = ns.utils.calc_diffusion_hyperparams(T=T, beta_0=1e-4, beta_T=0.02, fast=True)
+        with torch.no_grad():
+            net((torch.zeros(1, 1, L), torch.zeros(1, 1)))   # settle _setup_C before saving weights
+        torch.manual_seed(1234)
+        x0 = ns.generate.sampling(net, (B, 1, L), dh)
+        save("traj_" + name, cfg=np.array(repr(dict(cfg))), T=T, beta_0=1e-4, beta_T=0.02, seed=1234,
+             x0=x0.numpy(), **np_sd(net.state_dict()))
+
+    if args.full:
+        make_full(ns)
+
+
+FULL = {
+    # name: (base cfg, B, t, mel)
+    "full_wnet_h128_d30": ("wnet_h128_d30", 1, 100.0, None),
+    "full_unet_d64": ("unet_d64", 1, 100.0, None),
+    "full_unet_d32_cond": ("unet_d32_cond", 1, 25.0, (1, 80, 63)),
+}
+
+
+def make_full(ns):
+    """Reference eps at BASELINE sizes for weights made by diffwave_sashimi_b200's own seeded
+    initialiser: the GPU-box tests rebuild the same weights from the seed and compare the CUDA
+    engine with these stored reference outputs (64 KB each)."""
+    import diffwave_sashimi_b200 as dwb
+    for name, (base, B, tval, melshape) in FULL.items():
+        cfg = refshim.Cfg(refshim.MODEL_CFGS[base])
+        sd = dwb.init.seeded_state_dict(dict(cfg), seed=0)
+        net = ns.models.construct_model(cfg).eval()
+        net.load_state_dict(sd)
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(B, 1, 16000, generator=g)
+        mel = torch.randn(*melshape, generator=g) if melshape else None
+        outs = {}
+        with torch.no_grad():
+            for tv in (tval, 0.0):
+                outs[f"eps_t{int(tv)}"] = net((x, tv * torch.ones(B, 1)), mel_spec=mel).numpy()
+        save(name, cfg=np.array(repr(dict(cfg))), seed=0, xseed=5, **outs)
+
+
+if __name__ == "__main__":
+    main()
