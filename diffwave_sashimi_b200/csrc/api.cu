@@ -1,0 +1,815 @@
+// libdwb C ABI: plan life cycle, weight ingestion, forward and the graph-captured sampler.
+// Host-side orchestration only; all arithmetic lives in the kernel translation units.
+//
+// Reference call sites this file stands in for:
+//   generate.py:94-103  construct_model(cfg).cuda(); load_state_dict      -> dwb_plan_create / set_tensor / finalize
+//   generate.py:51      net((x, t), mel_spec)                              -> dwb_forward
+//   generate.py:23-55   sampling()                                         -> dwb_sample
+#include <stdarg.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "fft_plan.cuh"
+#include "kernels.h"
+
+namespace dwb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
+    return DWB_ERR_CUDA;
+}
+
+struct Tensor {
+    std::vector<int64_t> shape;
+    int dtype = DWB_F32;
+    void *dev = nullptr;
+    size_t bytes = 0;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto s : shape) n *= s;
+        return n;
+    }
+};
+
+enum OpKind { OP_BLOCK = 0, OP_DOWN = 1, OP_UP = 2 };
+
+struct Op {
+    int kind;
+    std::string prefix;
+    int H;        // block: width; pools: input width
+    int l;        // input length
+    int Ho;       // pools: output width
+    int s;        // pool factor
+    int in_buf = -1, out_buf = -1, skip_buf = -1;
+    // block weights
+    float ln1_m = 0, ln1_s = 1, ln2_m = 0, ln2_s = 1;
+    float *kf = nullptr, *k32 = nullptr;
+    float *Wo_t = nullptr, *bo = nullptr, *W1_t = nullptr, *b1 = nullptr, *W2_t = nullptr, *b2 = nullptr;
+    int F = 0;
+    int part_off = 0;      // offset of this block's fc_t rows in the stacked embedding output
+    int64_t cond_off = 0;  // float offset (per cond batch element) of this block's conditioning features
+    // pool weights
+    float *Wp_t = nullptr, *bp = nullptr;
+};
+
+struct WaveLayer {
+    int dilation;
+    float *Wd_t, *bd, *Wr_t, *br, *Ws_t, *bs;
+    int part_off;
+    int64_t cond_off;
+};
+
+struct GraphKey {
+    const void *xT = nullptr, *noise = nullptr, *cond = nullptr, *out = nullptr;
+    int cond_batch = 0, T = 0, B = 0, L = 0;
+    std::vector<float> coef;
+    bool operator==(const GraphKey &o) const {
+        return xT == o.xT && noise == o.noise && cond == o.cond && out == o.out && cond_batch == o.cond_batch &&
+               T == o.T && B == o.B && L == o.L && coef == o.coef;
+    }
+};
+
+}  // namespace dwb
+
+using namespace dwb;
+
+struct dwb_plan {
+    dwb_config cfg;
+    int device = 0;
+    bool finalized = false;
+    std::map<std::string, Tensor> tensors;
+    std::vector<void *> owned;
+    int64_t launches = 0;
+
+    // embedding
+    float *eW1 = nullptr, *eb1 = nullptr, *eW2 = nullptr, *eb2 = nullptr, *Wt_all = nullptr, *bt_all = nullptr;
+    int Mtot = 0;
+    // input conv / head
+    float *init_w = nullptr, *init_b = nullptr;
+    float *Wf_t = nullptr, *bf = nullptr, *wz = nullptr;
+    float bz = 0.f, norm_m = 0.f, norm_s = 1.f;
+    int headC = 0;
+
+    std::vector<Op> ops;           // sashimi
+    int n_bufs = 0;
+    std::vector<WaveLayer> wl;     // wavenet
+    int64_t cond_total = 0;        // floats of conditioning features per cond batch element
+
+    // workspace (grow-only, keyed on B*L)
+    int ws_B = 0, ws_L = 0;
+    std::vector<float *> bufs, stat_bufs;
+    float *g_buf = nullptr, *emb_buf = nullptr, *part_buf = nullptr;
+    float *skip_acc = nullptr;     // wavenet
+    std::vector<void *> ws_owned;
+
+    // sampler
+    float *table_emb = nullptr, *table_part = nullptr, *table_t = nullptr;   // (T, .) per-step fc_t outputs
+    int table_T = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    GraphKey graph_key;
+    int64_t graph_nodes = 0;
+};
+
+namespace dwb {
+
+static int dev_alloc(dwb_plan *p, size_t bytes, void **out, bool workspace = false) {
+    void *d = nullptr;
+    DWB_CUDA(cudaMalloc(&d, bytes ? bytes : 4));
+    (workspace ? p->ws_owned : p->owned).push_back(d);
+    *out = d;
+    return DWB_OK;
+}
+
+static const Tensor *find(dwb_plan *p, const std::string &name) {
+    auto it = p->tensors.find(name);
+    return it == p->tensors.end() ? nullptr : &it->second;
+}
+
+static int need(dwb_plan *p, const std::string &name, int64_t numel, const Tensor **out) {
+    const Tensor *t = find(p, name);
+    DWB_REQUIRE(t, DWB_ERR_MISSING, "state_dict entry `%s` was not supplied", name.c_str());
+    DWB_REQUIRE(t->dtype == DWB_F32, DWB_ERR_INVALID, "`%s` must be float32", name.c_str());
+    DWB_REQUIRE(t->numel() == numel, DWB_ERR_INVALID, "`%s` has %lld elements, expected %lld", name.c_str(),
+                (long long)t->numel(), (long long)numel);
+    *out = t;
+    return DWB_OK;
+}
+
+#define TRY(expr)                      \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != DWB_OK) return _rc; \
+    } while (0)
+
+static int scalar_of(dwb_plan *p, const std::string &name, float *out, cudaStream_t st) {
+    const Tensor *t;
+    TRY(need(p, name, 1, &t));
+    DWB_CUDA(cudaMemcpyAsync(out, t->dev, sizeof(float), cudaMemcpyDeviceToHost, st));
+    DWB_CUDA(cudaStreamSynchronize(st));
+    return DWB_OK;
+}
+
+// weight-normed conv `prefix`.{weight_v,weight_g,bias} (or plain .weight/.bias) -> transposed fold
+static int folded(dwb_plan *p, const std::string &prefix, int M, int Kin, int taps, bool weight_norm, float **Wt,
+                  float **bias, cudaStream_t st) {
+    const Tensor *v, *g = nullptr, *b;
+    TRY(need(p, prefix + (weight_norm ? ".weight_v" : ".weight"), (int64_t)M * Kin * taps, &v));
+    if (weight_norm) TRY(need(p, prefix + ".weight_g", M, &g));
+    TRY(need(p, prefix + ".bias", M, &b));
+    void *o;
+    TRY(dev_alloc(p, (size_t)M * Kin * taps * sizeof(float), &o));
+    TRY(fold_weight((const float *)v->dev, g ? (const float *)g->dev : nullptr, M, Kin, taps, (float *)o, st));
+    p->launches += 1;
+    *Wt = (float *)o;
+    *bias = (float *)b->dev;
+    return DWB_OK;
+}
+
+static int build_sashimi_ops(dwb_plan *p) {
+    const dwb_config &c = p->cfg;
+    int H = c.d_model, L = c.L, i = 0;
+    p->ops.clear();
+    for (int q = 0; q < c.n_pool; ++q) {
+        const int s = c.pool[q];
+        if (c.unet)
+            for (int k = 0; k < c.n_layers; ++k) {
+                Op o{};
+                o.kind = OP_BLOCK; o.prefix = "d_layers." + std::to_string(i++) + "."; o.H = H; o.l = L;
+                p->ops.push_back(o);
+            }
+        DWB_REQUIRE(L % s == 0, DWB_ERR_INVALID, "L=%d not divisible by pool %d", L, s);
+        Op o{};
+        o.kind = OP_DOWN; o.prefix = "d_layers." + std::to_string(i++) + "."; o.H = H; o.l = L; o.Ho = H * c.expand; o.s = s;
+        p->ops.push_back(o);
+        L /= s;
+        H *= c.expand;
+    }
+    for (int k = 0; k < c.n_layers; ++k) {
+        Op o{};
+        o.kind = OP_BLOCK; o.prefix = "c_layers." + std::to_string(k) + "."; o.H = H; o.l = L;
+        p->ops.push_back(o);
+    }
+    i = 0;
+    for (int q = c.n_pool - 1; q >= 0; --q) {
+        const int s = c.pool[q];
+        Op o{};
+        o.kind = OP_UP; o.prefix = "u_layers." + std::to_string(i++) + "."; o.H = H; o.l = L; o.Ho = H / c.expand; o.s = s;
+        p->ops.push_back(o);
+        H /= c.expand;
+        L *= s;
+        for (int k = 0; k < c.n_layers; ++k) {
+            Op b{};
+            b.kind = OP_BLOCK; b.prefix = "u_layers." + std::to_string(i++) + "."; b.H = H; b.l = L;
+            p->ops.push_back(b);
+        }
+    }
+    // ---- buffer assignment: UNet skip stack (sashimi.py:292-307) with a free list
+    std::vector<int> stack, freel;
+    std::vector<bool> saved;
+    int nb = 0;
+    auto alloc = [&]() {
+        if (!freel.empty()) { int b = freel.back(); freel.pop_back(); return b; }
+        saved.push_back(false);
+        return nb++;
+    };
+    int cur = alloc();   // output of init_conv
+    size_t idx = 0;
+    const size_t n_d = (size_t)c.n_pool * ((c.unet ? c.n_layers : 0) + 1);
+    for (; idx < n_d; ++idx) {          // down path: every input is saved
+        Op &o = p->ops[idx];
+        stack.push_back(cur); saved[cur] = true;
+        o.in_buf = cur; o.out_buf = alloc(); cur = o.out_buf;
+    }
+    stack.push_back(cur); saved[cur] = true;
+    for (int k = 0; k < c.n_layers; ++k, ++idx) {   // centre
+        Op &o = p->ops[idx];
+        o.in_buf = cur; o.out_buf = alloc();
+        if (!saved[cur]) freel.push_back(cur);
+        cur = o.out_buf;
+    }
+    {   // x = x + outputs.pop() after the centre stack: fused into the last centre block
+        Op &o = p->ops[idx - 1];
+        DWB_REQUIRE(c.n_layers >= 1, DWB_ERR_UNSUPPORTED, "n_layers must be >= 1");
+        o.skip_buf = stack.back(); stack.pop_back();
+    }
+    std::vector<int> pending_free;   // skip buffers are recycled one op after the op that read them
+    pending_free.push_back(p->ops[idx - 1].skip_buf);
+    for (; idx < p->ops.size(); ++idx) {
+        Op &o = p->ops[idx];
+        for (int b : pending_free) { saved[b] = false; freel.push_back(b); }
+        pending_free.clear();
+        o.in_buf = cur; o.out_buf = alloc();
+        if (o.kind == OP_UP || c.unet) {
+            DWB_REQUIRE(!stack.empty(), DWB_ERR_INVALID, "skip stack underflow");
+            o.skip_buf = stack.back(); stack.pop_back();
+            pending_free.push_back(o.skip_buf);
+        }
+        if (!saved[cur]) freel.push_back(cur);
+        cur = o.out_buf;
+    }
+    p->n_bufs = nb;
+    return DWB_OK;
+}
+
+static int finalize_common(dwb_plan *p, const std::string &emb_prefix, const std::string &init_prefix, int C,
+                           cudaStream_t st) {
+    const dwb_config &c = p->cfg;
+    const Tensor *t;
+    TRY(need(p, emb_prefix + "fc_t1.weight", (int64_t)c.embed_mid * c.embed_in, &t)); p->eW1 = (float *)t->dev;
+    TRY(need(p, emb_prefix + "fc_t1.bias", c.embed_mid, &t)); p->eb1 = (float *)t->dev;
+    TRY(need(p, emb_prefix + "fc_t2.weight", (int64_t)c.embed_out * c.embed_mid, &t)); p->eW2 = (float *)t->dev;
+    TRY(need(p, emb_prefix + "fc_t2.bias", c.embed_out, &t)); p->eb2 = (float *)t->dev;
+    float *wt;
+    TRY(folded(p, init_prefix, C, 1, 1, true, &wt, &p->init_b, st));
+    p->init_w = wt;   // [1][C]
+    return DWB_OK;
+}
+
+static int finalize_head(dwb_plan *p, int C, cudaStream_t st) {
+    TRY(folded(p, "final_conv.0.conv", C, C, 1, true, &p->Wf_t, &p->bf, st));
+    const Tensor *t;
+    TRY(need(p, "final_conv.2.conv.weight", C, &t)); p->wz = (float *)t->dev;
+    TRY(scalar_of(p, "final_conv.2.conv.bias", &p->bz, st));
+    p->headC = C;
+    return DWB_OK;
+}
+
+// stack every block's fc_t weight/bias into one (Mtot, E_out) matrix
+static int stack_fc_t(dwb_plan *p, const std::vector<std::pair<std::string, int>> &blocks, cudaStream_t st) {
+    const int E = p->cfg.embed_out;
+    int tot = 0;
+    for (auto &b : blocks) tot += b.second;
+    p->Mtot = tot;
+    void *W, *bb;
+    TRY(dev_alloc(p, (size_t)tot * E * sizeof(float), &W));
+    TRY(dev_alloc(p, (size_t)tot * sizeof(float), &bb));
+    int off = 0;
+    for (auto &b : blocks) {
+        const Tensor *w, *bi;
+        TRY(need(p, b.first + "fc_t.weight", (int64_t)b.second * E, &w));
+        TRY(need(p, b.first + "fc_t.bias", b.second, &bi));
+        DWB_CUDA(cudaMemcpyAsync((float *)W + (size_t)off * E, w->dev, (size_t)b.second * E * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+        DWB_CUDA(cudaMemcpyAsync((float *)bb + off, bi->dev, (size_t)b.second * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        off += b.second;
+    }
+    p->Wt_all = (float *)W;
+    p->bt_all = (float *)bb;
+    return DWB_OK;
+}
+
+static int finalize_sashimi(dwb_plan *p, cudaStream_t st) {
+    const dwb_config &c = p->cfg;
+    DWB_REQUIRE(c.n_pool >= 0 && c.n_pool <= DWB_MAX_POOL, DWB_ERR_INVALID, "n_pool=%d out of range", c.n_pool);
+    DWB_REQUIRE(c.expand >= 1 && c.ff >= 1 && c.d_model >= 1 && c.L >= 2, DWB_ERR_INVALID, "bad sashimi config");
+    TRY(build_sashimi_ops(p));
+    TRY(finalize_common(p, "", "init_conv.0.conv", c.d_model, st));
+    TRY(scalar_of(p, "norm.m", &p->norm_m, st));
+    TRY(scalar_of(p, "norm.s", &p->norm_s, st));
+    TRY(finalize_head(p, c.d_model, st));
+
+    const int N = c.d_state_half;
+    std::vector<std::pair<std::string, int>> fc;
+    size_t max_khat = 0, max_k64 = 0;
+    for (auto &o : p->ops)
+        if (o.kind == OP_BLOCK) {
+            max_khat = std::max(max_khat, (size_t)2 * o.H * (o.l / 2 + 1) * 2);
+            max_k64 = std::max(max_k64, (size_t)2 * o.H * o.l);
+        }
+    double *khat = nullptr, *k64 = nullptr;
+    DWB_CUDA(cudaMalloc(&khat, max_khat * sizeof(double)));
+    cudaError_t e = cudaMalloc(&k64, max_k64 * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(khat); return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
+    int rc = DWB_OK;
+    int part_off = 0;
+    int64_t cond_off = 0;
+    for (auto &o : p->ops) {
+        if (rc != DWB_OK) break;
+        auto body = [&]() -> int {
+            if (o.kind == OP_BLOCK) {
+                const std::string k = o.prefix + "layer.kernel.kernel.";
+                const int H = o.H, l = o.l;
+                const Tensor *C, *B, *P, *iwr, *wim, *ldt, *D;
+                TRY(need(p, k + "C", (int64_t)2 * H * N * 2, &C));
+                TRY(need(p, k + "B", (int64_t)H * N * 2, &B));
+                TRY(need(p, k + "P", (int64_t)H * N * 2, &P));
+                TRY(need(p, k + "inv_w_real", (int64_t)H * N, &iwr));
+                TRY(need(p, k + "w_imag", (int64_t)H * N, &wim));
+                TRY(need(p, k + "log_dt", H, &ldt));
+                TRY(need(p, o.prefix + "layer.D", H, &D));
+                if (const Tensor *Lt = find(p, k + "L")) {
+                    long long Lv = 0;
+                    DWB_REQUIRE(Lt->dtype == DWB_I64 && Lt->numel() == 1, DWB_ERR_INVALID, "`%sL` must be a scalar int64", k.c_str());
+                    DWB_CUDA(cudaMemcpyAsync(&Lv, Lt->dev, 8, cudaMemcpyDeviceToHost, st));
+                    DWB_CUDA(cudaStreamSynchronize(st));
+                    DWB_REQUIRE(Lv == l, DWB_ERR_STATE,
+                                "`%sL` is %lld but the stage length is %d: apply the one-off C rewrite "
+                                "(models/s4.py:525-551) on the host before loading", k.c_str(), Lv, l);
+                }
+                const Tensor *om = find(p, "nodes." + std::to_string(l));
+                if (om) DWB_REQUIRE(om->numel() == (int64_t)(l / 2 + 1) * 2, DWB_ERR_INVALID, "nodes.%d has wrong size", l);
+                void *k32, *kf;
+                TRY(dev_alloc(p, (size_t)2 * H * l * sizeof(float), &k32));
+                const int lg = fft_log2m_for(l);
+                DWB_REQUIRE(lg > 0, DWB_ERR_UNSUPPORTED, "stage length %d exceeds the in-shared-memory FFT (max %d)", l, 1 << FFT_MAX_LOG2M);
+                TRY(dev_alloc(p, (size_t)H * ((1 << lg) + 1) * 2 * sizeof(float), &kf));
+                TRY(s4_generate((const float *)C->dev, (const float *)B->dev, (const float *)P->dev, (const float *)iwr->dev,
+                                (const float *)wim->dev, (const float *)ldt->dev, om ? (const float *)om->dev : nullptr, H, N, l,
+                                khat, k64, (float *)k32, st, &p->launches));
+                TRY(fftconv_prepare_f64(k64, (const float *)D->dev, H, l, (float *)kf, st));
+                p->launches += 1;
+                const float2 *tw, *twp;
+                TRY(fft_twiddles(lg, st, &tw, &twp));
+                o.k32 = (float *)k32; o.kf = (float *)kf;
+                TRY(scalar_of(p, o.prefix + "norm1.m", &o.ln1_m, st));
+                TRY(scalar_of(p, o.prefix + "norm1.s", &o.ln1_s, st));
+                TRY(scalar_of(p, o.prefix + "norm2.m", &o.ln2_m, st));
+                TRY(scalar_of(p, o.prefix + "norm2.s", &o.ln2_s, st));
+                o.F = c.ff * H;
+                TRY(folded(p, o.prefix + "layer.output_linear.0", 2 * H, H, 1, false, &o.Wo_t, &o.bo, st));
+                TRY(folded(p, o.prefix + "ff.ff.0.conv", o.F, H, 1, true, &o.W1_t, &o.b1, st));
+                TRY(folded(p, o.prefix + "ff.ff.2.conv", H, o.F, 1, true, &o.W2_t, &o.b2, st));
+                o.part_off = part_off; part_off += H;
+                o.cond_off = cond_off; cond_off += (int64_t)H * l;
+                fc.push_back({o.prefix, H});
+            } else if (o.kind == OP_DOWN) {
+                TRY(folded(p, o.prefix + "linear.conv", o.Ho, o.H * o.s, 1, true, &o.Wp_t, &o.bp, st));
+            } else {
+                TRY(folded(p, o.prefix + "linear.conv", o.Ho * o.s, o.H, 1, true, &o.Wp_t, &o.bp, st));
+            }
+            return DWB_OK;
+        };
+        rc = body();
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(khat);
+    cudaFree(k64);
+    if (rc != DWB_OK) return rc;
+    p->cond_total = cond_off;
+    TRY(stack_fc_t(p, fc, st));
+    return DWB_OK;
+}
+
+static int finalize_wavenet(dwb_plan *p, cudaStream_t st) {
+    const dwb_config &c = p->cfg;
+    const int C = c.res_channels, S = c.skip_channels, N = c.num_res_layers;
+    DWB_REQUIRE(C >= 1 && S >= 1 && N >= 1 && c.dilation_cycle >= 1, DWB_ERR_INVALID, "bad wavenet config");
+    TRY(finalize_common(p, "residual_layer.", "init_conv.0.conv", C, st));
+    TRY(finalize_head(p, S, st));
+    std::vector<std::pair<std::string, int>> fc;
+    p->wl.clear();
+    int64_t cond_off = 0;
+    for (int n = 0; n < N; ++n) {
+        const std::string pre = "residual_layer.residual_blocks." + std::to_string(n) + ".";
+        WaveLayer w{};
+        w.dilation = 1 << (n % c.dilation_cycle);
+        TRY(folded(p, pre + "dilated_conv_layer.conv", 2 * C, C, 3, true, &w.Wd_t, &w.bd, st));
+        TRY(folded(p, pre + "res_conv", C, C, 1, true, &w.Wr_t, &w.br, st));
+        TRY(folded(p, pre + "skip_conv", S, C, 1, true, &w.Ws_t, &w.bs, st));
+        w.part_off = n * C;
+        w.cond_off = cond_off;
+        p->wl.push_back(w);
+        fc.push_back({pre, C});
+    }
+    TRY(stack_fc_t(p, fc, st));
+    return DWB_OK;
+}
+
+static int ensure_workspace(dwb_plan *p, int B, int L) {
+    const dwb_config &c = p->cfg;
+    const bool sash = c.model == DWB_MODEL_SASHIMI;
+    if (p->ws_B == B && p->ws_L == L) return DWB_OK;
+    DWB_CUDA(cudaDeviceSynchronize());
+    for (void *d : p->ws_owned) cudaFree(d);
+    p->ws_owned.clear();
+    p->bufs.clear();
+    p->stat_bufs.clear();
+    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    void *d;
+    if (sash) {
+        const size_t act = (size_t)B * c.d_model * L * sizeof(float);   // H*l never exceeds d_model*L when expand <= pool
+        size_t maxact = act;
+        for (auto &o : p->ops) {
+            maxact = std::max(maxact, (size_t)B * o.H * o.l * sizeof(float));
+            if (o.kind != OP_BLOCK) maxact = std::max(maxact, (size_t)B * o.Ho * (o.kind == OP_DOWN ? o.l / o.s : o.l * o.s) * sizeof(float));
+        }
+        for (int i = 0; i < p->n_bufs; ++i) {
+            TRY(dev_alloc(p, maxact, &d, true)); p->bufs.push_back((float *)d);
+            TRY(dev_alloc(p, (size_t)B * L * 2 * sizeof(float), &d, true)); p->stat_bufs.push_back((float *)d);
+        }
+        TRY(dev_alloc(p, maxact, &d, true)); p->g_buf = (float *)d;
+    } else {
+        for (int i = 0; i < 2; ++i) {
+            TRY(dev_alloc(p, (size_t)B * c.res_channels * L * sizeof(float), &d, true));
+            p->bufs.push_back((float *)d);
+        }
+        TRY(dev_alloc(p, (size_t)B * c.skip_channels * L * sizeof(float), &d, true)); p->skip_acc = (float *)d;
+    }
+    TRY(dev_alloc(p, (size_t)B * c.embed_out * sizeof(float), &d, true)); p->emb_buf = (float *)d;
+    TRY(dev_alloc(p, (size_t)B * p->Mtot * sizeof(float), &d, true)); p->part_buf = (float *)d;
+    p->ws_B = B;
+    p->ws_L = L;
+    return DWB_OK;
+}
+
+struct StepUpdate {           // fused DDPM update in the head, or plain eps
+    const float *x = nullptr, *noise = nullptr;
+    float c1 = 0, sqrt_alpha = 1, sigma = 0;
+};
+
+// one network evaluation; part = (rows, Mtot) fc_t outputs with batch stride psb (0 = shared row)
+static int run_network(dwb_plan *p, const float *x, const float *part, long long psb, const float *cond, int cond_batch,
+                       float *out, const StepUpdate *upd, int B, int L, cudaStream_t st) {
+    const dwb_config &c = p->cfg;
+    HeadArgs h{};
+    if (c.model == DWB_MODEL_SASHIMI) {
+        TRY(init_conv_launch(x, p->init_w, p->init_b, B, c.d_model, L, p->bufs[0], p->stat_bufs[0], st));
+        p->launches += 1;
+        int last = 0;
+        for (auto &o : p->ops) {
+            if (o.kind == OP_BLOCK) {
+                TRY(fftconv_launch(p->bufs[o.in_buf], p->stat_bufs[o.in_buf], part + o.part_off, psb, o.ln1_m, o.ln1_s,
+                                   o.kf, p->g_buf, B, o.H, o.l, st));
+                MixArgs a{};
+                a.g = p->g_buf; a.x = p->bufs[o.in_buf];
+                a.skip = o.skip_buf >= 0 ? p->bufs[o.skip_buf] : nullptr;
+                a.cond = cond ? cond + (size_t)cond_batch * o.cond_off : nullptr;
+                a.cond_stride_b = cond_batch > 1 ? 1 : 0;
+                a.Wo_t = o.Wo_t; a.bo = o.bo; a.W1_t = o.W1_t; a.b1 = o.b1; a.W2_t = o.W2_t; a.b2 = o.b2;
+                a.ln2_m = o.ln2_m; a.ln2_s = o.ln2_s;
+                a.out = p->bufs[o.out_buf]; a.stats_out = p->stat_bufs[o.out_buf];
+                a.H = o.H; a.F = o.F; a.l = o.l;
+                TRY(mix_launch(a, B, st));
+                p->launches += 2;
+            } else {
+                PoolArgs a{};
+                a.x = p->bufs[o.in_buf];
+                a.skip = o.skip_buf >= 0 ? p->bufs[o.skip_buf] : nullptr;
+                a.W_t = o.Wp_t; a.bias = o.bp;
+                a.out = p->bufs[o.out_buf]; a.stats_out = p->stat_bufs[o.out_buf];
+                a.Hi = o.H; a.Ho = o.Ho; a.s = o.s; a.li = o.l;
+                TRY(o.kind == OP_DOWN ? down_pool_launch(a, B, st) : up_pool_launch(a, B, st));
+                p->launches += 1;
+            }
+            last = o.out_buf;
+        }
+        h.x = p->bufs[last]; h.stats = p->stat_bufs[last];
+        h.ln_m = p->norm_m; h.ln_s = p->norm_s; h.prescale = 1.f;
+        h.C = c.d_model;
+    } else {
+        const int C = c.res_channels, S = c.skip_channels, N = c.num_res_layers;
+        TRY(init_conv_launch(x, p->init_w, p->init_b, B, C, L, p->bufs[0], nullptr, st));
+        p->launches += 1;
+        int cur = 0;
+        for (int n = 0; n < N; ++n) {
+            const WaveLayer &w = p->wl[n];
+            WaveBlockArgs a{};
+            a.h = p->bufs[cur]; a.h_out = p->bufs[cur ^ 1];
+            a.part_t = part + w.part_off; a.part_stride_b = psb;
+            a.cond = cond ? cond + (size_t)cond_batch * n * 2 * C * L : nullptr;
+            a.cond_stride_b = cond_batch > 1 ? 1 : 0;
+            a.Wd_t = w.Wd_t; a.bd = w.bd; a.Wr_t = w.Wr_t; a.br = w.br; a.Ws_t = w.Ws_t; a.bs = w.bs;
+            a.skip = p->skip_acc; a.first = n == 0;
+            a.C = C; a.S = S; a.L = L; a.dilation = w.dilation;
+            TRY(wave_block_launch(a, B, st));
+            p->launches += 1;
+            cur ^= 1;
+        }
+        h.x = p->skip_acc; h.stats = nullptr;
+        h.prescale = sqrtf(1.0f / (float)N);
+        h.C = S;
+    }
+    h.Wf_t = p->Wf_t; h.bf = p->bf; h.wz = p->wz; h.bz = p->bz;
+    h.out = out; h.l = L;
+    if (upd) { h.upd_x = upd->x; h.noise = upd->noise; h.c1 = upd->c1; h.sqrt_alpha = upd->sqrt_alpha; h.sigma = upd->sigma; }
+    TRY(head_launch(h, B, st));
+    p->launches += 1;
+    return DWB_OK;
+}
+
+static int check_run(dwb_plan *p, int B, int L, const float *cond, int cond_batch) {
+    DWB_REQUIRE(p && p->finalized, DWB_ERR_STATE, "plan is not finalized");
+    DWB_REQUIRE(B >= 1 && L >= 1, DWB_ERR_INVALID, "bad sizes B=%d L=%d", B, L);
+    DWB_REQUIRE(B <= 65535, DWB_ERR_UNSUPPORTED, "batch %d > 65535", B);
+    if (p->cfg.model == DWB_MODEL_SASHIMI)
+        DWB_REQUIRE(L == p->cfg.L, DWB_ERR_UNSUPPORTED,
+                    "sequence length %d differs from the configured L=%d (kernel truncation / overlap-save not built yet)", L, p->cfg.L);
+    if (cond) {
+        DWB_REQUIRE(!p->cfg.unconditional, DWB_ERR_INVALID, "conditioning passed to an unconditional model");
+        DWB_REQUIRE(cond_batch == 1 || cond_batch == B, DWB_ERR_INVALID, "cond_batch must be 1 or B");
+    } else {
+        DWB_REQUIRE(p->cfg.unconditional, DWB_ERR_INVALID, "conditional model called without conditioning features");
+    }
+    return DWB_OK;
+}
+
+}  // namespace dwb
+
+// =========================================================================================
+extern "C" {
+
+int dwb_version(void) { return DWB_VERSION; }
+const char *dwb_last_error(void) { return g_err; }
+
+int dwb_device_count(int *count) {
+    DWB_REQUIRE(count, DWB_ERR_INVALID, "null");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__); }
+    return DWB_OK;
+}
+
+int dwb_plan_create(const dwb_config *cfg, int device, dwb_plan **out) {
+    DWB_REQUIRE(cfg && out, DWB_ERR_INVALID, "dwb_plan_create: null pointer");
+    DWB_REQUIRE(cfg->model == DWB_MODEL_WAVENET || cfg->model == DWB_MODEL_SASHIMI, DWB_ERR_INVALID, "unknown model %d", cfg->model);
+    DWB_REQUIRE(cfg->embed_in >= 4 && cfg->embed_in % 2 == 0 && cfg->embed_mid >= 1 && cfg->embed_out >= 1, DWB_ERR_INVALID,
+                "bad embedding dims %d/%d/%d", cfg->embed_in, cfg->embed_mid, cfg->embed_out);
+    int n = 0;
+    TRY(dwb_device_count(&n));
+    DWB_REQUIRE(n > 0, DWB_ERR_CUDA, "no CUDA device: libdwb has no CPU fallback");
+    DWB_REQUIRE(device >= 0 && device < n, DWB_ERR_INVALID, "device %d out of range (have %d)", device, n);
+    DWB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DWB_CUDA(cudaGetDeviceProperties(&prop, device));
+    DWB_REQUIRE(prop.major == 10, DWB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libdwb is built for sm_100a only", device, prop.major, prop.minor);
+    dwb_plan *p = new dwb_plan();
+    p->cfg = *cfg;
+    p->device = device;
+    *out = p;
+    return DWB_OK;
+}
+
+int dwb_plan_destroy(dwb_plan *p) {
+    if (!p) return DWB_OK;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    for (auto &kv : p->tensors) cudaFree(kv.second.dev);
+    for (void *d : p->owned) cudaFree(d);
+    for (void *d : p->ws_owned) cudaFree(d);
+    cudaFree(p->table_emb); cudaFree(p->table_part); cudaFree(p->table_t);
+    delete p;
+    return DWB_OK;
+}
+
+int dwb_plan_set_tensor(dwb_plan *p, const char *name, const void *data, int dtype, const int64_t *shape, int ndim,
+                        int on_device, void *stream) {
+    DWB_REQUIRE(p && name && data, DWB_ERR_INVALID, "dwb_plan_set_tensor: null pointer");
+    DWB_REQUIRE(!p->finalized, DWB_ERR_STATE, "plan already finalized");
+    DWB_REQUIRE(dtype == DWB_F32 || dtype == DWB_I64, DWB_ERR_INVALID, "`%s`: unsupported dtype %d", name, dtype);
+    DWB_REQUIRE(ndim >= 0 && ndim <= 8, DWB_ERR_INVALID, "`%s`: bad ndim %d", name, ndim);
+    DWB_CUDA(cudaSetDevice(p->device));
+    Tensor t;
+    t.dtype = dtype;
+    for (int i = 0; i < ndim; ++i) {
+        DWB_REQUIRE(shape[i] >= 0, DWB_ERR_INVALID, "`%s`: negative dim", name);
+        t.shape.push_back(shape[i]);
+    }
+    t.bytes = (size_t)t.numel() * (dtype == DWB_F32 ? 4 : 8);
+    DWB_CUDA(cudaMalloc(&t.dev, t.bytes ? t.bytes : 4));
+    cudaError_t e = cudaMemcpyAsync(t.dev, data, t.bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                    (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) { cudaFree(t.dev); return cuda_fail(e, "copy tensor", __FILE__, __LINE__); }
+    auto it = p->tensors.find(name);
+    if (it != p->tensors.end()) { cudaFree(it->second.dev); p->tensors.erase(it); }
+    p->tensors[name] = t;
+    return DWB_OK;
+}
+
+int dwb_plan_finalize(dwb_plan *p, void *stream) {
+    DWB_REQUIRE(p, DWB_ERR_INVALID, "null plan");
+    DWB_REQUIRE(!p->finalized, DWB_ERR_STATE, "plan already finalized");
+    DWB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = p->cfg.model == DWB_MODEL_SASHIMI ? finalize_sashimi(p, st) : finalize_wavenet(p, st);
+    if (rc != DWB_OK) return rc;
+    DWB_CUDA(cudaStreamSynchronize(st));
+    p->finalized = true;
+    return DWB_OK;
+}
+
+int dwb_forward(dwb_plan *p, const float *x, const float *t, const float *cond, int cond_batch, float *eps, int B, int L,
+                void *stream) {
+    DWB_REQUIRE(p && x && t && eps, DWB_ERR_INVALID, "dwb_forward: null pointer");
+    TRY(check_run(p, B, L, cond, cond_batch));
+    DWB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ensure_workspace(p, B, L));
+    const dwb_config &c = p->cfg;
+    TRY(embed_launch(t, B, c.embed_in, c.embed_mid, c.embed_out, p->eW1, p->eb1, p->eW2, p->eb2, p->Wt_all, p->bt_all,
+                     p->Mtot, p->emb_buf, p->part_buf, st));
+    p->launches += 2;
+    return run_network(p, x, p->part_buf, p->Mtot, cond, cond_batch, eps, nullptr, B, L, st);
+}
+
+int dwb_sample(dwb_plan *p, const float *x_T, const float *noise, const float *cond, int cond_batch,
+               const float *coef_host, int T, float *out, int B, int L, int use_graph, void *stream) {
+    DWB_REQUIRE(p && x_T && out && coef_host, DWB_ERR_INVALID, "dwb_sample: null pointer");
+    DWB_REQUIRE(T >= 1, DWB_ERR_INVALID, "T=%d", T);
+    DWB_REQUIRE(noise || T == 1, DWB_ERR_INVALID, "noise is required for T > 1");
+    TRY(check_run(p, B, L, cond, cond_batch));
+    DWB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ensure_workspace(p, B, L));
+    const dwb_config &c = p->cfg;
+
+    GraphKey key;
+    key.xT = x_T; key.noise = noise; key.cond = cond; key.out = out; key.cond_batch = cond_batch;
+    key.T = T; key.B = B; key.L = L;
+    key.coef.assign(coef_host, coef_host + 3 * T);
+    if (use_graph && p->graph_exec && key == p->graph_key) {
+        DWB_CUDA(cudaGraphLaunch(p->graph_exec, st));
+        p->launches += p->graph_nodes;
+        return DWB_OK;
+    }
+
+    // per-step t-embedding table: same step for the whole batch (generate.py:50)
+    if (p->table_T != T) {
+        DWB_CUDA(cudaStreamSynchronize(st));
+        if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+        cudaFree(p->table_emb); cudaFree(p->table_part); cudaFree(p->table_t);
+        p->table_emb = p->table_part = p->table_t = nullptr;
+        p->table_T = 0;
+        DWB_CUDA(cudaMalloc(&p->table_emb, (size_t)T * c.embed_out * sizeof(float)));
+        DWB_CUDA(cudaMalloc(&p->table_part, (size_t)T * p->Mtot * sizeof(float)));
+        DWB_CUDA(cudaMalloc(&p->table_t, (size_t)T * sizeof(float)));
+        std::vector<float> ts(T);
+        for (int i = 0; i < T; ++i) ts[i] = (float)i;
+        DWB_CUDA(cudaMemcpyAsync(p->table_t, ts.data(), T * sizeof(float), cudaMemcpyHostToDevice, st));
+        DWB_CUDA(cudaStreamSynchronize(st));
+        TRY(embed_launch(p->table_t, T, c.embed_in, c.embed_mid, c.embed_out, p->eW1, p->eb1, p->eW2, p->eb2, p->Wt_all,
+                         p->bt_all, p->Mtot, p->table_emb, p->table_part, st));
+        p->launches += 2;
+        p->table_T = T;
+    }
+    const size_t BL = (size_t)B * L;
+    auto body = [&]() -> int {
+        DWB_CUDA(cudaMemcpyAsync(out, x_T, BL * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        for (int t = T - 1; t >= 0; --t) {
+            StepUpdate u;
+            u.x = out;
+            u.c1 = coef_host[t]; u.sqrt_alpha = coef_host[T + t]; u.sigma = coef_host[2 * T + t];
+            u.noise = t > 0 ? noise + (size_t)(T - 1 - t) * BL : nullptr;
+            TRY(run_network(p, out, p->table_part + (size_t)t * p->Mtot, 0, cond, cond_batch, out, &u, B, L, st));
+        }
+        return DWB_OK;
+    };
+    if (!use_graph) return body();
+
+    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    const int64_t before = p->launches;
+    DWB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = body();
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != DWB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+    p->graph_nodes = p->launches - before;
+    p->launches = before;
+    e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { p->graph_exec = nullptr; return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+    p->graph_key = key;
+    DWB_CUDA(cudaGraphLaunch(p->graph_exec, st));
+    p->launches += p->graph_nodes;
+    return DWB_OK;
+}
+
+int dwb_plan_cond_layout(dwb_plan *p, int L, int *n_blocks, int *channels, int *lengths, int64_t *offsets) {
+    DWB_REQUIRE(p && p->finalized && n_blocks, DWB_ERR_STATE, "plan is not finalized");
+    int n = 0;
+    if (p->cfg.model == DWB_MODEL_SASHIMI) {
+        for (auto &o : p->ops)
+            if (o.kind == OP_BLOCK) {
+                if (channels) { channels[n] = o.H; lengths[n] = o.l; offsets[n] = o.cond_off; }
+                ++n;
+            }
+    } else {
+        for (size_t i = 0; i < p->wl.size(); ++i) {
+            if (channels) { channels[n] = 2 * p->cfg.res_channels; lengths[n] = L; offsets[n] = (int64_t)i * 2 * p->cfg.res_channels * L; }
+            ++n;
+        }
+    }
+    *n_blocks = n;
+    return DWB_OK;
+}
+
+int dwb_plan_launch_count(dwb_plan *p, int64_t *count) {
+    DWB_REQUIRE(p && count, DWB_ERR_INVALID, "null");
+    *count = p->launches;
+    return DWB_OK;
+}
+
+int dwb_plan_s4_blocks(dwb_plan *p, int *n_blocks) {
+    DWB_REQUIRE(p && p->finalized && n_blocks, DWB_ERR_STATE, "plan is not finalized");
+    int n = 0;
+    for (auto &o : p->ops) n += o.kind == OP_BLOCK;
+    *n_blocks = n;
+    return DWB_OK;
+}
+
+int dwb_plan_s4_kernel(dwb_plan *p, int block, float *k_out, int64_t capacity, int *H, int *l) {
+    DWB_REQUIRE(p && p->finalized, DWB_ERR_STATE, "plan is not finalized");
+    int n = 0;
+    for (auto &o : p->ops)
+        if (o.kind == OP_BLOCK) {
+            if (n == block) {
+                if (H) *H = o.H;
+                if (l) *l = o.l;
+                if (k_out) {
+                    DWB_REQUIRE(capacity >= (int64_t)2 * o.H * o.l, DWB_ERR_INVALID, "k_out too small");
+                    DWB_CUDA(cudaMemcpy(k_out, o.k32, (size_t)2 * o.H * o.l * sizeof(float), cudaMemcpyDeviceToDevice));
+                }
+                return DWB_OK;
+            }
+            ++n;
+        }
+    set_error("block %d out of range", block);
+    return DWB_ERR_INVALID;
+}
+
+int dwb_plan_work(dwb_plan *p, int L, double *bytes, double *flops) {
+    DWB_REQUIRE(p && p->finalized && bytes && flops, DWB_ERR_STATE, "plan is not finalized");
+    const dwb_config &c = p->cfg;
+    double by = 0, fl = 0;
+    if (c.model == DWB_MODEL_SASHIMI) {
+        // two passes per block (read x, write g | read g and x, write x') = 5*4*H*l,
+        // UNet skip reads, pool in/out(+skip), init/head I/O.  GEMM flops 12 H^2 l (ff = 2) + FFT flops.
+        by += 4.0 * L + 4.0 * c.d_model * L;
+        for (auto &o : p->ops) {
+            if (o.kind == OP_BLOCK) {
+                const double Hl = (double)o.H * o.l, n = 2.0 * (1 << fft_log2m_for(o.l));
+                by += 20.0 * Hl + (o.skip_buf >= 0 ? 4.0 * Hl : 0.0);
+                fl += (4.0 + 4.0 * c.ff) * o.H * Hl + 2.0 * 2.5 * n * log2(n) * o.H + 6.0 * (n / 2 + 1) * o.H;
+            } else {
+                const double in = (double)o.H * o.l, outn = (double)o.Ho * (o.kind == OP_DOWN ? o.l / o.s : o.l * o.s);
+                by += 4.0 * (in + outn + (o.skip_buf >= 0 ? outn : 0.0));
+                fl += 2.0 * (o.kind == OP_DOWN ? (double)o.H * o.s * o.Ho * (o.l / o.s) : (double)o.H * o.Ho * o.s * o.l);
+            }
+        }
+        by += 4.0 * c.d_model * L + 4.0 * L;
+        fl += 2.0 * c.d_model * c.d_model * L + 2.0 * c.d_model * L + 2.0 * c.d_model * L;
+    } else {
+        const double C = c.res_channels, S = c.skip_channels, N = c.num_res_layers;
+        fl = N * (12.0 * C * C * L + 2.0 * C * C * L + 2.0 * C * S * L) + 2.0 * S * S * L + 2.0 * S * L + 2.0 * C * L;
+        by = N * 4.0 * (2.0 * C + 2.0 * S) * L + 4.0 * L * (2.0 + C + S);
+    }
+    *bytes = by;
+    *flops = fl;
+    return DWB_OK;
+}
+
+}  // extern "C"

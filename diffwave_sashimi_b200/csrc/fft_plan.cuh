@@ -1,0 +1,62 @@
+// Radix plan shared by the per-step FFT convolution (fftconv.cu) and by the one-off spectrum
+// builder (s4_kernelgen.cu), which must agree on the digit-reversed order of the spectrum.
+//
+// The length-n real convolution is done as one M = n/2 point complex FFT per (batch, channel)
+// row, in place in shared memory: decimation-in-frequency forward passes (natural -> digit
+// reversed), the real-FFT untangle + spectrum product + re-tangle directly in digit-reversed
+// order, then decimation-in-time inverse passes (digit reversed -> natural).  No reordering
+// pass ever runs; the cached spectrum is simply stored in the order the forward passes leave.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dwb {
+
+constexpr int FFT_MIN_LOG2M = 4;
+constexpr int FFT_MAX_LOG2M = 14;   // M = 16384 complex = 128 KB (+pad) of shared memory
+constexpr int FFT_MAX_PASSES = 4;
+
+// log2 of the radix of pass i (pass 0 has span M); zero-terminated.  16s first, remainder last.
+__host__ __device__ constexpr int fft_radix_log2(int log2M, int pass) {
+    // number of radix-16 passes, then one pass of the remaining bits
+    return (pass < log2M / 4) ? 4 : ((pass == log2M / 4) ? (log2M % 4) : 0);
+}
+__host__ __device__ constexpr int fft_num_passes(int log2M) { return log2M / 4 + ((log2M % 4) ? 1 : 0); }
+
+// smallest supported M = 2^log2M with M >= l (so n = 2M >= 2l: no circular wrap); 0 if too long
+__host__ __device__ inline int fft_log2m_for(int l) {
+    for (int lg = FFT_MIN_LOG2M; lg <= FFT_MAX_LOG2M; ++lg)
+        if ((1 << lg) >= l) return lg;
+    return 0;
+}
+
+// slot in shared memory (before padding) where the forward passes leave X[k]:
+// k = q0 + R0 (q1 + R1 (q2 + ...)),  pos = q0 M/R0 + q1 M/(R0 R1) + ...
+__host__ __device__ inline int fft_pos(int k, int log2M) {
+    int pos = 0, shift = log2M;
+    const int np = fft_num_passes(log2M);
+    for (int p = 0; p < np; ++p) {
+        const int lr = fft_radix_log2(log2M, p);
+        shift -= lr;
+        pos |= (k & ((1 << lr) - 1)) << shift;
+        k >>= lr;
+    }
+    return pos;
+}
+// inverse map: which frequency sits in slot pos
+__host__ __device__ inline int fft_freq(int pos, int log2M) {
+    int k = 0, shift = log2M, kshift = 0;
+    const int np = fft_num_passes(log2M);
+    for (int p = 0; p < np; ++p) {
+        const int lr = fft_radix_log2(log2M, p);
+        shift -= lr;
+        k |= ((pos >> shift) & ((1 << lr) - 1)) << kshift;
+        kshift += lr;
+    }
+    return k;
+}
+
+// shared-memory padding: one float2 of slack per 16 so that the stride-16 and stride-1
+// passes (16 consecutive elements per thread) are bank-conflict free
+__host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 4); }
+
+}  // namespace dwb

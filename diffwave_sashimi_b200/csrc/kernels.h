@@ -1,0 +1,78 @@
+// Internal launch interfaces between the plan (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dwb {
+
+struct MixArgs {
+    const float *g, *x;            // (B,H,l) S4 activation output, block input
+    const float *skip;             // (B,H,l) UNet skip added to the block output, or null
+    const float *cond;             // (cond_batch,H,l) conditioning features, or null
+    int cond_stride_b;             // 0: broadcast over batch
+    const float *Wo_t, *bo;        // [H][2H], (2H)
+    const float *W1_t, *b1;        // [H][F],  (F)
+    const float *W2_t, *b2;        // [F][H],  (H)
+    float ln2_m, ln2_s;
+    float *out, *stats_out;        // (B,H,l), (B,l,2)
+    int H, F, l;
+};
+
+struct PoolArgs {
+    const float *x;                // (B,Hi,li)
+    const float *skip;             // up only: (B,Ho,li*s) or null
+    const float *W_t, *bias;       // down: [Hi*s][Ho]; up: [Hi][Ho*s]
+    float *out, *stats_out;
+    int Hi, Ho, s, li;
+};
+
+struct HeadArgs {
+    const float *x;                // (B,C,l)
+    const float *stats;            // (B,l,2) or null (no LN)
+    float ln_m, ln_s, prescale;
+    const float *Wf_t, *bf;        // [C][C], (C)
+    const float *wz;               // (C)
+    float bz;
+    // optional fused DDPM update: out = (upd_x - c1 eps)/sqrt_alpha (+ sigma noise)
+    const float *upd_x, *noise;
+    float c1, sqrt_alpha, sigma;
+    float *out;                    // (B,l)
+    int C, l;
+};
+
+struct WaveBlockArgs {
+    const float *h;                // (B,C,L) layer input
+    const float *part_t;           // (B,C) or (C): fc_t(emb) for this layer
+    long long part_stride_b;
+    const float *cond;             // (cond_batch,2C,L) or null
+    int cond_stride_b;
+    const float *Wd_t, *bd;        // [3C][2C] tap-major rows (t-d, t, t+d), (2C)
+    const float *Wr_t, *br;        // [C][C], (C)
+    const float *Ws_t, *bs;        // [C][S], (S)
+    float *h_out;                  // (B,C,L)
+    float *skip;                   // (B,S,L) accumulated in place
+    int first;                     // 1: skip is written, not accumulated
+    int C, S, L, dilation;
+};
+
+int fold_weight(const float *v, const float *g, int M, int Kin, int taps, float *out, cudaStream_t st);
+int embed_launch(const float *t, int rows, int E_in, int E_mid, int E_out, const float *W1, const float *b1,
+                 const float *W2, const float *b2, const float *Wt, const float *bt, int Mtot, float *emb, float *part,
+                 cudaStream_t st);
+int init_conv_launch(const float *x, const float *w, const float *bias, int B, int C, int l, float *out, float *stats,
+                     cudaStream_t st);
+int mix_launch(const MixArgs &a, int B, cudaStream_t st);
+int down_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
+int up_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
+int head_launch(const HeadArgs &a, int B, cudaStream_t st);
+int wave_block_launch(const WaveBlockArgs &a, int B, cudaStream_t st);
+
+int fftconv_launch(const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
+                   const float *kf, float *g, int B, int H, int l, cudaStream_t st);
+int fft_twiddles(int log2M, cudaStream_t st, const float2 **tw, const float2 **twpos);
+int s4_generate(const float *C, const float *Bp, const float *P, const float *inv_w_real, const float *w_imag,
+                const float *log_dt, const float *omega, int H, int N, int l, double *khat, double *k64, float *k32,
+                cudaStream_t st, int64_t *launches);
+int fftconv_prepare_f64(const double *k64, const float *D, int H, int l, float *kf, cudaStream_t st);
+
+}  // namespace dwb

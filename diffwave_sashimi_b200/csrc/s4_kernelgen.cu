@@ -1,0 +1,371 @@
+// S4 (NPLR, rank 1, bidirectional) convolution-kernel generation — once per weight load.
+//
+// Reference: models/s4.py:674-807 (SSKernelNPLR.forward) with the Cauchy sum of
+// extensions/cauchy/cauchy_cuda.cu:242-347, then models/s4.py:1391-1403 (two-sided kernel and
+// its spectrum).  The reference redoes all of this on every diffusion step; it depends only on
+// parameters, so the engine runs it at dwb_plan_finalize() and caches the spectrum.
+//
+// Design: everything here is input independent and off the per-step path, so it is evaluated
+// in fp64 straight from the stored fp32 parameters ("exact arithmetic is the target"):
+//   1. s4_khat_kernel   fused Cauchy + Woodbury + bilinear factor: one thread per (h, node),
+//                       the six (B|P)x(C0|C1|Q) products share the two reciprocals per state
+//                       and never touch memory -> writes 2H x (l/2+1) instead of 6H x (l/2+1).
+//   2. irdft_kernel     l-point inverse real DFT by direct summation with a rotating phasor
+//                       (l = 16000/4000/1000 is 2^a 5^3; exact table re-sync every 256 terms).
+//   3. kf_kernel        spectrum of the wrapped two-sided kernel at the power-of-two size used
+//                       by the per-step FFT convolution, with D folded in and the transform
+//                       scale absorbed; stored in the digit-reversed order of fftconv.cu.
+// Also here: the standalone complex64 Cauchy op that replaces cauchy_mult_sym_fwd.
+#include "common.cuh"
+#include "fft_plan.cuh"
+
+namespace dwb {
+
+struct cd {  // complex double
+    double x, y;
+};
+__device__ __forceinline__ cd operator+(cd a, cd b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cd operator-(cd a, cd b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cd operator*(cd a, cd b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cd operator*(cd a, double s) { return {a.x * s, a.y * s}; }
+__device__ __forceinline__ cd conj(cd a) { return {a.x, -a.y}; }
+__device__ __forceinline__ cd inv(cd a) {
+    double d = 1.0 / (a.x * a.x + a.y * a.y);
+    return {a.x * d, -a.y * d};
+}
+__device__ __forceinline__ cd operator/(cd a, cd b) { return a * inv(b); }
+
+// ---------------------------------------------------------------------------------------
+// 1. K^j[h, m] for j in {0,1}, nodes m = 0..l/2
+// ---------------------------------------------------------------------------------------
+constexpr int KHAT_THREADS = 128;
+
+__global__ void __launch_bounds__(KHAT_THREADS)
+s4_khat_kernel(const float *__restrict__ C, const float *__restrict__ Bp, const float *__restrict__ P,
+               const float *__restrict__ inv_w_real, const float *__restrict__ w_imag,
+               const float *__restrict__ log_dt, const float *__restrict__ omega /* (nk,2) or null */,
+               int H, int N, int l, double *__restrict__ khat /* (2,H,nk,2) */) {
+    extern __shared__ double sm[];
+    // per state n: lambda (2), then six products v (12)
+    double *lam = sm;            // N*2
+    double *vv = sm + 2 * N;     // N*12
+    const int h = blockIdx.y;
+    const int nk = l / 2 + 1;
+    const double dt = exp((double)log_dt[h]);
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const int i = h * N + n;
+        double wr = -exp((double)inv_w_real[i]), wi = (double)w_imag[i];
+        lam[2 * n] = wr * dt;
+        lam[2 * n + 1] = wi * dt;
+        cd b = {(double)Bp[2 * i], (double)Bp[2 * i + 1]};
+        cd p = {(double)P[2 * i], (double)P[2 * i + 1]};
+        cd c0 = {(double)C[2 * i], (double)C[2 * i + 1]};
+        cd c1 = {(double)C[2 * (H * N + i)], (double)C[2 * (H * N + i) + 1]};
+        cd q = conj(p);
+        cd pr[6] = {b * c0, b * c1, b * q, p * c0, p * c1, p * q};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            vv[12 * n + 2 * k] = pr[k].x;
+            vv[12 * n + 2 * k + 1] = pr[k].y;
+        }
+    }
+    __syncthreads();
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nk) return;
+    cd out0, out1;
+    const bool exact = (omega == nullptr);
+    if (exact && (l % 2 == 0) && m == l / 2) {
+        // omega = -1: z -> inf.  Limit of the whole expression is dt * Re sum_n B_n C^j_n.
+        double s0 = 0, s1 = 0;
+        for (int n = 0; n < N; ++n) {
+            s0 += vv[12 * n + 0];
+            s1 += vv[12 * n + 2];
+        }
+        out0 = {dt * s0, 0.0};
+        out1 = {dt * s1, 0.0};
+    } else {
+        cd om;
+        if (exact) {
+            double s, c;
+            sincospi(-2.0 * (double)m / (double)l, &s, &c);
+            om = {c, s};
+        } else {
+            om = {(double)omega[2 * m], (double)omega[2 * m + 1]};
+        }
+        const cd one = {1.0, 0.0};
+        const cd opw = one + om;                 // 1 + omega
+        const cd z = ((one - om) * 2.0) / opw;   // bilinear node
+        cd acc[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[k] = {0.0, 0.0};
+        for (int n = 0; n < N; ++n) {
+            cd la = {lam[2 * n], lam[2 * n + 1]};
+            cd r1 = inv(z - la);
+            cd r2 = inv(z - conj(la));
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                cd v = {vv[12 * n + 2 * k], vv[12 * n + 2 * k + 1]};
+                acc[k] = acc[k] + v * r1 + conj(v) * r2;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[k] = acc[k] * dt;
+        // Woodbury (rank 1): k = r00 - r01 r10 / (1 + r11); rows {B,P} x cols {C0,C1,Q}
+        const cd den = inv(one + acc[5]);
+        const cd f = (one * 2.0) / opw;
+        out0 = (acc[0] - acc[2] * acc[3] * den) * f;
+        out1 = (acc[1] - acc[2] * acc[4] * den) * f;
+    }
+    const size_t o0 = ((size_t)(0 * H + h) * nk + m) * 2, o1 = ((size_t)(1 * H + h) * nk + m) * 2;
+    khat[o0] = out0.x;
+    khat[o0 + 1] = out0.y;
+    khat[o1] = out1.x;
+    khat[o1 + 1] = out1.y;
+}
+
+// ---------------------------------------------------------------------------------------
+// 2. k[r, t] = irfft(khat[r, :], n = l)[t]      (rows r = 2H)
+// ---------------------------------------------------------------------------------------
+constexpr int DFT_THREADS = 128;
+constexpr int DFT_CHUNK = 256;   // phasor re-synchronised from sincospi every chunk
+
+__global__ void __launch_bounds__(DFT_THREADS)
+irdft_kernel(const double *__restrict__ khat /* (R,nk,2) */, int l, double *__restrict__ k64 /* (R,l) */,
+             float *__restrict__ k32 /* (R,l) or null */) {
+    __shared__ double sk[2 * DFT_CHUNK];
+    const int r = blockIdx.y;
+    const int nk = l / 2 + 1;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const double *row = khat + (size_t)r * nk * 2;
+    const int last = (l % 2 == 0) ? l / 2 : nk;   // terms 1..last-1 are doubled
+    double acc = 0.0;
+    double ws, wc;
+    sincospi(2.0 * (double)(t % l) / (double)l, &ws, &wc);   // e^{+2 pi i t / l}
+    for (int m0 = 1; m0 < last; m0 += DFT_CHUNK) {
+        const int cnt = min(DFT_CHUNK, last - m0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * cnt; i += blockDim.x) sk[i] = row[2 * m0 + i];
+        __syncthreads();
+        if (t < l) {
+            double ps, pc;
+            const long long ph = ((long long)m0 * (long long)t) % l;
+            sincospi(2.0 * (double)ph / (double)l, &ps, &pc);
+            for (int i = 0; i < cnt; ++i) {
+                acc += sk[2 * i] * pc - sk[2 * i + 1] * ps;
+                const double nc = pc * wc - ps * ws;
+                ps = pc * ws + ps * wc;
+                pc = nc;
+            }
+        }
+    }
+    if (t >= l) return;
+    double v = row[0] + 2.0 * acc;
+    if (l % 2 == 0) v += (t & 1) ? -row[2 * (l / 2)] : row[2 * (l / 2)];
+    v /= (double)l;
+    k64[(size_t)r * l + t] = v;
+    if (k32) k32[(size_t)r * l + t] = (float)v;
+}
+
+// ---------------------------------------------------------------------------------------
+// 3. spectrum of the wrapped two-sided kernel, in fftconv's layout
+//    kk[s] = k0[s] (s < l), kk[n - s] = k1[s-1] (s = 1..l);  K[f] = sum_j kk[j] e^{-2 pi i f j / n}
+//    stored value: (K[f] + D[h]) / (4 M), M = n/2, at slot fft_pos(f) for f < M, Nyquist at slot M.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(DFT_THREADS)
+kf_kernel(const T *__restrict__ k /* (2,H,l) */, const float *__restrict__ D /* (H) or null */, int H, int l,
+          int log2M, float *__restrict__ kf /* (H, M+1, 2) */) {
+    __shared__ double s0[DFT_CHUNK], s1[DFT_CHUNK];
+    const int h = blockIdx.y;
+    const int M = 1 << log2M, n = 2 * M;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;   // 0..M
+    const T *k0 = k + (size_t)h * l;
+    const T *k1 = k + (size_t)(H + h) * l;
+    double ar = 0.0, ai = 0.0;
+    double ws, wc;
+    sincospi(-2.0 * (double)(f % n) / (double)n, &ws, &wc);   // W = e^{-2 pi i f / n}
+    for (int j0 = 0; j0 < l; j0 += DFT_CHUNK) {
+        const int cnt = min(DFT_CHUNK, l - j0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            s0[i] = (double)k0[j0 + i];
+            s1[i] = (double)k1[j0 + i];
+        }
+        __syncthreads();
+        if (f <= M) {
+            // causal part: k0[s] W^{f s}, s = j0 + i ; anti-causal: k1[s-1] W^{-f s}, s = j0 + i + 1
+            double ps, pc, qs, qc;
+            const long long ph = ((long long)f * (long long)j0) % n;
+            sincospi(-2.0 * (double)ph / (double)n, &ps, &pc);           // W^{f j0}
+            const long long qh = ((long long)f * (long long)(j0 + 1)) % n;
+            sincospi(2.0 * (double)qh / (double)n, &qs, &qc);            // W^{-f (j0+1)}
+            for (int i = 0; i < cnt; ++i) {
+                ar += s0[i] * pc + s1[i] * qc;
+                ai += s0[i] * ps + s1[i] * qs;
+                double nc = pc * wc - ps * ws;
+                ps = pc * ws + ps * wc;
+                pc = nc;
+                nc = qc * wc + qs * ws;       // multiply by conj(W)
+                qs = qs * wc - qc * ws;
+                qc = nc;
+            }
+        }
+    }
+    if (f > M) return;
+    const double scale = 1.0 / (4.0 * (double)M);
+    const double d = D ? (double)D[h] : 0.0;
+    const int slot = (f == M) ? M : fft_pos(f, log2M);
+    float *o = kf + ((size_t)h * (M + 1) + slot) * 2;
+    o[0] = (float)((ar + d) * scale);
+    o[1] = (float)(ai * scale);
+}
+
+// ---------------------------------------------------------------------------------------
+// standalone complex64 Cauchy op (drop-in for cauchy_mult_sym_fwd)
+// ---------------------------------------------------------------------------------------
+constexpr int CAUCHY_THREADS = 256;
+constexpr int CAUCHY_NCHUNK = 256;
+
+// LPL = lanes cooperating on one output l (split of the state dimension, warp-shuffle reduced)
+template <int LPL>
+__global__ void __launch_bounds__(CAUCHY_THREADS)
+cauchy_sym_fwd_kernel(const float2 *__restrict__ v, const float2 *__restrict__ z, const float2 *__restrict__ w,
+                      float2 *__restrict__ out, int N, int L) {
+    __shared__ float2 sv[CAUCHY_NCHUNK], sw[CAUCHY_NCHUNK];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x % LPL;
+    const int li = blockIdx.x * (CAUCHY_THREADS / LPL) + threadIdx.x / LPL;
+    const bool live = li < L;
+    const float2 zz = live ? z[li] : make_float2(0.f, 0.f);
+    float ar = 0.f, ai = 0.f;
+    for (int n0 = 0; n0 < N; n0 += CAUCHY_NCHUNK) {
+        const int cnt = min(CAUCHY_NCHUNK, N - n0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += CAUCHY_THREADS) {
+            sv[i] = v[(size_t)b * N + n0 + i];
+            sw[i] = w[(size_t)b * N + n0 + i];
+        }
+        __syncthreads();
+        if (live) {
+            for (int i = lane; i < cnt; i += LPL) {
+                const float2 vn = sv[i], wn = sw[i];
+                // v/(z-w) + conj(v)/(z-conj(w)); both denominators share (z.x - w.x)
+                const float dx = zz.x - wn.x;
+                const float dy1 = zz.y - wn.y, dy2 = zz.y + wn.y;
+                const float i1 = 1.0f / (dx * dx + dy1 * dy1), i2 = 1.0f / (dx * dx + dy2 * dy2);
+                // v * conj(d1) * i1 ; conj(v) * conj(d2) * i2
+                ar += (vn.x * dx + vn.y * dy1) * i1 + (vn.x * dx - vn.y * dy2) * i2;
+                ai += (vn.y * dx - vn.x * dy1) * i1 + (-vn.y * dx - vn.x * dy2) * i2;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = LPL / 2; off > 0; off >>= 1) {
+        ar += __shfl_down_sync(0xffffffffu, ar, off, LPL);
+        ai += __shfl_down_sync(0xffffffffu, ai, off, LPL);
+    }
+    if (live && lane == 0) out[(size_t)b * L + li] = make_float2(ar, ai);
+}
+
+}  // namespace dwb
+
+using namespace dwb;
+
+extern "C" int dwb_cauchy_sym_fwd(const float *v, const float *z, const float *w, float *out, int batch, int N,
+                                  int L, void *stream) {
+    DWB_REQUIRE(v && z && w && out, DWB_ERR_INVALID, "dwb_cauchy_sym_fwd: null pointer");
+    DWB_REQUIRE(batch >= 0 && N >= 1 && L >= 0, DWB_ERR_INVALID, "dwb_cauchy_sym_fwd: bad sizes batch=%d N=%d L=%d",
+                batch, N, L);
+    DWB_REQUIRE(batch <= 65535, DWB_ERR_UNSUPPORTED, "dwb_cauchy_sym_fwd: batch %d > 65535", batch);
+    if (batch == 0 || L == 0) return DWB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float2 *v2 = (const float2 *)v, *z2 = (const float2 *)z, *w2 = (const float2 *)w;
+    float2 *o2 = (float2 *)out;
+    // few outputs and many states: split the state dimension over a full warp; otherwise 4 lanes
+    if ((int64_t)batch * L < 4096 && N >= 64) {
+        dim3 grid(ceil_div(L, CAUCHY_THREADS / 32), batch);
+        cauchy_sym_fwd_kernel<32><<<grid, CAUCHY_THREADS, 0, st>>>(v2, z2, w2, o2, N, L);
+    } else if (N >= 8) {
+        dim3 grid(ceil_div(L, CAUCHY_THREADS / 4), batch);
+        cauchy_sym_fwd_kernel<4><<<grid, CAUCHY_THREADS, 0, st>>>(v2, z2, w2, o2, N, L);
+    } else {
+        dim3 grid(ceil_div(L, CAUCHY_THREADS), batch);
+        cauchy_sym_fwd_kernel<1><<<grid, CAUCHY_THREADS, 0, st>>>(v2, z2, w2, o2, N, L);
+    }
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+namespace dwb {
+// used by the plan and by the single-op entry; khat/k64 are caller-provided fp64 scratch
+int s4_generate(const float *C, const float *Bp, const float *P, const float *inv_w_real, const float *w_imag,
+                const float *log_dt, const float *omega, int H, int N, int l, double *khat, double *k64,
+                float *k32, cudaStream_t st, int64_t *launches) {
+    const int nk = l / 2 + 1;
+    DWB_REQUIRE(H <= 65535 / 2, DWB_ERR_UNSUPPORTED, "s4_generate: H=%d too large", H);
+    {
+        dim3 grid(ceil_div(nk, KHAT_THREADS), H);
+        size_t smem = (size_t)N * 14 * sizeof(double);
+        DWB_REQUIRE(smem <= 48 * 1024, DWB_ERR_UNSUPPORTED, "s4_generate: N=%d too large", N);
+        s4_khat_kernel<<<grid, KHAT_THREADS, smem, st>>>(C, Bp, P, inv_w_real, w_imag, log_dt, omega, H, N, l, khat);
+        DWB_LAUNCH_CHECK();
+    }
+    {
+        dim3 grid(ceil_div(l, DFT_THREADS), 2 * H);
+        irdft_kernel<<<grid, DFT_THREADS, 0, st>>>(khat, l, k64, k32);
+        DWB_LAUNCH_CHECK();
+    }
+    if (launches) *launches += 2;
+    return DWB_OK;
+}
+
+int fftconv_prepare_f64(const double *k64, const float *D, int H, int l, float *kf, cudaStream_t st) {
+    int log2M = fft_log2m_for(l);
+    DWB_REQUIRE(log2M > 0, DWB_ERR_UNSUPPORTED, "fftconv: stage length %d unsupported (max %d)", l, 1 << FFT_MAX_LOG2M);
+    dim3 grid(ceil_div((1 << log2M) + 1, DFT_THREADS), H);
+    kf_kernel<double><<<grid, DFT_THREADS, 0, st>>>(k64, D, H, l, log2M, kf);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+}  // namespace dwb
+
+extern "C" int dwb_s4_kernel_gen(const float *C, const float *Bp, const float *P, const float *inv_w_real,
+                                 const float *w_imag, const float *log_dt, const float *omega, int H, int N, int l,
+                                 float *k_out, void *stream) {
+    DWB_REQUIRE(C && Bp && P && inv_w_real && w_imag && log_dt && k_out, DWB_ERR_INVALID, "dwb_s4_kernel_gen: null pointer");
+    DWB_REQUIRE(H >= 1 && N >= 1 && l >= 2, DWB_ERR_INVALID, "dwb_s4_kernel_gen: bad sizes H=%d N=%d l=%d", H, N, l);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nk = l / 2 + 1;
+    double *khat = nullptr, *k64 = nullptr;
+    DWB_CUDA(cudaMalloc(&khat, (size_t)2 * H * nk * 2 * sizeof(double)));
+    cudaError_t e = cudaMalloc(&k64, (size_t)2 * H * l * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaFree(khat);
+        return cuda_fail(e, "cudaMalloc k64", __FILE__, __LINE__);
+    }
+    int rc = s4_generate(C, Bp, P, inv_w_real, w_imag, log_dt, omega, H, N, l, khat, k64, k_out, st, nullptr);
+    cudaError_t es = cudaStreamSynchronize(st);
+    cudaFree(khat);
+    cudaFree(k64);
+    if (rc != DWB_OK) return rc;
+    if (es != cudaSuccess) return cuda_fail(es, "dwb_s4_kernel_gen sync", __FILE__, __LINE__);
+    return DWB_OK;
+}
+
+extern "C" int dwb_fftconv_size(int l, int *nfft) {
+    DWB_REQUIRE(nfft, DWB_ERR_INVALID, "dwb_fftconv_size: null");
+    int log2M = fft_log2m_for(l);
+    DWB_REQUIRE(log2M > 0, DWB_ERR_UNSUPPORTED, "fftconv: stage length %d unsupported (max %d)", l, 1 << FFT_MAX_LOG2M);
+    *nfft = 2 << log2M;
+    return DWB_OK;
+}
+
+extern "C" int dwb_fftconv_prepare(const float *k, const float *D, int H, int l, float *kf, void *stream) {
+    DWB_REQUIRE(k && kf, DWB_ERR_INVALID, "dwb_fftconv_prepare: null pointer");
+    int log2M = fft_log2m_for(l);
+    DWB_REQUIRE(log2M > 0, DWB_ERR_UNSUPPORTED, "fftconv: stage length %d unsupported (max %d)", l, 1 << FFT_MAX_LOG2M);
+    dim3 grid(ceil_div((1 << log2M) + 1, DFT_THREADS), H);
+    kf_kernel<float><<<grid, DFT_THREADS, 0, (cudaStream_t)stream>>>(k, D, H, l, log2M, kf);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}

@@ -1,0 +1,285 @@
+"""Host mirror of the plan API: marshals a reference-keyed state_dict into libdwb and runs it.
+
+All arithmetic on the per-step path happens inside libdwb.  The host side does the cold,
+input-independent pieces the survey keeps in PyTorch:
+  * the one-off `C` rewrite of fresh (kernel.L == 0) checkpoints    (models/s4.py:525-551)
+  * the FFT node table in the reference's own complex64 recipe       (models/s4.py:553-571)
+  * the t-independent mel upsampling features, once per utterance    (models/sashimi.py:160-175)
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import Config, check, lib, ptr, stream_ptr
+
+
+def reference_nodes(l: int) -> torch.Tensor:
+    """omega exactly as models/s4.py:561-565 builds it on the CPU: primitive root rounded to
+    complex64, integer powers taken in complex64.  These drift from the true roots of unity by up
+    to 1.4e-4 at l=16000 — enough to move the S4 kernels by 3e-3 — and every checkpoint was
+    trained against them, so they are part of the function the engine reproduces."""
+    omega = torch.tensor(np.exp(-2j * np.pi / l), dtype=torch.complex64)
+    return omega ** torch.arange(0, l // 2 + 1)
+
+
+@torch.no_grad()
+def setup_C(C, B, P, inv_w_real, w_imag, log_dt, L: int):
+    """C <- [C~ (I - dA^L)][:N], C~ = [C, conj C], dA the bilinear discretisation of
+    A = diag(w~) - P~ P~^H at step dt (models/s4.py:525-551).  complex128, batched over H."""
+    cd = torch.complex128
+    Cc = torch.view_as_complex(C.double().contiguous()).to(cd)            # (2,H,N)
+    Pc = torch.view_as_complex(P.double().contiguous())[0].to(cd)         # (H,N)
+    w = torch.complex(-torch.exp(inv_w_real.double()), w_imag.double())   # (H,N)
+    dt = torch.exp(log_dt.double())
+    H, N = w.shape
+    wt, Pt = torch.cat([w, w.conj()], -1), torch.cat([Pc, Pc.conj()], -1)
+    A = torch.diag_embed(wt) - Pt[:, :, None] * Pt.conj()[:, None, :]
+    eye = torch.eye(2 * N, dtype=cd, device=A.device)
+    s = (2.0 / dt)[:, None, None].to(cd)
+    dA = torch.linalg.inv(s * eye - A) @ (s * eye + A)
+    acc, base, e = eye.expand(H, -1, -1).clone(), dA, L                    # dA^L by repeated squaring
+    while e:
+        if e & 1:
+            acc = base @ acc
+        base = base @ base
+        e >>= 1
+    Ct = torch.cat([Cc, Cc.conj()], -1)
+    Ct = Ct - torch.einsum("chn,hnm->chm", Ct, acc)
+    return torch.view_as_real(Ct[..., :N].contiguous()).float()
+
+
+def _fold(v, g):
+    n = v.reshape(v.shape[0], -1).norm(dim=1).reshape((-1,) + (1,) * (v.dim() - 1))
+    return v * (g / n)
+
+
+class Engine:
+    """One libdwb plan for one model on one device."""
+
+    def __init__(self, cfg: dict, module_or_sd, device=None, nodes="reference"):
+        self._plan = ctypes.c_void_p()
+        sd = module_or_sd.state_dict() if hasattr(module_or_sd, "state_dict") else dict(module_or_sd)
+        if device is None:
+            device = next((v.device for v in sd.values() if v.is_cuda), None)
+            if device is None:
+                if not torch.cuda.is_available():
+                    raise RuntimeError("diffwave_sashimi_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+                device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.cfg = dict(cfg)
+        self.sashimi = cfg["_name_"] == "sashimi"
+        c = Config()
+        c.model = _lib.MODEL_SASHIMI if self.sashimi else _lib.MODEL_WAVENET
+        c.unconditional = int(bool(cfg.get("unconditional", False)))
+        c.embed_in = cfg.get("diffusion_step_embed_dim_in", 128)
+        c.embed_mid = cfg.get("diffusion_step_embed_dim_mid", 512)
+        c.embed_out = cfg.get("diffusion_step_embed_dim_out", 512)
+        c.mel_bands = 80
+        if self.sashimi:
+            pool = list(cfg["pool"])
+            if len(pool) > _lib.DWB_MAX_POOL:
+                raise ValueError("too many pool stages")
+            c.d_model, c.n_layers, c.n_pool = cfg["d_model"], cfg["n_layers"], len(pool)
+            for i, p in enumerate(pool):
+                c.pool[i] = p
+            c.expand, c.ff, c.unet, c.L = cfg["expand"], cfg["ff"], int(bool(cfg.get("unet", True))), cfg["L"]
+            c.d_state_half = 32
+        else:
+            c.res_channels, c.skip_channels = cfg["res_channels"], cfg["skip_channels"]
+            c.num_res_layers, c.dilation_cycle = cfg["num_res_layers"], cfg["dilation_cycle"]
+        self._c = c
+        with torch.cuda.device(self.device):
+            check(lib().dwb_plan_create(ctypes.byref(c), self.device.index or 0, ctypes.byref(self._plan)))
+            try:
+                self._load(sd, module_or_sd if hasattr(module_or_sd, "state_dict") else None, nodes)
+                check(lib().dwb_plan_finalize(self._plan, stream_ptr(self.device)))
+            except Exception:
+                self.close()
+                raise
+        self._sd = sd if not c.unconditional else None   # conditioning weights stay on the host mirror
+        self._cond_cache = None
+
+    # ---- weights ------------------------------------------------------------------------
+    def _block_prefixes(self):
+        from .models import Sashimi  # noqa: F401  (layout mirrors Sashimi.__init__)
+        cfg = self.cfg
+        H, l, out, i = cfg["d_model"], cfg["L"], [], 0
+        for p in cfg["pool"]:
+            if cfg.get("unet", True):
+                for _ in range(cfg["n_layers"]):
+                    out.append((f"d_layers.{i}.", H, l)); i += 1
+            i += 1
+            l //= p; H *= cfg["expand"]
+        for j in range(cfg["n_layers"]):
+            out.append((f"c_layers.{j}.", H, l))
+        i = 0
+        for p in list(cfg["pool"])[::-1]:
+            H //= cfg["expand"]; l *= p
+            i += 1
+            for _ in range(cfg["n_layers"]):
+                out.append((f"u_layers.{i}.", H, l)); i += 1
+        return out
+
+    @torch.no_grad()
+    def _load(self, sd, module, nodes):
+        st = stream_ptr(self.device)
+        if self.sashimi:
+            lengths = set()
+            for (p, H, l) in self._block_prefixes():
+                k = p + "layer.kernel.kernel."
+                lengths.add(l)
+                Lcur = int(sd[k + "L"])
+                if Lcur == 0:      # fresh checkpoint: the reference rewrites C on its first forward
+                    newC = setup_C(sd[k + "C"], sd[k + "B"], sd[k + "P"], sd[k + "inv_w_real"], sd[k + "w_imag"],
+                                   sd[k + "log_dt"], l).to(sd[k + "C"].device)
+                    sd[k + "C"] = newC
+                    sd[k + "L"] = torch.tensor(l)
+                    if module is not None:   # keep the module's state identical to the reference's after a forward
+                        tgt = dict(module.named_parameters())[k + "C"]
+                        tgt.copy_(newC)
+                        dict(module.named_buffers())[k + "L"].fill_(l)
+                elif Lcur != l:
+                    raise NotImplementedError(
+                        f"{k}L = {Lcur} but the stage length is {l}: kernel length doubling (s4.py:531-534) is not built")
+            if nodes != "exact":
+                for l in sorted(lengths):
+                    om = reference_nodes(l) if nodes == "reference" else (
+                        torch.tensor(np.exp(-2j * np.pi / l), dtype=torch.complex64, device=self.device)
+                        ** torch.arange(0, l // 2 + 1, device=self.device)).cpu()
+                    self._set(f"nodes.{l}", torch.view_as_real(om).contiguous(), st)
+        for name, t in sd.items():
+            if "upsample_conv2d" in name or "mel_conv" in name:
+                continue   # conditioning front-end runs on the host mirror, once per utterance
+            self._set(name, t, st)
+
+    def _set(self, name, t, st):
+        t = t.detach()
+        if t.dtype in (torch.int64, torch.int32, torch.int16, torch.uint8, torch.bool):
+            t, dt = t.to(torch.int64), _lib.I64
+        else:
+            t, dt = t.to(torch.float32), _lib.F32
+        t = t.contiguous()
+        shape = (ctypes.c_int64 * max(1, t.dim()))(*t.shape)
+        check(lib().dwb_plan_set_tensor(self._plan, name.encode(), ptr(t), dt, shape, t.dim(), int(t.is_cuda), st))
+
+    # ---- conditioning -------------------------------------------------------------------
+    def cond_layout(self, L):
+        n = ctypes.c_int(0)
+        check(lib().dwb_plan_cond_layout(self._plan, L, ctypes.byref(n), None, None, None))
+        ch, ln, off = (ctypes.c_int * n.value)(), (ctypes.c_int * n.value)(), (ctypes.c_int64 * n.value)()
+        check(lib().dwb_plan_cond_layout(self._plan, L, ctypes.byref(n), ch, ln, off))
+        return list(ch), list(ln), list(off)
+
+    @torch.no_grad()
+    def cond_features(self, mel, L):
+        """(cond_batch, sum_i H_i l_i) conditioning features from a mel (cb, 80, frames): per block
+        two weight-normed ConvTranspose2d + leaky-ReLU(0.4), crop to the FIRST l_i samples, 1x1
+        80 -> H_i (models/sashimi.py:160-175, models/wavenet.py:98-111).  t-independent."""
+        key = (mel.data_ptr(), tuple(mel.shape), mel._version, L)
+        if self._cond_cache is not None and self._cond_cache[0] == key:
+            return self._cond_cache[1]
+        sd = self._sd
+        mel = mel.to(self.device, torch.float32)
+        cb = mel.shape[0]
+        if self.sashimi:
+            prefixes = [p for (p, _, _) in self._block_prefixes()]
+        else:
+            prefixes = [f"residual_layer.residual_blocks.{n}." for n in range(self.cfg["num_res_layers"])]
+        ch, ln, off = self.cond_layout(L)
+        total = off[-1] + ch[-1] * ln[-1]
+        out = torch.empty(cb * total, dtype=torch.float32, device=self.device)
+        for p, Hc, l, o in zip(prefixes, ch, ln, off):
+            m = mel.unsqueeze(1)
+            for i in range(2):
+                v = sd[f"{p}upsample_conv2d.{i}.weight_v"].to(self.device, torch.float32)
+                g = sd[f"{p}upsample_conv2d.{i}.weight_g"].to(self.device, torch.float32)
+                s = v.shape[-1] // 2
+                m = F.leaky_relu(F.conv_transpose2d(m, _fold(v, g), sd[f"{p}upsample_conv2d.{i}.bias"].to(self.device),
+                                                    stride=(1, s), padding=(1, s // 2)), 0.4)
+            m = m.squeeze(1)
+            if m.shape[-1] < l:
+                raise RuntimeError(f"upsampled mel has {m.shape[-1]} samples < {l}")
+            w = _fold(sd[p + "mel_conv.conv.weight_v"].to(self.device, torch.float32),
+                      sd[p + "mel_conv.conv.weight_g"].to(self.device, torch.float32))[:, :, 0]
+            f = torch.einsum("mk,bkl->bml", w, m[:, :, :l]) + sd[p + "mel_conv.conv.bias"].to(self.device)[None, :, None]
+            out[cb * o: cb * o + cb * Hc * l] = f.reshape(-1)
+        self._cond_cache = (key, out)
+        return out
+
+    # ---- hot path -----------------------------------------------------------------------
+    def _cond(self, mel, L):
+        if mel is None:
+            return None, 0
+        return self.cond_features(mel, L), mel.shape[0]
+
+    @torch.no_grad()
+    def forward(self, audio, diffusion_steps, mel_spec=None):
+        """eps = net((audio, diffusion_steps), mel_spec)   (generate.py:51)"""
+        x = audio.to(self.device, torch.float32).contiguous()
+        B, ch, L = x.shape
+        assert ch == 1
+        t = diffusion_steps.to(self.device, torch.float32).reshape(-1).contiguous()
+        if t.numel() != B:
+            raise ValueError("diffusion_steps must have one entry per batch element")
+        cond, cb = self._cond(mel_spec, L)
+        eps = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            check(lib().dwb_forward(self._plan, ptr(x), ptr(t), ptr(cond), cb, ptr(eps), B, L, stream_ptr(self.device)))
+        return eps
+
+    @torch.no_grad()
+    def sample(self, x_T, noise, coef, mel_spec=None, out=None, use_graph=True):
+        """x_0 of the T-step reverse loop (generate.py:47-54) from pre-drawn noise.
+        x_T (B,1,L), noise (T-1,B,1,L) on the device; coef (3,T) fp32 host tensor (see dwb.h)."""
+        B, _, L = x_T.shape
+        T = coef.shape[1]
+        assert x_T.is_cuda and x_T.is_contiguous() and x_T.dtype == torch.float32
+        if T > 1:
+            assert noise.is_cuda and noise.is_contiguous() and noise.dtype == torch.float32 and noise.shape[0] == T - 1
+        cond, cb = self._cond(mel_spec, L)
+        if out is None:
+            out = torch.empty_like(x_T)
+        coef = coef.detach().to("cpu", torch.float32).contiguous()
+        cp = coef.numpy().ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        with torch.cuda.device(self.device):
+            check(lib().dwb_sample(self._plan, ptr(x_T), ptr(noise) if T > 1 else None, ptr(cond), cb, cp, T, ptr(out),
+                                   B, L, int(use_graph), stream_ptr(self.device)))
+        return out
+
+    # ---- introspection ------------------------------------------------------------------
+    def launch_count(self):
+        n = ctypes.c_int64(0)
+        check(lib().dwb_plan_launch_count(self._plan, ctypes.byref(n)))
+        return n.value
+
+    def work(self, L):
+        b, f = ctypes.c_double(0), ctypes.c_double(0)
+        check(lib().dwb_plan_work(self._plan, L, ctypes.byref(b), ctypes.byref(f)))
+        return b.value, f.value
+
+    def s4_kernels(self):
+        n = ctypes.c_int(0)
+        check(lib().dwb_plan_s4_blocks(self._plan, ctypes.byref(n)))
+        out = []
+        for i in range(n.value):
+            H, l = ctypes.c_int(0), ctypes.c_int(0)
+            check(lib().dwb_plan_s4_kernel(self._plan, i, None, 0, ctypes.byref(H), ctypes.byref(l)))
+            k = torch.empty(2, H.value, l.value, dtype=torch.float32, device=self.device)
+            check(lib().dwb_plan_s4_kernel(self._plan, i, ptr(k), k.numel(), ctypes.byref(H), ctypes.byref(l)))
+            out.append(k)
+        return out
+
+    def close(self):
+        if getattr(self, "_plan", None) is not None and self._plan.value:
+            lib().dwb_plan_destroy(self._plan)
+            self._plan = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,162 @@
+/*
+ * dwb.h — C ABI of libdwb.so, the B200 (sm_100a) DiffWave denoising engine.
+ *
+ * Drop-in boundary for the reverse-sampling hot path of albertfgu/diffwave-sashimi:
+ *   generate.py:23-55 (sampling)  ->  net((x, t), mel)  ->  models/wavenet.py | models/sashimi.py + models/s4.py
+ * and for the reference's only native FFI, the pybind11 module `cauchy_mult`
+ * (extensions/cauchy/cauchy.cpp:86-95).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.  Every entry returns an int
+ *     (DWB_OK or an error code); dwb_last_error() gives the message (thread-local).
+ *   - All tensor pointers are DEVICE pointers unless the parameter name ends in _host.
+ *     The caller owns every buffer it passes; the plan owns folded weights, tables,
+ *     cached S4 spectra and its activation workspace.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); entries
+ *     only enqueue work on it and never synchronise unless documented.
+ *   - One plan per (device, model).  A plan is not re-entrant; independent plans are
+ *     thread-safe.  There is no global mutable state besides the thread-local error string.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry fails with
+ *     DWB_ERR_CUDA.
+ */
+#ifndef DWB_H_
+#define DWB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DWB_VERSION 100
+
+enum dwb_status {
+    DWB_OK = 0,
+    DWB_ERR_INVALID = 1,     /* bad argument / shape */
+    DWB_ERR_CUDA = 2,        /* CUDA runtime error (message has the cudaError string) */
+    DWB_ERR_STATE = 3,       /* call order violated (e.g. forward before finalize) */
+    DWB_ERR_MISSING = 4,     /* a required state_dict tensor was never supplied */
+    DWB_ERR_UNSUPPORTED = 5  /* configuration outside what the kernels implement */
+};
+
+enum dwb_model { DWB_MODEL_WAVENET = 0, DWB_MODEL_SASHIMI = 1 };
+enum dwb_dtype { DWB_F32 = 0, DWB_I64 = 1 };
+
+#define DWB_MAX_POOL 4
+
+/* Mirrors the constructor kwargs of the reference plugins
+ * (configs/model/{wavenet,sashimi}*.yaml; models/wavenet.py:168-176; models/sashimi.py:188-203). */
+typedef struct dwb_config {
+    int32_t model;              /* enum dwb_model  <- model._name_ */
+    int32_t unconditional;      /* 1 = no mel conditioning */
+    int32_t embed_in;           /* diffusion_step_embed_dim_in  (128) */
+    int32_t embed_mid;          /* diffusion_step_embed_dim_mid (512) */
+    int32_t embed_out;          /* diffusion_step_embed_dim_out (512) */
+    /* wavenet */
+    int32_t res_channels, skip_channels, num_res_layers, dilation_cycle;
+    /* sashimi */
+    int32_t d_model, n_layers, n_pool, pool[DWB_MAX_POOL], expand, ff, unet;
+    int32_t L;                  /* l_max of the top stage (dataset.segment_length) */
+    int32_t d_state_half;       /* N: conjugate pairs per SSM (d_state/2 = 32) */
+    /* conditioning */
+    int32_t mel_bands;          /* 80 */
+} dwb_config;
+
+typedef struct dwb_plan dwb_plan;
+
+/* ---- housekeeping ------------------------------------------------------------------ */
+int dwb_version(void);
+const char *dwb_last_error(void);
+/* number of CUDA devices visible to the library (0 => every compute entry fails) */
+int dwb_device_count(int *count);
+
+/* ---- plan life cycle --------------------------------------------------------------- */
+/* replaces models.construct_model(cfg).cuda()  (models/__init__.py:4-12, generate.py:94) */
+int dwb_plan_create(const dwb_config *cfg, int device, dwb_plan **out);
+int dwb_plan_destroy(dwb_plan *plan);
+
+/* replaces net.load_state_dict(...) (generate.py:103): hand over ONE state_dict entry under
+ * its reference key, e.g. "d_layers.3.layer.kernel.kernel.C".
+ * `data` may be host or device memory (`on_device`); it is copied.  Besides state_dict keys the
+ * plan accepts "nodes.<l>" = complex64 FFT nodes omega (l/2+1, 2) for S4 kernel generation at
+ * stage length l (models/s4.py:553-571); a stage without supplied nodes uses exact roots of
+ * unity. */
+int dwb_plan_set_tensor(dwb_plan *plan, const char *name, const void *data, int dtype,
+                        const int64_t *shape, int ndim, int on_device, void *stream);
+
+/* Folds weight norm, lays weights out for the kernels, builds the t-embedding weight stack and
+ * generates + caches every S4 convolution spectrum (Cauchy -> Woodbury -> irfft -> wrapped rfft;
+ * models/s4.py:674-807,1391-1403).  Input independent; once per weight load.  Synchronises. */
+int dwb_plan_finalize(dwb_plan *plan, void *stream);
+
+/* ---- the hot path ------------------------------------------------------------------- */
+/* eps = net((x, t), mel_spec)                     (generate.py:51; wavenet.py:202-210; sashimi.py:277-313)
+ *   x    (B,1,L) f32        t  (B) f32 diffusion steps (any real value, per batch element)
+ *   cond NULL, or the concatenated per-block conditioning features produced by
+ *        dwb_plan_cond_layout()/the host mirror (t-independent, cached per utterance)
+ *   cond_batch 1 (broadcast over B) or B
+ *   eps  (B,1,L) f32 */
+int dwb_forward(dwb_plan *plan, const float *x, const float *t, const float *cond, int cond_batch,
+                float *eps, int B, int L, void *stream);
+
+/* x_0 = sampling(net, (B,1,L), diffusion_hyperparams, condition)        (generate.py:23-55)
+ *   x_T        (B,1,L)        first normal draw
+ *   noise      (T-1,B,1,L)    draw i is used at step t = T-1-i  (reference RNG order)
+ *   coef_host  (3,T) host f32: row 0 = (1-alpha_t)/sqrt(1-alpha_bar_t), row 1 = sqrt(alpha_t),
+ *                              row 2 = sigma_t      (utils.py:121-151, computed by the caller in
+ *                              torch fp32 so the tables are bit-identical to the reference's)
+ *   out        (B,1,L)
+ *   use_graph  1: the whole T-step loop is captured once into a CUDA graph (cached on
+ *                 (B, L, T, pointers)) and replayed; 0: plain stream launches */
+int dwb_sample(dwb_plan *plan, const float *x_T, const float *noise, const float *cond, int cond_batch,
+               const float *coef_host, int T, float *out, int B, int L, int use_graph, void *stream);
+
+/* conditioning feature layout: number of blocks and, per block, channels H_i and length l_i;
+ * features for block i are (cond_batch, H_i, l_i) f32 at float offset cond_batch * offset_i.
+ * Pass NULL arrays to query n_blocks only. */
+int dwb_plan_cond_layout(dwb_plan *plan, int L, int *n_blocks, int *channels, int *lengths, int64_t *offsets);
+
+/* ---- introspection / accounting ------------------------------------------------------ */
+/* kernels launched by this plan since creation (graph replays count their node launches) */
+int dwb_plan_launch_count(dwb_plan *plan, int64_t *count);
+/* number of S4 blocks, and a copy of block i's generated time-domain kernel k (2,H,l) f32 */
+int dwb_plan_s4_blocks(dwb_plan *plan, int *n_blocks);
+int dwb_plan_s4_kernel(dwb_plan *plan, int block, float *k_out, int64_t capacity, int *H, int *l);
+/* algorithmic HBM bytes and flops of one forward per clip (SURVEY.md §8(d) formulas) */
+int dwb_plan_work(dwb_plan *plan, int L, double *bytes_per_clip_step, double *flops_per_clip_step);
+
+/* ---- single ops (same kernels the plan uses; exported for tests and for callers that
+ *      only want to replace one reference op) ------------------------------------------ */
+/* out[b,l] = sum_n v[b,n]/(z[l]-w[b,n]) + conj(v[b,n])/(z[l]-conj(w[b,n]))
+ * complex64 as interleaved float pairs; v,w (batch,N); z (L); out (batch,L).
+ * Replaces cauchy_mult_sym_fwd (extensions/cauchy/cauchy.cpp:55-66, cauchy_cuda.cu:242-375);
+ * N is the HALF state size as passed by models/s4.py:758; any N >= 1 (the reference requires a
+ * power of two in 2..1024). */
+int dwb_cauchy_sym_fwd(const float *v, const float *z, const float *w, float *out,
+                       int batch, int N, int L, void *stream);
+
+/* S4 NPLR kernel generation for one layer (models/s4.py:674-807, rank 1, bidirectional):
+ * parameters exactly as stored in the state_dict (f32): C (2,H,N,2) B (1,H,N,2) P (1,H,N,2)
+ * inv_w_real (H,N) w_imag (H,N) log_dt (H); omega (l/2+1,2) complex64 nodes or NULL for exact
+ * roots of unity (+ analytic Nyquist limit).  Evaluated in fp64; k_out (2,H,l) f32. */
+int dwb_s4_kernel_gen(const float *C, const float *Bp, const float *P, const float *inv_w_real,
+                      const float *w_imag, const float *log_dt, const float *omega,
+                      int H, int N, int l, float *k_out, void *stream);
+
+/* Cache the spectrum for the long convolution: kf (H, nfft/2+1, 2) f32 in the kernel's internal
+ * order and scale from k (2,H,l) and D (H).  nfft = dwb_fftconv_size(l). */
+int dwb_fftconv_size(int l, int *nfft);
+int dwb_fftconv_prepare(const float *k, const float *D, int H, int l, float *kf, void *stream);
+
+/* g = GELU( conv(y, k0 | k1) + D*y ),  y = (ln_s*rstd)*(x - mean + ln_m) + part_t[h]
+ *   x (B,H,l); stats (B,l,2) = (mean, rstd) over channels; part_t (B,H) or (H) with
+ *   part_stride_b = 0; kf from dwb_fftconv_prepare; g (B,H,l).
+ * (models/sashimi.py:148-157 + models/s4.py:1391-1430 up to the activation) */
+int dwb_fftconv(const float *x, const float *stats, const float *part_t, int64_t part_stride_b,
+                float ln_m, float ln_s, const float *kf, float *g, int B, int H, int l, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DWB_H_ */

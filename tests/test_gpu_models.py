@@ -1,0 +1,177 @@
+"""`-m gpu`: whole-network parity of the CUDA engine (through the C ABI) against
+(1) golden eps produced by the unmodified reference, (2) the oracle on the same seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden, rel_l2, rel_max
+from oracle import diffwave_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3       # north star: 1e-3 relative; measured values are printed and are ~1e-5
+
+
+@pytest.fixture(scope="module")
+def dwb():
+    import diffwave_sashimi_b200 as d
+    assert torch.cuda.is_available()
+    return d
+
+
+def _model(dwb, cfg, sd):
+    net = dwb.construct_model(dict(cfg))
+    net.load_state_dict(sd)
+    return net.cuda().eval()
+
+
+@pytest.mark.parametrize("name", ["tiny_unet", "tiny_snet", "tiny_unet_e128", "tiny_unet_cond", "tiny_unet_condB",
+                                  "tiny_wnet", "tiny_wnet_cond"])
+def test_tiny_forward_vs_reference_golden(dwb, name):
+    g = load_golden(name)
+    net = _model(dwb, g["cfg"], g["sd"])
+    x, t = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()
+    mel = torch.from_numpy(g["mel"]).cuda() if "mel" in g else None
+    with torch.no_grad():
+        eps = net((x, t), mel_spec=mel).cpu()
+    e2, em = rel_l2(eps, g["eps"]), rel_max(eps, g["eps"])
+    print(f"{name}: rel_l2 {e2:.2e} rel_max {em:.2e}")
+    assert e2 < 1e-4 and em < 1e-4
+
+
+@pytest.mark.parametrize("name", ["tiny_unet", "tiny_snet", "tiny_unet_cond"])
+def test_fresh_checkpoint_C_rewrite(dwb, name):
+    # a kernel.L == 0 state_dict must give the same eps, and leave the module in the state the
+    # reference leaves its own module in after the first forward (models/s4.py:525-551)
+    g = load_golden(name)
+    sd = dict(g["sd"])
+    for k, v in g["sd0"].items():
+        sd[k] = v
+    net = _model(dwb, g["cfg"], sd)
+    x, t = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()
+    mel = torch.from_numpy(g["mel"]).cuda() if "mel" in g else None
+    with torch.no_grad():
+        eps = net((x, t), mel_spec=mel).cpu()
+    assert rel_l2(eps, g["eps"]) < 1e-4
+    after = net.state_dict()
+    for k in g["sd0"]:
+        if k.endswith(".C"):
+            assert rel_max(after[k].cpu(), g["sd"][k]) < 1e-4
+        else:
+            assert int(after[k]) == int(g["sd"][k])
+
+
+@pytest.mark.parametrize("name", ["tiny_unet", "tiny_wnet"])
+@pytest.mark.parametrize("graph", [True, False])
+def test_trajectory_vs_reference_golden(dwb, name, graph):
+    g = load_golden("traj_" + name)
+    net = _model(dwb, g["cfg"], g["sd"])
+    T = int(g["T"])
+    dh = dwb.calc_diffusion_hyperparams(T, float(g["beta_0"]), float(g["beta_T"]), fast=True)
+    torch.manual_seed(int(g["seed"]))
+    x0 = dwb.sampling(net, g["x0"].shape, dh, use_graph=graph, verbose=False).cpu()
+    e2, em = rel_l2(x0, g["x0"]), rel_max(x0, g["x0"])
+    print(f"traj {name} graph={graph}: rel_l2 {e2:.2e} rel_max {em:.2e}")
+    assert e2 < 1e-4 and em < 1e-4
+    if graph:   # replaying the cached graph gives bit-identical output
+        torch.manual_seed(int(g["seed"]))
+        eng = net._engine_get()
+        x_T, noise = dwb.draw_noise(tuple(g["x0"].shape), T)
+        x_T, noise = x_T.cuda(), noise.cuda()
+        coef = dwb.step_coefficients(dh)
+        out = torch.empty_like(x_T)
+        a = eng.sample(x_T, noise, coef, out=out).clone()
+        b = eng.sample(x_T, noise, coef, out=out).clone()
+        assert torch.equal(a, b) and rel_l2(a.cpu(), g["x0"]) < 1e-4
+
+
+FULL = {
+    "wnet_h128_d30": ("full_wnet_h128_d30", None),
+    "unet_d64": ("full_unet_d64", None),
+    "unet_d32_cond": ("full_unet_d32_cond", (1, 80, 63)),
+}
+
+
+def _full_inputs(melshape):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 1, 16000, generator=g)
+    mel = torch.randn(*melshape, generator=g) if melshape else None
+    return x, mel
+
+
+@pytest.mark.parametrize("name", list(FULL))
+def test_baseline_size_vs_reference_golden(dwb, name):
+    """BASELINE.json configs at full size: weights are rebuilt from the seed by our own
+    initialiser; the stored eps came from the unmodified reference with those weights loaded."""
+    from oracle.refshim import MODEL_CFGS
+    fname, melshape = FULL[name]
+    path = os.path.join(GOLDEN, fname + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("full-size golden not generated")
+    g = load_golden(fname)
+    cfg = dict(MODEL_CFGS[name])
+    sd = dwb.init.seeded_state_dict(cfg, seed=0)
+    net = _model(dwb, cfg, sd)
+    x, mel = _full_inputs(melshape)
+    for key in [k for k in g if k.startswith("eps_t")]:
+        tv = float(key[5:])
+        with torch.no_grad():
+            eps = net((x.cuda(), torch.full((1, 1), tv).cuda()), mel_spec=None if mel is None else mel.cuda()).cpu()
+        e2, em = rel_l2(eps, g[key]), rel_max(eps, g[key])
+        print(f"{name} t={tv}: rel_l2 {e2:.2e} rel_max {em:.2e} (std eps {eps.std():.3f})")
+        assert e2 < TOL and em < TOL
+
+
+@pytest.mark.parametrize("name,B", [("unet_d64", 2), ("wnet_h128_d30", 1)])
+def test_baseline_size_vs_oracle_fp64(dwb, name, B):
+    from oracle.refshim import MODEL_CFGS
+    cfg = dict(MODEL_CFGS[name])
+    sd = dwb.init.seeded_state_dict(cfg, seed=3)
+    net = _model(dwb, cfg, sd)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, 1, 16000, generator=g)
+    t = torch.tensor([[100.0], [3.0]])[:B]
+    with torch.no_grad():
+        eps = net((x.cuda(), t.cuda())).cpu()
+    sd_after = {k: v.cpu() for k, v in net.state_dict().items()}   # C rewritten, L set
+    ref = O.forward(cfg, sd_after, x, t)
+    e2, em = rel_l2(eps, ref), rel_max(eps, ref)
+    print(f"{name} vs fp64 oracle: rel_l2 {e2:.2e} rel_max {em:.2e}")
+    assert e2 < TOL and em < TOL
+
+
+def test_batch_elements_are_independent(dwb):
+    from oracle.refshim import MODEL_CFGS
+    cfg = dict(MODEL_CFGS["unet_d64"])
+    net = _model(dwb, cfg, dwb.init.seeded_state_dict(cfg, seed=1))
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 1, 16000, generator=g).cuda()
+    t = torch.tensor([[5.0], [150.0], [77.0]]).cuda()
+    with torch.no_grad():
+        full = net((x, t))
+        for b in range(3):
+            one = net((x[b:b + 1], t[b:b + 1]))
+            assert torch.equal(one, full[b:b + 1])
+
+
+def test_errors(dwb):
+    from oracle.refshim import MODEL_CFGS
+    g = load_golden("tiny_unet")
+    net = _model(dwb, g["cfg"], g["sd"])
+    with pytest.raises(RuntimeError):        # wrong length for this plan
+        with torch.no_grad():
+            net((torch.zeros(1, 1, 128).cuda(), torch.zeros(1, 1).cuda()))
+    with pytest.raises(RuntimeError):        # conditioning on an unconditional model
+        with torch.no_grad():
+            net((torch.zeros(1, 1, 256).cuda(), torch.zeros(1, 1).cuda()), mel_spec=torch.zeros(1, 80, 2).cuda())
+    with pytest.raises(RuntimeError):        # no CPU path
+        with torch.no_grad():
+            net((torch.zeros(1, 1, 256), torch.zeros(1, 1)))
+    with pytest.raises(RuntimeError):        # inference engine only
+        net((torch.zeros(1, 1, 256).cuda(), torch.zeros(1, 1).cuda()))
+    sd = dict(g["sd"])
+    sd.pop("d_layers.0.layer.D")
+    with pytest.raises(RuntimeError):        # missing tensor is reported by name
+        dwb.Engine(g["cfg"], {k: v.cuda() for k, v in sd.items()})

@@ -1,0 +1,141 @@
+"""`-m gpu`: single libdwb ops (through the C ABI) against the oracle / golden fixtures."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, rel_max
+from oracle import diffwave_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dwb():
+    import diffwave_sashimi_b200 as d
+    assert torch.cuda.is_available()
+    return d
+
+
+@pytest.mark.parametrize("N", [4, 8, 64, 256])
+@pytest.mark.parametrize("L", [3, 17, 489, 1024, 1047])
+def test_cauchy_vs_reference_complex128(dwb, N, L):
+    # inputs and expected values of extensions/cauchy/test_cauchy.py:53-66 (seed 2357, batch 4);
+    # the op receives the HALF spectra like models/s4.py:758
+    g = load_golden("cauchy")
+    v, w, z = (torch.from_numpy(g[f"{k}_{N}_{L}"]).cuda() for k in "vwz")
+    out = dwb.ops.cauchy_mult_sym_fwd(v, z, w).cpu()
+    ref = torch.from_numpy(g[f"out_{N}_{L}"])
+    err = (out.to(torch.complex128) - ref).abs()
+    assert (err.max() / ref.abs().max()).item() < 2e-5
+    assert (err / ref.abs()).mean().item() < 1e-4       # the reference's own criterion is 10x KeOps + 1e-4
+
+
+@pytest.mark.parametrize("N,L,batch", [(1, 5, 3), (2, 33, 2), (32, 8001, 6), (512, 3, 4), (1024, 64, 2), (32, 2 ** 16, 2)])
+def test_cauchy_shapes(dwb, N, L, batch):
+    g = torch.Generator().manual_seed(N * 1000 + L)
+    v = torch.randn(batch, N, dtype=torch.complex64, generator=g)
+    w = torch.randn(batch, N, dtype=torch.complex64, generator=g)
+    z = torch.exp(1j * torch.randn(L, generator=g)).to(torch.complex64)
+    ref = O.cauchy_sym(v.cdouble(), z.cdouble(), w.cdouble())
+    out = dwb.ops.cauchy_mult(v.cuda(), z.cuda(), w.cuda(), symmetric=True).cpu()
+    err = (out.to(torch.complex128) - ref).abs()
+    assert (err.max() / ref.abs().max()).item() < 2e-5
+
+
+def test_cauchy_broadcast_wrapper(dwb):
+    # the call shape of models/s4.py:758: v (2,3,H,N), w (H,N), z (L)
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(2, 3, 5, 32, dtype=torch.complex64, generator=g)
+    w = torch.randn(5, 32, dtype=torch.complex64, generator=g) - 2
+    z = torch.exp(1j * torch.randn(77, generator=g)).to(torch.complex64)
+    out = dwb.ops.cauchy_mult(v.cuda(), z.cuda(), w.cuda()).cpu()
+    ref = O.cauchy_sym(v.cdouble(), z.cdouble(), w.cdouble().expand(2, 3, 5, 32))
+    assert out.shape == (2, 3, 5, 77)
+    assert rel_max(torch.view_as_real(out), torch.view_as_real(ref)) < 2e-5
+
+
+@pytest.mark.parametrize("H,L", [(4, 64), (3, 100), (2, 250), (2, 1000)])
+def test_s4_kernel_gen_vs_reference(dwb, H, L):
+    g = load_golden(f"s4kernel_H{H}_L{L}")
+    sd = {k: v.cuda() for k, v in g["sd1"].items()}
+    p = "kernel.kernel."
+    args = (sd[p + "C"], sd[p + "B"], sd[p + "P"], sd[p + "inv_w_real"], sd[p + "w_imag"], sd[p + "log_dt"], L)
+    k = dwb.ops.s4_kernel_gen(*args, omega=torch.from_numpy(g["omega"]).cuda()).cpu()
+    assert rel_max(k, g["k"]) < 2e-5            # reference fp32 kernel, reference nodes
+    sd1 = {"layer." + kk: v for kk, v in g["sd1"].items()}
+    k_exact = dwb.ops.s4_kernel_gen(*args, omega=None).cpu()
+    assert rel_max(k_exact, O.s4_kernel(sd1, "layer.", L, nodes="exact")) < 1e-6
+    k_ref64 = O.s4_kernel(sd1, "layer.", L, nodes="reference")
+    assert rel_max(k, k_ref64) < 1e-6
+
+
+@pytest.mark.parametrize("L", [16000, 4000])
+def test_s4_kernel_gen_full_length(dwb, L):
+    H = 4
+    torch.manual_seed(L)
+    p = dwb.init.s4_layer_params(H)
+    sd = {"layer." + k: v for k, v in p.items()}
+    sd["layer.kernel.kernel.C"] = O.s4_setup_C(sd, "layer.", L).float()
+    kk = "layer.kernel.kernel."
+    k = dwb.ops.s4_kernel_gen(*(sd[kk + n].cuda() for n in ("C", "B", "P", "inv_w_real", "w_imag", "log_dt")), L,
+                              omega=dwb.engine.reference_nodes(L).cuda()).cpu()
+    ref = O.s4_kernel(sd, "layer.", L, nodes="reference")
+    assert rel_max(k, ref) < 1e-6
+
+
+def _fftconv_ref(x, stats, part, m, s, k, D):
+    x = x.double()
+    if stats is not None:
+        y = (s * stats[..., 1].double())[:, None, :] * (x - stats[..., 0].double()[:, None, :] + m)
+    else:
+        y = x
+    if part is not None:
+        y = y + (part.double()[:, :, None] if part.dim() == 2 else part.double()[None, :, None])
+    c = O.s4_apply(k.double(), D.double().reshape(1, -1), y)
+    return torch.nn.functional.gelu(c)
+
+
+@pytest.mark.parametrize("B,H,l", [(1, 1, 16), (2, 3, 40), (1, 2, 33), (3, 2, 64), (2, 2, 100), (1, 3, 250), (2, 2, 1000),
+                                   (1, 2, 1001), (2, 3, 4000), (2, 2, 16000), (1, 1, 16384)])
+def test_fftconv_vs_oracle(dwb, B, H, l):
+    g = torch.Generator().manual_seed(B * 7 + H * 13 + l)
+    x = torch.randn(B, H, l, generator=g) * 2 + 0.3
+    k = torch.randn(2, H, l, generator=g) * torch.exp(-torch.arange(l) / (0.2 * l + 3))[None, None] * 0.3
+    D = torch.randn(H, generator=g)
+    stats = torch.stack([torch.randn(B, l, generator=g) * 0.1, torch.rand(B, l, generator=g) + 0.5], -1)
+    part = torch.randn(B, H, generator=g)
+    kf = dwb.ops.fftconv_prepare(k.cuda(), D.cuda())
+    out = dwb.ops.fftconv(x.cuda(), kf, stats.cuda(), part.cuda(), ln_m=0.05, ln_s=1.3).cpu()
+    ref = _fftconv_ref(x, stats, part, 0.05, 1.3, k, D)
+    assert rel_l2(out, ref) < 2e-5 and rel_max(out, ref) < 2e-5
+    # no LN / shared t-embedding row
+    out2 = dwb.ops.fftconv(x.cuda(), kf, None, part[0].cuda()).cpu()
+    ref2 = _fftconv_ref(x, None, part[0], 0, 1, k, D)
+    assert rel_l2(out2, ref2) < 2e-5
+
+
+def test_fftconv_is_linear_before_gelu_and_shift_covariant(dwb):
+    # size-independent properties at the BASELINE length: conv(a x) = a conv(x) where GELU is
+    # ~identity (large positive values), and an impulse reproduces the two-sided kernel itself
+    l, H = 16000, 2
+    g = torch.Generator().manual_seed(3)
+    k = torch.randn(2, H, l, generator=g) * torch.exp(-torch.arange(l) / 500.0)[None, None]
+    D = torch.zeros(H)
+    kf = dwb.ops.fftconv_prepare(k.cuda(), D.cuda())
+    x = torch.zeros(1, H, l)
+    t0 = 7000
+    x[0, :, t0] = 1.0
+    bias = torch.full((H,), 0.0)
+    y = dwb.ops.fftconv(x.cuda(), kf, None, bias.cuda()).cpu()
+    # y = gelu(c), c[t] = k0[t - t0] (t >= t0), k1[t0 - t - 1] (t < t0)
+    c = torch.zeros(H, l, dtype=torch.float64)
+    c[:, t0:] = k[0, :, : l - t0].double()
+    c[:, :t0] = k[1, :, :t0].flip(-1).double()
+    assert rel_max(y[0], torch.nn.functional.gelu(c)) < 2e-5
+
+
+def test_fftconv_rejects_too_long(dwb):
+    with pytest.raises(RuntimeError):
+        dwb.ops.fftconv_size(20000)
