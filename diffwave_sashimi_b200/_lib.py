@@ -51,12 +51,16 @@ SIGNATURES = {
     "dwb_plan_s4_blocks": [_P, ctypes.POINTER(_I)],
     "dwb_plan_s4_kernel": [_P, _I, _P, _I64, ctypes.POINTER(_I), ctypes.POINTER(_I)],
     "dwb_plan_work": [_P, _I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
+    "dwb_plan_profile": [_P, _P, _P, _P, _I, _P, _I, _I, _I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64), _P],
     "dwb_cauchy_sym_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "dwb_s4_kernel_gen": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
     "dwb_fftconv_size": [_I, ctypes.POINTER(_I)],
     "dwb_fftconv_prepare": [_P, _P, _I, _I, _P, _P],
     "dwb_fftconv": [_P, _P, _P, _I64, _F, _F, _P, _P, _I, _I, _I, _P],
 }
+
+PROF_CATEGORIES = ["embed", "init_conv", "head", "pool", "fftconv_s0", "fftconv_s1", "fftconv_s2", "fftconv_s3",
+                   "mix_s0", "mix_s1", "mix_s2", "mix_s3", "wave_block"]
 
 _lib = None
 

@@ -118,6 +118,7 @@ struct dwb_plan {
     float *table_emb = nullptr, *table_part = nullptr, *table_t = nullptr;   // (T, .) per-step fc_t outputs
     int table_T = 0;
     cudaGraphExec_t graph_exec = nullptr;
+    cudaStream_t cap_stream = nullptr;   // capture happens on a plan-owned stream (the legacy default stream cannot capture)
     GraphKey graph_key;
     int64_t graph_nodes = 0;
 };
@@ -464,6 +465,37 @@ static int ensure_workspace(dwb_plan *p, int B, int L) {
     return DWB_OK;
 }
 
+// per-category device timing of one eager (non-graph) network evaluation: an event after every
+// launch; the interval since the previous event is charged to the launch's category
+struct Prof {
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> cat;
+    cudaStream_t st;
+    int begin() {
+        cudaEvent_t e;
+        DWB_CUDA(cudaEventCreate(&e));
+        DWB_CUDA(cudaEventRecord(e, st));
+        ev.push_back(e);
+        cat.push_back(-1);
+        return DWB_OK;
+    }
+    int mark(int c) {
+        cudaEvent_t e;
+        DWB_CUDA(cudaEventCreate(&e));
+        DWB_CUDA(cudaEventRecord(e, st));
+        ev.push_back(e);
+        cat.push_back(c);
+        return DWB_OK;
+    }
+};
+#define PROF(c) do { if (prof) TRY(prof->mark(c)); } while (0)
+
+static int stage_of(const dwb_plan *p, int l) {   // 0 = top stage, 1 = after first pool, ...
+    int s = 0, cur = p->cfg.L;
+    while (cur > l && s < p->cfg.n_pool) { cur /= p->cfg.pool[s]; ++s; }
+    return s;
+}
+
 struct StepUpdate {           // fused DDPM update in the head, or plain eps
     const float *x = nullptr, *noise = nullptr;
     float c1 = 0, sqrt_alpha = 1, sigma = 0;
@@ -471,17 +503,19 @@ struct StepUpdate {           // fused DDPM update in the head, or plain eps
 
 // one network evaluation; part = (rows, Mtot) fc_t outputs with batch stride psb (0 = shared row)
 static int run_network(dwb_plan *p, const float *x, const float *part, long long psb, const float *cond, int cond_batch,
-                       float *out, const StepUpdate *upd, int B, int L, cudaStream_t st) {
+                       float *out, const StepUpdate *upd, int B, int L, cudaStream_t st, Prof *prof = nullptr) {
     const dwb_config &c = p->cfg;
     HeadArgs h{};
     if (c.model == DWB_MODEL_SASHIMI) {
         TRY(init_conv_launch(x, p->init_w, p->init_b, B, c.d_model, L, p->bufs[0], p->stat_bufs[0], st));
         p->launches += 1;
+        PROF(DWB_PROF_INIT);
         int last = 0;
         for (auto &o : p->ops) {
             if (o.kind == OP_BLOCK) {
                 TRY(fftconv_launch(p->bufs[o.in_buf], p->stat_bufs[o.in_buf], part + o.part_off, psb, o.ln1_m, o.ln1_s,
                                    o.kf, p->g_buf, B, o.H, o.l, st));
+                PROF(DWB_PROF_FFTCONV0 + std::min(stage_of(p, o.l), 3));
                 MixArgs a{};
                 a.g = p->g_buf; a.x = p->bufs[o.in_buf];
                 a.skip = o.skip_buf >= 0 ? p->bufs[o.skip_buf] : nullptr;
@@ -493,6 +527,7 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
                 a.H = o.H; a.F = o.F; a.l = o.l;
                 TRY(mix_launch(a, B, st));
                 p->launches += 2;
+                PROF(DWB_PROF_MIX0 + std::min(stage_of(p, o.l), 3));
             } else {
                 PoolArgs a{};
                 a.x = p->bufs[o.in_buf];
@@ -502,6 +537,7 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
                 a.Hi = o.H; a.Ho = o.Ho; a.s = o.s; a.li = o.l;
                 TRY(o.kind == OP_DOWN ? down_pool_launch(a, B, st) : up_pool_launch(a, B, st));
                 p->launches += 1;
+                PROF(DWB_PROF_POOL);
             }
             last = o.out_buf;
         }
@@ -512,6 +548,7 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
         const int C = c.res_channels, S = c.skip_channels, N = c.num_res_layers;
         TRY(init_conv_launch(x, p->init_w, p->init_b, B, C, L, p->bufs[0], nullptr, st));
         p->launches += 1;
+        PROF(DWB_PROF_INIT);
         int cur = 0;
         for (int n = 0; n < N; ++n) {
             const WaveLayer &w = p->wl[n];
@@ -525,6 +562,7 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
             a.C = C; a.S = S; a.L = L; a.dilation = w.dilation;
             TRY(wave_block_launch(a, B, st));
             p->launches += 1;
+            PROF(DWB_PROF_WAVEBLOCK);
             cur ^= 1;
         }
         h.x = p->skip_acc; h.stats = nullptr;
@@ -536,6 +574,7 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
     if (upd) { h.upd_x = upd->x; h.noise = upd->noise; h.c1 = upd->c1; h.sqrt_alpha = upd->sqrt_alpha; h.sigma = upd->sigma; }
     TRY(head_launch(h, B, st));
     p->launches += 1;
+    PROF(DWB_PROF_HEAD);
     return DWB_OK;
 }
 
@@ -596,6 +635,7 @@ int dwb_plan_destroy(dwb_plan *p) {
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     for (auto &kv : p->tensors) cudaFree(kv.second.dev);
     for (void *d : p->owned) cudaFree(d);
     for (void *d : p->ws_owned) cudaFree(d);
@@ -696,7 +736,7 @@ int dwb_sample(dwb_plan *p, const float *x_T, const float *noise, const float *c
         p->table_T = T;
     }
     const size_t BL = (size_t)B * L;
-    auto body = [&]() -> int {
+    auto body = [&](cudaStream_t st) -> int {
         DWB_CUDA(cudaMemcpyAsync(out, x_T, BL * sizeof(float), cudaMemcpyDeviceToDevice, st));
         for (int t = T - 1; t >= 0; --t) {
             StepUpdate u;
@@ -707,14 +747,15 @@ int dwb_sample(dwb_plan *p, const float *x_T, const float *noise, const float *c
         }
         return DWB_OK;
     };
-    if (!use_graph) return body();
+    if (!use_graph) return body(st);
 
     if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    if (!p->cap_stream) DWB_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
     const int64_t before = p->launches;
-    DWB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = body();
+    DWB_CUDA(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = body(p->cap_stream);
     cudaGraph_t graph = nullptr;
-    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    cudaError_t e = cudaStreamEndCapture(p->cap_stream, &graph);
     if (rc != DWB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
     p->graph_nodes = p->launches - before;
@@ -725,6 +766,38 @@ int dwb_sample(dwb_plan *p, const float *x_T, const float *noise, const float *c
     p->graph_key = key;
     DWB_CUDA(cudaGraphLaunch(p->graph_exec, st));
     p->launches += p->graph_nodes;
+    return DWB_OK;
+}
+
+int dwb_plan_profile(dwb_plan *p, const float *x, const float *t, const float *cond, int cond_batch, float *eps, int B,
+                     int L, int iters, double *ms, int64_t *counts, void *stream) {
+    DWB_REQUIRE(p && x && t && eps && ms && counts && iters >= 1, DWB_ERR_INVALID, "dwb_plan_profile: bad arguments");
+    TRY(check_run(p, B, L, cond, cond_batch));
+    DWB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ensure_workspace(p, B, L));
+    const dwb_config &c = p->cfg;
+    for (int i = 0; i < DWB_PROF_NCAT; ++i) { ms[i] = 0; counts[i] = 0; }
+    for (int it = 0; it < iters; ++it) {
+        Prof prof;
+        prof.st = st;
+        int rc = prof.begin();
+        if (rc == DWB_OK) rc = embed_launch(t, B, c.embed_in, c.embed_mid, c.embed_out, p->eW1, p->eb1, p->eW2, p->eb2,
+                                            p->Wt_all, p->bt_all, p->Mtot, p->emb_buf, p->part_buf, st);
+        if (rc == DWB_OK) { p->launches += 2; rc = prof.mark(DWB_PROF_EMBED); }
+        if (rc == DWB_OK) rc = run_network(p, x, p->part_buf, p->Mtot, cond, cond_batch, eps, nullptr, B, L, st, &prof);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (rc == DWB_OK && e == cudaSuccess)
+            for (size_t i = 1; i < prof.ev.size(); ++i) {
+                float dt = 0.f;
+                cudaEventElapsedTime(&dt, prof.ev[i - 1], prof.ev[i]);
+                ms[prof.cat[i]] += dt;
+                counts[prof.cat[i]] += 1;
+            }
+        for (auto ev : prof.ev) cudaEventDestroy(ev);
+        if (rc != DWB_OK) return rc;
+        if (e != cudaSuccess) return cuda_fail(e, "profile sync", __FILE__, __LINE__);
+    }
     return DWB_OK;
 }
 

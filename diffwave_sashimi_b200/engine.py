@@ -250,6 +250,21 @@ class Engine:
                                    B, L, int(use_graph), stream_ptr(self.device)))
         return out
 
+    @torch.no_grad()
+    def profile(self, audio, diffusion_steps, mel_spec=None, iters=3):
+        """{category: (ms per forward, launches per forward)} from CUDA events around every launch."""
+        x = audio.to(self.device, torch.float32).contiguous()
+        B, _, L = x.shape
+        t = diffusion_steps.to(self.device, torch.float32).reshape(-1).contiguous()
+        cond, cb = self._cond(mel_spec, L)
+        eps = torch.empty_like(x)
+        n = len(_lib.PROF_CATEGORIES)
+        ms, cnt = (ctypes.c_double * n)(), (ctypes.c_int64 * n)()
+        with torch.cuda.device(self.device):
+            check(lib().dwb_plan_profile(self._plan, ptr(x), ptr(t), ptr(cond), cb, ptr(eps), B, L, iters, ms, cnt,
+                                         stream_ptr(self.device)))
+        return {c: (ms[i] / iters, cnt[i] // iters) for i, c in enumerate(_lib.PROF_CATEGORIES) if cnt[i]}
+
     # ---- introspection ------------------------------------------------------------------
     def launch_count(self):
         n = ctypes.c_int64(0)

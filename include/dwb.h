@@ -126,6 +126,18 @@ int dwb_plan_s4_kernel(dwb_plan *plan, int block, float *k_out, int64_t capacity
 /* algorithmic HBM bytes and flops of one forward per clip (SURVEY.md §8(d) formulas) */
 int dwb_plan_work(dwb_plan *plan, int L, double *bytes_per_clip_step, double *flops_per_clip_step);
 
+/* Device time per kernel category of `iters` eager forwards (CUDA events on `stream` after every
+ * launch; synchronises).  ms[c] = total milliseconds, counts[c] = launches, c < DWB_PROF_NCAT.
+ * FFTCONVs / MIXs: SaShiMi stage s (0 = top, L samples; 1, 2 = after each pool). */
+enum dwb_prof_category {
+    DWB_PROF_EMBED = 0, DWB_PROF_INIT = 1, DWB_PROF_HEAD = 2, DWB_PROF_POOL = 3,
+    DWB_PROF_FFTCONV0 = 4, DWB_PROF_FFTCONV1 = 5, DWB_PROF_FFTCONV2 = 6, DWB_PROF_FFTCONV3 = 7,
+    DWB_PROF_MIX0 = 8, DWB_PROF_MIX1 = 9, DWB_PROF_MIX2 = 10, DWB_PROF_MIX3 = 11,
+    DWB_PROF_WAVEBLOCK = 12, DWB_PROF_NCAT = 13
+};
+int dwb_plan_profile(dwb_plan *plan, const float *x, const float *t, const float *cond, int cond_batch,
+                     float *eps, int B, int L, int iters, double *ms, int64_t *counts, void *stream);
+
 /* ---- single ops (same kernels the plan uses; exported for tests and for callers that
  *      only want to replace one reference op) ------------------------------------------ */
 /* out[b,l] = sum_n v[b,n]/(z[l]-w[b,n]) + conj(v[b,n])/(z[l]-conj(w[b,n]))
