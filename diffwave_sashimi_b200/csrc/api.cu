@@ -6,6 +6,7 @@
 //   generate.py:51      net((x, t), mel_spec)                              -> dwb_forward
 //   generate.py:23-55   sampling()                                         -> dwb_sample
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <map>
 #include <string>
@@ -57,6 +58,8 @@ struct Op {
     float ln1_m = 0, ln1_s = 1, ln2_m = 0, ln2_s = 1;
     float *kf = nullptr, *k32 = nullptr;
     float *Wo_t = nullptr, *bo = nullptr, *W1_t = nullptr, *b1 = nullptr, *W2_t = nullptr, *b2 = nullptr;
+    uint4 *Wo_f[2] = {nullptr, nullptr}, *W1_f[2] = {nullptr, nullptr}, *W2_f[2] = {nullptr, nullptr};
+    bool mma = false;
     int F = 0;
     int part_off = 0;      // offset of this block's fc_t rows in the stacked embedding output
     int64_t cond_off = 0;  // float offset (per cond batch element) of this block's conditioning features
@@ -92,6 +95,7 @@ struct dwb_plan {
     std::map<std::string, Tensor> tensors;
     std::vector<void *> owned;
     int64_t launches = 0;
+    bool use_mma = true;           // DWB_MIX=simt in the environment selects the exact-fp32 SIMT channel mixing
 
     // embedding
     float *eW1 = nullptr, *eb1 = nullptr, *eW2 = nullptr, *eb2 = nullptr, *Wt_all = nullptr, *bt_all = nullptr;
@@ -382,6 +386,22 @@ static int finalize_sashimi(dwb_plan *p, cudaStream_t st) {
                 TRY(folded(p, o.prefix + "layer.output_linear.0", 2 * H, H, 1, false, &o.Wo_t, &o.bo, st));
                 TRY(folded(p, o.prefix + "ff.ff.0.conv", o.F, H, 1, true, &o.W1_t, &o.b1, st));
                 TRY(folded(p, o.prefix + "ff.ff.2.conv", H, o.F, 1, true, &o.W2_t, &o.b2, st));
+                o.mma = p->use_mma && mix_mma_supported(H, o.F, l);
+                if (o.mma) {
+                    auto pack = [&](const float *Wt, int M, int K, uint4 **f) -> int {
+                        for (int q = 0; q < 2; ++q) {
+                            void *d;
+                            TRY(dev_alloc(p, (size_t)M * K * 2, &d));
+                            f[q] = (uint4 *)d;
+                        }
+                        TRY(frag_pack(Wt, M, K, (uint32_t *)f[0], (uint32_t *)f[1], st));
+                        p->launches += 1;
+                        return DWB_OK;
+                    };
+                    TRY(pack(o.Wo_t, 2 * H, H, o.Wo_f));
+                    TRY(pack(o.W1_t, o.F, H, o.W1_f));
+                    TRY(pack(o.W2_t, H, o.F, o.W2_f));
+                }
                 o.part_off = part_off; part_off += H;
                 o.cond_off = cond_off; cond_off += (int64_t)H * l;
                 fc.push_back({o.prefix, H});
@@ -525,7 +545,9 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
                 a.ln2_m = o.ln2_m; a.ln2_s = o.ln2_s;
                 a.out = p->bufs[o.out_buf]; a.stats_out = p->stat_bufs[o.out_buf];
                 a.H = o.H; a.F = o.F; a.l = o.l;
-                TRY(mix_launch(a, B, st));
+                a.Wo_fh = o.Wo_f[0]; a.Wo_fl = o.Wo_f[1]; a.W1_fh = o.W1_f[0]; a.W1_fl = o.W1_f[1];
+                a.W2_fh = o.W2_f[0]; a.W2_fl = o.W2_f[1];
+                TRY(o.mma ? mix_mma_launch(a, B, st) : mix_launch(a, B, st));
                 p->launches += 2;
                 PROF(DWB_PROF_MIX0 + std::min(stage_of(p, o.l), 3));
             } else {
@@ -624,6 +646,7 @@ int dwb_plan_create(const dwb_config *cfg, int device, dwb_plan **out) {
     DWB_CUDA(cudaGetDeviceProperties(&prop, device));
     DWB_REQUIRE(prop.major == 10, DWB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libdwb is built for sm_100a only", device, prop.major, prop.minor);
     dwb_plan *p = new dwb_plan();
+    if (const char *e = getenv("DWB_MIX")) p->use_mma = std::string(e) != "simt";
     p->cfg = *cfg;
     p->device = device;
     *out = p;

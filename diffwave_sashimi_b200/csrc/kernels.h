@@ -13,6 +13,8 @@ struct MixArgs {
     const float *Wo_t, *bo;        // [H][2H], (2H)
     const float *W1_t, *b1;        // [H][F],  (F)
     const float *W2_t, *b2;        // [F][H],  (H)
+    // split-bf16 mma A fragments of the same weights (mix_mma.cu), or null
+    const uint4 *Wo_fh, *Wo_fl, *W1_fh, *W1_fl, *W2_fh, *W2_fl;
     float ln2_m, ln2_s;
     float *out, *stats_out;        // (B,H,l), (B,l,2)
     int H, F, l;
@@ -62,6 +64,9 @@ int embed_launch(const float *t, int rows, int E_in, int E_mid, int E_out, const
 int init_conv_launch(const float *x, const float *w, const float *bias, int B, int C, int l, float *out, float *stats,
                      cudaStream_t st);
 int mix_launch(const MixArgs &a, int B, cudaStream_t st);
+bool mix_mma_supported(int H, int F, int l);
+int mix_mma_launch(const MixArgs &a, int B, cudaStream_t st);
+int frag_pack(const float *Wt, int M, int K, uint32_t *fhi, uint32_t *flo, cudaStream_t st);
 int down_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
 int up_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
 int head_launch(const HeadArgs &a, int B, cudaStream_t st);

@@ -1,0 +1,340 @@
+// DiffWaveBlock channel mixing on tensor cores (split-bf16, fp32 accumulate).
+//
+// Same computation, tiling and epilogues as sashimi_mix_kernel (sashimi_kernels.cu):
+//   q = Wo g + bo ; y = q[:H] * sigmoid(q[H:]) (+cond) ; x1 = x + y
+//   x2 = x1 + W2 gelu(W1 LN2(x1) + b1) + b2 (+skip) ; stats(x2)
+// but the three channel contractions (12 H^2 flop per time step, ~27 GFLOP per clip-step at
+// d_model 64: 10x more than an fp32 SIMT pipe can do inside the HBM time of the block) run on
+// the tensor cores.  fp32 operands are split x = hi + lo into two bf16 halves and each product
+// is evaluated as hi*hi + lo*hi + hi*lo with fp32 accumulation (relative error ~2^-17 per
+// product, i.e. 1e-5 — the parity budget is 1e-3 and single-pass bf16/tf32 would consume all of
+// it).
+//
+// Layout: weights are pre-split and stored in mma.m16n8k16 A-fragment order at finalize
+// (one coalesced 16-byte load per lane per fragment, no shared-memory staging, no ldmatrix);
+// activations sit in shared memory as [k][t] bf16 (t contiguous, exactly how they stream in from
+// HBM) and reach the B fragments through ldmatrix.trans.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tile_gemm.cuh"
+
+namespace dwb {
+
+// ---------------------------------------------------------------------------------------
+// finalize: folded fp32 weight Wt [K][M] (transposed) -> hi / lo bf16 A fragments
+//   frag[((mt*KT + kt)*32 + lane)*4 + r]: r0={a0,a1} r1={a2,a3} r2={a4,a5} r3={a6,a7}
+// ---------------------------------------------------------------------------------------
+__global__ void frag_pack_kernel(const float *__restrict__ Wt, int M, int K, uint32_t *__restrict__ fhi,
+                                 uint32_t *__restrict__ flo) {
+    const int KT = K / 16;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one (mt, kt, lane, r)
+    const size_t total = (size_t)(M / 16) * KT * 32 * 4;
+    if (idx >= total) return;
+    const int r = idx & 3, lane = (idx >> 2) & 31;
+    const size_t tile = idx >> 7;
+    const int kt = tile % KT, mt = tile / KT;
+    const int g = lane >> 2, t = lane & 3;
+    const int m = mt * 16 + g + ((r & 1) ? 8 : 0);
+    const int k = kt * 16 + 2 * t + ((r & 2) ? 8 : 0);
+    const float w0 = Wt[(size_t)k * M + m], w1 = Wt[(size_t)(k + 1) * M + m];
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(w0 - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(w1 - __bfloat162float(h1));
+    fhi[idx] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    flo[idx] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
+int frag_pack(const float *Wt, int M, int K, uint32_t *fhi, uint32_t *flo, cudaStream_t st) {
+    DWB_REQUIRE(M % 16 == 0 && K % 16 == 0, DWB_ERR_INVALID, "frag_pack: M=%d K=%d must be multiples of 16", M, K);
+    const size_t total = (size_t)(M / 16) * (K / 16) * 128;
+    frag_pack_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(Wt, M, K, fhi, flo);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void *p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(a));
+}
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint4 &a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void split_store(__nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t i, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ void split_store2(__nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t i, float v0, float v1) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+    *reinterpret_cast<__nv_bfloat162 *>(hi + i) = __halves2bfloat162(h0, h1);
+    *reinterpret_cast<__nv_bfloat162 *>(lo + i) = __halves2bfloat162(
+        __float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+}
+
+// acc[i][n][:] += sum_k A[tile_i][k] * B[k][col0 + 8n ..]     (split-bf16, 3 MMAs per product)
+//   fhi/flo: A fragments of the whole weight; tiles[i]: m-tile indices this warp owns
+//   Bhi/Blo: smem [K][TTP] bf16; col0: first column of this warp
+template <int MT, int NT, int TTP>
+__device__ __forceinline__ void gemm_split_bf16(const uint4 *__restrict__ fhi, const uint4 *__restrict__ flo, int KT,
+                                                const int (&tiles)[MT], const __nv_bfloat16 *Bhi,
+                                                const __nv_bfloat16 *Blo, int col0, float (&acc)[MT][NT][4], int lane) {
+    static_assert(NT % 2 == 0, "n-tiles are loaded in pairs");
+    // ldmatrix.x4.trans lane addressing: lanes 0-7 k0..7 @n0, 8-15 k8..15 @n0, 16-23 k0..7 @n0+8, 24-31 k8..15 @n0+8
+    const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int lcol = (lane >> 4) * 8;
+    uint4 ah[MT], al[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        ah[i] = __ldg(fhi + ((size_t)tiles[i] * KT) * 32 + lane);
+        al[i] = __ldg(flo + ((size_t)tiles[i] * KT) * 32 + lane);
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        uint4 nh[MT], nl[MT];
+        const int kn = (kt + 1 < KT) ? kt + 1 : kt;      // prefetch the next k-step's weight fragments
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            nh[i] = __ldg(fhi + ((size_t)tiles[i] * KT + kn) * 32 + lane);
+            nl[i] = __ldg(flo + ((size_t)tiles[i] * KT + kn) * 32 + lane);
+        }
+        uint32_t bh[NT / 2][4], bl[NT / 2][4];
+        const size_t boff = (size_t)(kt * 16 + lrow) * TTP + col0 + lcol;
+#pragma unroll
+        for (int n2 = 0; n2 < NT / 2; ++n2) {
+            ldsm_x4_trans(bh[n2], Bhi + boff + n2 * 16);
+            ldsm_x4_trans(bl[n2], Blo + boff + n2 * 16);
+        }
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int n2 = 0; n2 < NT / 2; ++n2) {
+                mma_bf16(acc[i][2 * n2], ah[i], bh[n2][0], bh[n2][1]);
+                mma_bf16(acc[i][2 * n2 + 1], ah[i], bh[n2][2], bh[n2][3]);
+                mma_bf16(acc[i][2 * n2], al[i], bh[n2][0], bh[n2][1]);
+                mma_bf16(acc[i][2 * n2 + 1], al[i], bh[n2][2], bh[n2][3]);
+                mma_bf16(acc[i][2 * n2], ah[i], bl[n2][0], bl[n2][1]);
+                mma_bf16(acc[i][2 * n2 + 1], ah[i], bl[n2][2], bl[n2][3]);
+            }
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            ah[i] = nh[i];
+            al[i] = nl[i];
+        }
+    }
+}
+
+template <int MT, int NT>
+__device__ __forceinline__ void zero3(float (&acc)[MT][NT][4]) {
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][n][j] = 0.f;
+}
+
+// H: block width; FM: F / H; TT: time columns per CTA; WM x WN warps (WM*WN = 8)
+template <int H, int FM, int TT, int WM, int WN>
+struct MmaCfg {
+    static constexpr int F = FM * H;
+    static constexpr int TTP = TT + 8;                 // bf16 row pitch: odd multiple of 16 B
+    static constexpr int XS = TT + 4;                  // fp32 row pitch
+    static constexpr int NT = TT / 8 / WN;             // n-tiles per warp
+    static constexpr int PAIRS = H / 16 / WM;          // GLU tile pairs per warp (G1)
+    static constexpr int MT2 = F / 16 / WM;            // m-tiles per warp (G2)
+    static constexpr int MT3 = H / 16 / WM;            // m-tiles per warp (G3)
+    static constexpr size_t SMEM = (size_t)H * XS * 4            // X1 fp32
+                                   + (size_t)2 * H * TTP * 2      // g / z split
+                                   + (size_t)2 * F * TTP * 2      // hidden split
+                                   + (2 * MIX_THREADS + 2 * TT) * 4;
+    static_assert(WM * WN == 8 && PAIRS >= 1 && MT3 >= 1 && NT >= 2, "bad tiling");
+};
+
+template <int H, int FM, int TT, int WM, int WN>
+__global__ void __launch_bounds__(MIX_THREADS)
+sashimi_mix_mma_kernel(MixArgs a) {
+    using C = MmaCfg<H, FM, TT, WM, WN>;
+    constexpr int F = C::F, TTP = C::TTP, XS = C::XS, NT = C::NT;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float *X1 = reinterpret_cast<float *>(smraw);                                  // [H][XS]
+    __nv_bfloat16 *Ghi = reinterpret_cast<__nv_bfloat16 *>(X1 + (size_t)H * XS);   // [H][TTP]
+    __nv_bfloat16 *Glo = Ghi + (size_t)H * TTP;
+    __nv_bfloat16 *Hhi = Glo + (size_t)H * TTP;                                    // [F][TTP]
+    __nv_bfloat16 *Hlo = Hhi + (size_t)F * TTP;
+    float *scratch = reinterpret_cast<float *>(Hlo + (size_t)F * TTP);
+    float *stat_s = scratch + 2 * MIX_THREADS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % WM, wn = warp / WM;
+    const int col0 = wn * (TT / WN);
+    const int g = lane >> 2, tq = lane & 3;
+    const int b = blockIdx.y, t0 = blockIdx.x * TT, l = a.l;
+    const size_t boff = (size_t)b * H * l;
+
+    // ---- load g (split) and x (fp32); l and t0 are even so float2 accesses stay in range pairwise
+    for (int i = tid; i < H * (TT / 2); i += MIX_THREADS) {
+        const int r = i / (TT / 2), c = 2 * (i - r * (TT / 2));
+        float2 gv = make_float2(0.f, 0.f), xv = make_float2(0.f, 0.f);
+        const size_t gi = boff + (size_t)r * l + t0 + c;
+        if (t0 + c + 1 < l) {
+            gv = *reinterpret_cast<const float2 *>(a.g + gi);
+            xv = *reinterpret_cast<const float2 *>(a.x + gi);
+        } else if (t0 + c < l) {
+            gv.x = a.g[gi];
+            xv.x = a.x[gi];
+        }
+        split_store2(Ghi, Glo, (size_t)r * TTP + c, gv.x, gv.y);
+        *reinterpret_cast<float2 *>(X1 + (size_t)r * XS + c) = xv;
+    }
+    __syncthreads();
+
+    // ---- G1: output_linear + GLU + residual -> X1
+    constexpr int PG = C::PAIRS > 2 ? 2 : C::PAIRS;   // at most 4 m-tiles of accumulators live at once
+    for (int grp = 0; grp < C::PAIRS / PG; ++grp) {
+        constexpr int MT = 2 * PG;
+        int tiles[MT];
+#pragma unroll
+        for (int p = 0; p < PG; ++p) {
+            tiles[2 * p] = wm * C::PAIRS + grp * PG + p;
+            tiles[2 * p + 1] = tiles[2 * p] + H / 16;
+        }
+        float acc[MT][NT][4];
+        zero3(acc);
+        gemm_split_bf16<MT, NT, TTP>(a.Wo_fh, a.Wo_fl, H / 16, tiles, Ghi, Glo, col0, acc, lane);
+#pragma unroll
+        for (int p = 0; p < PG; ++p)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int h = tiles[2 * p] * 16 + g + half * 8;
+                const float ba = a.bo[h], bb = a.bo[H + h];
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int c = col0 + n * 8 + 2 * tq + j;
+                        float y = (acc[2 * p][n][half * 2 + j] + ba) * sigmoidf_(acc[2 * p + 1][n][half * 2 + j] + bb);
+                        if (a.cond && t0 + c < l) y += a.cond[((size_t)(a.cond_stride_b ? b : 0) * H + h) * l + t0 + c];
+                        X1[(size_t)h * XS + c] += y;
+                    }
+            }
+    }
+    __syncthreads();
+
+    // ---- LN2 -> z (split) over the g tile
+    tile_col_stats<TT>(X1, H, scratch, stat_s, tid);
+    for (int i = tid; i < H * (TT / 2); i += MIX_THREADS) {
+        const int r = i / (TT / 2), c = 2 * (i - r * (TT / 2));
+        const float2 xv = *reinterpret_cast<const float2 *>(X1 + (size_t)r * XS + c);
+        const float z0 = (a.ln2_s * stat_s[2 * c + 1]) * (xv.x - stat_s[2 * c] + a.ln2_m);
+        const float z1 = (a.ln2_s * stat_s[2 * c + 3]) * (xv.y - stat_s[2 * c + 2] + a.ln2_m);
+        split_store2(Ghi, Glo, (size_t)r * TTP + c, z0, z1);
+    }
+    __syncthreads();
+
+    // ---- G2: hidden = gelu(W1 z + b1) (split)
+    constexpr int G2 = C::MT2 > 4 ? 4 : C::MT2;
+    for (int grp = 0; grp < C::MT2 / G2; ++grp) {
+        constexpr int MT = G2;
+        int tiles[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) tiles[i] = wm * C::MT2 + grp * G2 + i;
+        float acc[MT][NT][4];
+        zero3(acc);
+        gemm_split_bf16<MT, NT, TTP>(a.W1_fh, a.W1_fl, H / 16, tiles, Ghi, Glo, col0, acc, lane);
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int m = tiles[i] * 16 + g + half * 8;
+                const float bv = a.b1[m];
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const int c = col0 + n * 8 + 2 * tq;
+                    split_store2(Hhi, Hlo, (size_t)m * TTP + c, gelu_erf(acc[i][n][half * 2] + bv),
+                                 gelu_erf(acc[i][n][half * 2 + 1] + bv));
+                }
+            }
+    }
+    __syncthreads();
+
+    // ---- G3: x2 = x1 + W2 hidden + b2 (+skip) -> X1 in place
+    constexpr int G3 = C::MT3 > 4 ? 4 : C::MT3;
+    for (int grp = 0; grp < C::MT3 / G3; ++grp) {
+        constexpr int MT = G3;
+        int tiles[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) tiles[i] = wm * C::MT3 + grp * G3 + i;
+        float acc[MT][NT][4];
+        zero3(acc);
+        gemm_split_bf16<MT, NT, TTP>(a.W2_fh, a.W2_fl, F / 16, tiles, Hhi, Hlo, col0, acc, lane);
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int h = tiles[i] * 16 + g + half * 8;
+                const float bv = a.b2[h];
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int c = col0 + n * 8 + 2 * tq + j;
+                        float v = X1[(size_t)h * XS + c] + acc[i][n][half * 2 + j] + bv;
+                        if (a.skip && t0 + c < l) v += a.skip[boff + (size_t)h * l + t0 + c];
+                        X1[(size_t)h * XS + c] = v;
+                    }
+            }
+    }
+    __syncthreads();
+
+    // ---- statistics for the next norm, store
+    tile_col_stats<TT>(X1, H, scratch, stat_s, tid);
+    for (int i = tid; i < H * (TT / 2); i += MIX_THREADS) {
+        const int r = i / (TT / 2), c = 2 * (i - r * (TT / 2));
+        const float2 v = *reinterpret_cast<const float2 *>(X1 + (size_t)r * XS + c);
+        const size_t gi = boff + (size_t)r * l + t0 + c;
+        if (t0 + c + 1 < l) *reinterpret_cast<float2 *>(a.out + gi) = v;
+        else if (t0 + c < l) a.out[gi] = v.x;
+    }
+    if (tid < TT && t0 + tid < l) {
+        a.stats_out[((size_t)b * l + t0 + tid) * 2] = stat_s[2 * tid];
+        a.stats_out[((size_t)b * l + t0 + tid) * 2 + 1] = stat_s[2 * tid + 1];
+    }
+}
+
+template <int H, int FM, int TT, int WM, int WN>
+static int launch_mma(const MixArgs &a, int B, cudaStream_t st) {
+    using C = MmaCfg<H, FM, TT, WM, WN>;
+    auto k = sashimi_mix_mma_kernel<H, FM, TT, WM, WN>;
+    static_assert(C::SMEM <= 227 * 1024, "tile does not fit shared memory");
+    if (C::SMEM > 48 * 1024) DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    dim3 grid(ceil_div(a.l, TT), B);
+    k<<<grid, MIX_THREADS, C::SMEM, st>>>(a);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+bool mix_mma_supported(int H, int F, int l) {
+    return F == 2 * H && (l % 2 == 0) && (H == 64 || H == 128 || H == 256 || H == 512);
+}
+
+int mix_mma_launch(const MixArgs &a, int B, cudaStream_t st) {
+    switch (a.H) {
+        case 64: return launch_mma<64, 2, 64, 4, 2>(a, B, st);
+        case 128: return launch_mma<128, 2, 64, 8, 1>(a, B, st);
+        case 256: return launch_mma<256, 2, 32, 8, 1>(a, B, st);
+        case 512: return launch_mma<512, 2, 16, 8, 1>(a, B, st);
+    }
+    set_error("mix_mma: H=%d unsupported", a.H);
+    return DWB_ERR_UNSUPPORTED;
+}
+
+}  // namespace dwb

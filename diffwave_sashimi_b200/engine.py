@@ -213,7 +213,11 @@ class Engine:
     # ---- hot path -----------------------------------------------------------------------
     def _cond(self, mel, L):
         if mel is None:
+            if not self._c.unconditional:
+                raise RuntimeError("conditional model called without mel_spec")
             return None, 0
+        if self._c.unconditional:
+            raise RuntimeError("mel_spec passed to an unconditional model (models/sashimi.py:161 asserts the same)")
         return self.cond_features(mel, L), mel.shape[0]
 
     @torch.no_grad()

@@ -142,6 +142,32 @@ def test_baseline_size_vs_oracle_fp64(dwb, name, B):
     assert e2 < TOL and em < TOL
 
 
+@pytest.mark.parametrize("d,L,B,pool", [(64, 1024, 3, [4, 4]), (128, 512, 2, [4, 4]), (64, 192, 2, [2, 2])])
+def test_tensor_core_mixing_vs_oracle_fp64(dwb, d, L, B, pool, monkeypatch):
+    """Widths 64..512 take the split-bf16 mma path (mix_mma.cu); short sequences keep the fp64 oracle
+    cheap.  The exact-fp32 SIMT path (DWB_MIX=simt) must agree with it far inside the tolerance."""
+    from oracle.refshim import MODEL_CFGS
+    cfg = dict(MODEL_CFGS["unet_d64"], d_model=d, L=L, n_layers=2, pool=pool)
+    sd = dwb.init.seeded_state_dict(cfg, seed=5)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, 1, L, generator=g)
+    t = torch.tensor([[100.0], [3.0], [57.0]])[:B]
+    net = _model(dwb, cfg, sd)
+    with torch.no_grad():
+        eps = net((x.cuda(), t.cuda())).cpu()
+    sd_after = {k: v.cpu() for k, v in net.state_dict().items()}
+    ref = O.forward(cfg, sd_after, x, t)
+    e2, em = rel_l2(eps, ref), rel_max(eps, ref)
+    monkeypatch.setenv("DWB_MIX", "simt")
+    net2 = _model(dwb, cfg, sd_after)
+    with torch.no_grad():
+        eps2 = net2((x.cuda(), t.cuda())).cpu()
+    monkeypatch.delenv("DWB_MIX")
+    s2 = rel_l2(eps2, ref)
+    print(f"d={d} L={L}: mma rel_l2 {e2:.2e} rel_max {em:.2e}; simt rel_l2 {s2:.2e}")
+    assert e2 < 1e-4 and em < 1e-4 and s2 < 2e-5
+
+
 def test_batch_elements_are_independent(dwb):
     from oracle.refshim import MODEL_CFGS
     cfg = dict(MODEL_CFGS["unet_d64"])
