@@ -65,6 +65,7 @@ struct Op {
     int64_t cond_off = 0;  // float offset (per cond batch element) of this block's conditioning features
     // pool weights
     float *Wp_t = nullptr, *bp = nullptr;
+    uint4 *Wp_f[2] = {nullptr, nullptr};
 };
 
 struct WaveLayer {
@@ -405,10 +406,20 @@ static int finalize_sashimi(dwb_plan *p, cudaStream_t st) {
                 o.part_off = part_off; part_off += H;
                 o.cond_off = cond_off; cond_off += (int64_t)H * l;
                 fc.push_back({o.prefix, H});
-            } else if (o.kind == OP_DOWN) {
-                TRY(folded(p, o.prefix + "linear.conv", o.Ho, o.H * o.s, 1, true, &o.Wp_t, &o.bp, st));
             } else {
-                TRY(folded(p, o.prefix + "linear.conv", o.Ho * o.s, o.H, 1, true, &o.Wp_t, &o.bp, st));
+                const bool up = o.kind == OP_UP;
+                const int M = up ? o.Ho * o.s : o.Ho, K = up ? o.H : o.H * o.s;
+                TRY(folded(p, o.prefix + "linear.conv", M, K, 1, true, &o.Wp_t, &o.bp, st));
+                o.mma = p->use_mma && pool_mma_supported(o.H, o.Ho, o.s, up);
+                if (o.mma) {
+                    for (int q = 0; q < 2; ++q) {
+                        void *d;
+                        TRY(dev_alloc(p, (size_t)M * K * 2, &d));
+                        o.Wp_f[q] = (uint4 *)d;
+                    }
+                    TRY(frag_pack(o.Wp_t, M, K, (uint32_t *)o.Wp_f[0], (uint32_t *)o.Wp_f[1], st));
+                    p->launches += 1;
+                }
             }
             return DWB_OK;
         };
@@ -557,7 +568,9 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
                 a.W_t = o.Wp_t; a.bias = o.bp;
                 a.out = p->bufs[o.out_buf]; a.stats_out = p->stat_bufs[o.out_buf];
                 a.Hi = o.H; a.Ho = o.Ho; a.s = o.s; a.li = o.l;
-                TRY(o.kind == OP_DOWN ? down_pool_launch(a, B, st) : up_pool_launch(a, B, st));
+                a.W_fh = o.Wp_f[0]; a.W_fl = o.Wp_f[1];
+                if (o.mma) TRY(o.kind == OP_DOWN ? down_pool_mma_launch(a, B, st) : up_pool_mma_launch(a, B, st));
+                else TRY(o.kind == OP_DOWN ? down_pool_launch(a, B, st) : up_pool_launch(a, B, st));
                 p->launches += 1;
                 PROF(DWB_PROF_POOL);
             }

@@ -24,6 +24,7 @@ struct PoolArgs {
     const float *x;                // (B,Hi,li)
     const float *skip;             // up only: (B,Ho,li*s) or null
     const float *W_t, *bias;       // down: [Hi*s][Ho]; up: [Hi][Ho*s]
+    const uint4 *W_fh, *W_fl;      // split-bf16 mma A fragments, or null
     float *out, *stats_out;
     int Hi, Ho, s, li;
 };
@@ -66,6 +67,9 @@ int init_conv_launch(const float *x, const float *w, const float *bias, int B, i
 int mix_launch(const MixArgs &a, int B, cudaStream_t st);
 bool mix_mma_supported(int H, int F, int l);
 int mix_mma_launch(const MixArgs &a, int B, cudaStream_t st);
+bool pool_mma_supported(int Hi, int Ho, int s, bool up);
+int down_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st);
+int up_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st);
 int frag_pack(const float *Wt, int M, int K, uint32_t *fhi, uint32_t *flo, cudaStream_t st);
 int down_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
 int up_pool_launch(const PoolArgs &a, int B, cudaStream_t st);

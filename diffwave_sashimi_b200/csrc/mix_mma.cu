@@ -337,4 +337,137 @@ int mix_mma_launch(const MixArgs &a, int B, cudaStream_t st) {
     return DWB_ERR_UNSUPPORTED;
 }
 
+// ---------------------------------------------------------------------------------------
+// pools on the same split-bf16 path                               (models/sashimi.py:23-58)
+// ---------------------------------------------------------------------------------------
+constexpr int POOL_TT = 32;
+
+// down(s): x'[h*s+j][c] = x[b, h, (t0+c)*s + j];  out = W x' + bias  (K = Hi*s -> Ho), + stats
+__global__ void __launch_bounds__(MIX_THREADS)
+down_pool_mma_kernel(PoolArgs a) {
+    constexpr int TT = POOL_TT, TTP = TT + 8, XS = TT + 4, NT = TT / 8;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int Hi = a.Hi, Ho = a.Ho, s = a.s, li = a.li, lo = li / s, K = Hi * s;
+    float *Os = reinterpret_cast<float *>(smraw);                                  // [Ho][XS]
+    __nv_bfloat16 *Bhi = reinterpret_cast<__nv_bfloat16 *>(Os + (size_t)Ho * XS);  // [K][TTP]
+    __nv_bfloat16 *Blo = Bhi + (size_t)K * TTP;
+    float *scratch = reinterpret_cast<float *>(Blo + (size_t)K * TTP);
+    float *stat_s = scratch + 2 * MIX_THREADS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    for (int i = tid; i < Hi * TT * s; i += MIX_THREADS) {
+        const int h = i / (TT * s), r = i - h * (TT * s);    // r = c*s + j: consecutive input samples
+        const int c = r / s, j = r - c * s;
+        const float v = (t0 + c < lo) ? a.x[((size_t)b * Hi + h) * li + (size_t)t0 * s + r] : 0.f;
+        split_store(Bhi, Blo, (size_t)(h * s + j) * TTP + c, v);
+    }
+    __syncthreads();
+    for (int mt = warp; mt < Ho / 16; mt += MIX_THREADS / 32) {
+        int tiles[1] = {mt};
+        float acc[1][NT][4];
+        zero3(acc);
+        gemm_split_bf16<1, NT, TTP>(a.W_fh, a.W_fl, K / 16, tiles, Bhi, Blo, 0, acc, lane);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int m = mt * 16 + g + half * 8;
+            const float bv = a.bias[m];
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) Os[(size_t)m * XS + n * 8 + 2 * tq + j] = acc[0][n][half * 2 + j] + bv;
+        }
+    }
+    __syncthreads();
+    tile_col_stats<TT>(Os, Ho, scratch, stat_s, tid);
+    for (int i = tid; i < Ho * TT; i += MIX_THREADS) {
+        const int r = i / TT, c = i - r * TT;
+        if (t0 + c < lo) a.out[((size_t)b * Ho + r) * lo + t0 + c] = Os[(size_t)r * XS + c];
+    }
+    if (tid < TT && t0 + tid < lo) {
+        a.stats_out[((size_t)b * lo + t0 + tid) * 2] = stat_s[2 * tid];
+        a.stats_out[((size_t)b * lo + t0 + tid) * 2 + 1] = stat_s[2 * tid + 1];
+    }
+}
+
+// up(s): y = W x + bias (Hi -> Ho*s);  out[b, h, (t0+c)*s + j] = y[h*s+j][c] (+ skip), + stats
+template <int S>
+__global__ void __launch_bounds__(MIX_THREADS)
+up_pool_mma_kernel(PoolArgs a) {
+    constexpr int TT = 16, TTP = TT + 8, NT = TT / 8, TTO = TT * S, XSO = TTO + 4;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int Hi = a.Hi, Ho = a.Ho, li = a.li, lo = li * S, M = Ho * S;
+    float *Os = reinterpret_cast<float *>(smraw);                                   // [Ho][XSO]
+    __nv_bfloat16 *Bhi = reinterpret_cast<__nv_bfloat16 *>(Os + (size_t)Ho * XSO);  // [Hi][TTP]
+    __nv_bfloat16 *Blo = Bhi + (size_t)Hi * TTP;
+    float *scratch = reinterpret_cast<float *>(Blo + (size_t)Hi * TTP);
+    float *stat_s = scratch + 2 * MIX_THREADS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    for (int i = tid; i < Hi * TT; i += MIX_THREADS) {
+        const int r = i / TT, c = i - r * TT;
+        split_store(Bhi, Blo, (size_t)r * TTP + c, (t0 + c < li) ? a.x[((size_t)b * Hi + r) * li + t0 + c] : 0.f);
+    }
+    __syncthreads();
+    for (int mt = warp; mt < M / 16; mt += MIX_THREADS / 32) {
+        int tiles[1] = {mt};
+        float acc[1][NT][4];
+        zero3(acc);
+        gemm_split_bf16<1, NT, TTP>(a.W_fh, a.W_fl, Hi / 16, tiles, Bhi, Blo, 0, acc, lane);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int m = mt * 16 + g + half * 8;
+            const int h = m / S, j = m - h * S;
+            const float bv = a.bias[m];
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) Os[(size_t)h * XSO + (n * 8 + 2 * tq + jj) * S + j] = acc[0][n][half * 2 + jj] + bv;
+        }
+    }
+    __syncthreads();
+    if (a.skip) {
+        for (int i = tid; i < Ho * TTO; i += MIX_THREADS) {
+            const int r = i / TTO, c = i - r * TTO;
+            if (t0 * S + c < lo) Os[(size_t)r * XSO + c] += a.skip[((size_t)b * Ho + r) * lo + (size_t)t0 * S + c];
+        }
+        __syncthreads();
+    }
+    tile_col_stats<TTO>(Os, Ho, scratch, stat_s, tid);
+    for (int i = tid; i < Ho * TTO; i += MIX_THREADS) {
+        const int r = i / TTO, c = i - r * TTO;
+        if (t0 * S + c < lo) a.out[((size_t)b * Ho + r) * lo + (size_t)t0 * S + c] = Os[(size_t)r * XSO + c];
+    }
+    if (tid < TTO && t0 * S + tid < lo) {
+        a.stats_out[((size_t)b * lo + (size_t)t0 * S + tid) * 2] = stat_s[2 * tid];
+        a.stats_out[((size_t)b * lo + (size_t)t0 * S + tid) * 2 + 1] = stat_s[2 * tid + 1];
+    }
+}
+
+bool pool_mma_supported(int Hi, int Ho, int s, bool up) {
+    if (up) return (s == 2 || s == 4) && Hi % 16 == 0 && (Ho * s) % 16 == 0;
+    return (Hi * s) % 16 == 0 && Ho % 16 == 0;
+}
+
+template <typename KernelT>
+static int launch_pool(KernelT k, const PoolArgs &a, dim3 grid, size_t sm, cudaStream_t st) {
+    DWB_REQUIRE(sm <= 227 * 1024, DWB_ERR_UNSUPPORTED, "pool tile needs %zu B of shared memory", sm);
+    if (sm > 48 * 1024) DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k<<<grid, MIX_THREADS, sm, st>>>(a);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+int down_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st) {
+    constexpr int TT = POOL_TT;
+    const size_t sm = (size_t)a.Ho * (TT + 4) * 4 + (size_t)2 * a.Hi * a.s * (TT + 8) * 2 + (2 * MIX_THREADS + 2 * TT) * 4;
+    return launch_pool(down_pool_mma_kernel, a, dim3(ceil_div(a.li / a.s, TT), B), sm, st);
+}
+
+int up_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st) {
+    constexpr int TT = 16;
+    const size_t sm = (size_t)a.Ho * (TT * a.s + 4) * 4 + (size_t)2 * a.Hi * (TT + 8) * 2 + (2 * MIX_THREADS + 2 * TT * a.s) * 4;
+    const dim3 grid(ceil_div(a.li, TT), B);
+    return a.s == 2 ? launch_pool(up_pool_mma_kernel<2>, a, grid, sm, st) : launch_pool(up_pool_mma_kernel<4>, a, grid, sm, st);
+}
+
 }  // namespace dwb
