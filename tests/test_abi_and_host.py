@@ -172,3 +172,54 @@ def test_fresh_model_outputs_exactly_zero_like_reference(dwb):
     net = dwb.construct_model(dict(refshim.MODEL_CFGS["wnet_h128_d30"]))
     assert float(net.final_conv[2].conv.weight.abs().max()) == 0.0
     assert float(net.final_conv[2].conv.bias.abs().max()) == 0.0
+
+
+def test_run_directory_names_match_reference_exp_tree(dwb, tmp_path):
+    # exp/ directory names shipped by the reference pin these formats (utils.py:96-116)
+    from diffwave_sashimi_b200 import experiment as E
+    from diffwave_sashimi_b200.config import compose
+    cfg = compose(os.path.join(ROOT, "configs"), overrides=["model=sashimi_small"])
+    assert E.run_id(None, cfg.model, cfg.diffusion, cfg.dataset) == "unet_d64_n6_pool_2_expand2_ff2_T200_betaT0.02_uncond"
+    cfg = compose(os.path.join(ROOT, "configs"), overrides=["model=wavenet"])
+    assert E.run_id(None, cfg.model, cfg.diffusion, cfg.dataset) == "wnet_h256_d36_T200_betaT0.02_uncond"
+    cfg = compose(os.path.join(ROOT, "configs"), overrides=["experiment=ljspeech", "model.d_model=32"])
+    assert E.run_id(None, cfg.model, cfg.diffusion, cfg.dataset) == "unet_d32_n6_pool_2_expand2_ff2_T50_betaT0.05_L16000_hop256_cond"
+    assert E.run_id("run7", cfg.model, cfg.diffusion, cfg.dataset).startswith("run7_unet_d32")
+    if refshim.available():
+        have = set(os.listdir(os.path.join(refshim.REF_ROOT, "exp")))
+        assert "unet_d64_n6_pool_2_expand2_ff2_T200_betaT0.02_uncond" in have
+        assert "wnet_h256_d36_T200_betaT0.02_uncond" in have
+
+
+def test_config_composition_matches_reference_files(dwb):
+    from diffwave_sashimi_b200.config import compose
+    cfg = compose(os.path.join(ROOT, "configs"))
+    assert cfg.model._name_ == "sashimi" and cfg.model.d_model == 128 and cfg.model.L == 16000   # ${dataset.segment_length}
+    assert cfg.diffusion == dict(T=200, beta_0=0.0001, beta_T=0.02, beta=None)
+    assert cfg.generate.n_samples == 16 and cfg.generate.mel_name is None
+    lj = compose(os.path.join(ROOT, "configs"), overrides=["experiment=ljspeech", "generate.n_samples=3"])
+    assert lj.model.unconditional is False and lj.model.mel_upsample == [16, 16] and lj.dataset.hop_length == 256
+    assert lj.diffusion.T == 50 and lj.generate.n_samples == 3 and lj.generate.mel_name == "LJ001-0001"
+    if refshim.available():
+        import yaml
+        for rel in ("model/sashimi.yaml", "model/sashimi_small.yaml", "model/wavenet.yaml", "model/wavenet_small.yaml",
+                    "dataset/sc09.yaml", "dataset/ljspeech.yaml", "experiment/sc09.yaml", "experiment/ljspeech.yaml"):
+            ours = yaml.safe_load(open(os.path.join(ROOT, "configs", rel)))
+            ref = yaml.safe_load(open(os.path.join(refshim.REF_ROOT, "configs", rel)))
+            assert ours == ref, rel
+
+
+def test_checkpoint_discovery_and_averaging(dwb, tmp_path):
+    from diffwave_sashimi_b200 import experiment as E
+    d = tmp_path / "checkpoint"
+    d.mkdir()
+    for it, v in ((1000, 1.0), (2000, 3.0), (3000, 5.0)):
+        torch.save({"model_state_dict": {"w": torch.full((2,), v)}, "optimizer_state_dict": {}}, d / f"{it}.pkl")
+    (d / "notes.txt").write_text("x")
+    assert E.find_max_epoch(str(d)) == 3000
+    it, sd = E.load_state_dict(str(d), "max")
+    assert it == 3000 and float(sd["w"][0]) == 5.0
+    it, sd = E.load_state_dict(str(d), 3000, ckpt_smooth=1000)      # mean of 2000, 3000
+    assert float(sd["w"][0]) == 4.0
+    with pytest.raises(FileNotFoundError):
+        E.load_state_dict(str(d), 4000)
