@@ -41,6 +41,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
     // torch.nn.functional.gelu (erf form): 0.5 x (1 + erf(x / sqrt 2))
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+// GELU (erf form) through erfc(|x|/sqrt2) = t(a1 + t(a2 + ...)) exp(-x^2/2), t = 1/(1 + p|x|/sqrt2)
+// (Abramowitz-Stegun 7.1.26): branch free, 2 MUFU + ~12 FP32 ops instead of erff's ~40 with
+// divergent ranges.  |error| <= 3.4e-7 absolute over the real line (checked against float64 erf),
+// far inside the 1e-3 parity budget; the exact-fp32 SIMT path keeps erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(t, p, 1.421413741f);
+    p = fmaf(t, p, -0.284496736f);
+    p = fmaf(t, p, 0.254829592f);
+    const float e = (p * t) * __expf(-z * z);       // erfc(|x|/sqrt 2)
+    const float h = 0.5f * x * e;                    // x < 0: 0.5 x (1 + erf) = 0.5 x erfc
+    return x >= 0.f ? x - h : h;
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {

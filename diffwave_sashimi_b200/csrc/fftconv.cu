@@ -50,6 +50,20 @@ struct Radix<1, INV> {
     static __device__ __forceinline__ void run(float2 *) {}
 };
 
+// w[q] = w1^q, q = 1..R-1, by squaring/products of depth log2 R (a serial chain w *= w1 puts R-1
+// dependent complex multiplies on the critical path of every butterfly)
+template <int R>
+__device__ __forceinline__ void twiddle_powers(float2 w1, float2 (&w)[R]) {
+    w[0] = make_float2(1.f, 0.f);
+    if (R > 1) w[1] = w1;
+#pragma unroll
+    for (int q = 2; q < R; ++q) {
+        int hb = 1;
+        while (hb * 2 <= q) hb *= 2;
+        w[q] = (q == hb) ? cmul(w[q / 2], w[q / 2]) : cmul(w[hb], w[q - hb]);
+    }
+}
+
 // ---- one in-place pass over the shared array ---------------------------------------------
 // forward (DIF): u_q = sum_p x[j + p sub] w_R^{pq};  store u_q W_S^{jq} at j + q sub
 // inverse (DIT): y_q = s[j + q sub] conj(W_S^{jq});  x_p = sum_q y_q w_R^{-pq} at j + p sub
@@ -64,27 +78,20 @@ __device__ __forceinline__ void fft_pass(float2 *s, const float2 *__restrict__ t
         float2 x[R];
 #pragma unroll
         for (int p = 0; p < R; ++p) x[p] = s[fft_pad(base + (p << log2sub))];
-        float2 w1 = make_float2(1.f, 0.f);
+        float2 w[R];
         if (log2sub > 0) {
-            w1 = tw[(2 * j) << (LOG2M - log2S)];   // W_S^j = W_n^{2 j M / S}
+            float2 w1 = tw[j << (LOG2M - log2S)];   // W_S^j = W_M^{j M / S}, shared-memory table
             if (INV) w1.y = -w1.y;
+            twiddle_powers<R>(w1, w);
         }
         if (INV && log2sub > 0) {
-            float2 w = w1;
 #pragma unroll
-            for (int q = 1; q < R; ++q) {
-                x[q] = cmul(x[q], w);
-                w = cmul(w, w1);
-            }
+            for (int q = 1; q < R; ++q) x[q] = cmul(x[q], w[q]);
         }
         Radix<R, INV>::run(x);
         if (!INV && log2sub > 0) {
-            float2 w = w1;
 #pragma unroll
-            for (int q = 1; q < R; ++q) {
-                x[q] = cmul(x[q], w);
-                w = cmul(w, w1);
-            }
+            for (int q = 1; q < R; ++q) x[q] = cmul(x[q], w[q]);
         }
 #pragma unroll
         for (int p = 0; p < R; ++p) s[fft_pad(base + (p << log2sub))] = x[p];
@@ -108,7 +115,9 @@ template <int LOG2M>
 struct FftCfg {
     static constexpr int M = 1 << LOG2M;
     static constexpr int NT = (M / 16 > 512) ? 512 : ((M / 16 < 64) ? 64 : M / 16);
-    static constexpr int SMEM = (M + M / 16 + 1) * (int)sizeof(float2);
+    static constexpr int NTW = M / 16;                         // W_M^j, j < M/16: enough for every twiddled pass
+    static constexpr int SDATA = M + M / 16 + 1;               // padded data array (float2)
+    static constexpr int SMEM = (SDATA + NTW) * (int)sizeof(float2);
 };
 
 template <int LOG2M>
@@ -119,7 +128,9 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
                float *__restrict__ g, int B, int H, int l) {
     constexpr int M = 1 << LOG2M, NT = FftCfg<LOG2M>::NT;
     extern __shared__ float2 s[];
+    float2 *stw = s + FftCfg<LOG2M>::SDATA;
     const int tid = threadIdx.x;
+    for (int j = tid; j < FftCfg<LOG2M>::NTW; j += NT) stw[j] = tw[2 * j];
     const int row = blockIdx.x;
     const int h = row / B, b = row - h * B;
     const size_t off = ((size_t)b * H + h) * (size_t)l;
@@ -130,20 +141,44 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
 
     // ---- prologue: y = (ln_s rstd)(x - mean + ln_m) + part_t, packed z[j] = y[2j] + i y[2j+1]
     const bool vec = ((l & 1) == 0);
+    if (vec && st) {
+        // hot case: batches of 4 independent (x, stats) loads in flight per thread
+        const int half = l >> 1;
+        const float2 *x2 = reinterpret_cast<const float2 *>(xr);
+        const float4 *s4 = reinterpret_cast<const float4 *>(st);
+        for (int j0 = tid; j0 < M; j0 += 4 * NT) {
+            float2 xv[4];
+            float4 sv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * NT;
+                if (j < half) {
+                    xv[u] = x2[j];
+                    sv[u] = s4[j];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * NT;
+                if (j < M) {
+                    float2 v = make_float2(0.f, 0.f);
+                    if (j < half) {
+                        v.x = (ln_s * sv[u].y) * (xv[u].x - sv[u].x + ln_m) + pt;
+                        v.y = (ln_s * sv[u].w) * (xv[u].y - sv[u].z + ln_m) + pt;
+                    }
+                    s[fft_pad(j)] = v;
+                }
+            }
+        }
+    } else
     for (int j = tid; j < M; j += NT) {
         float2 v = make_float2(0.f, 0.f);
         const int t0 = 2 * j;
         if (vec) {
             if (t0 < l) {
                 const float2 xv = *reinterpret_cast<const float2 *>(xr + t0);
-                if (st) {
-                    const float4 sv = *reinterpret_cast<const float4 *>(st + 2 * t0);
-                    v.x = (ln_s * sv.y) * (xv.x - sv.x + ln_m) + pt;
-                    v.y = (ln_s * sv.w) * (xv.y - sv.z + ln_m) + pt;
-                } else {
-                    v.x = xv.x + pt;
-                    v.y = xv.y + pt;
-                }
+                v.x = xv.x + pt;
+                v.y = xv.y + pt;
             }
         } else {
             if (t0 < l) v.x = st ? (ln_s * st[2 * t0 + 1]) * (xr[t0] - st[2 * t0] + ln_m) + pt : xr[t0] + pt;
@@ -155,10 +190,10 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
     __syncthreads();
 
     // ---- forward passes (natural -> digit reversed)
-    fft_run_pass<LOG2M, NT, false, 0>(s, tw, tid);
-    fft_run_pass<LOG2M, NT, false, 1>(s, tw, tid);
-    fft_run_pass<LOG2M, NT, false, 2>(s, tw, tid);
-    fft_run_pass<LOG2M, NT, false, 3>(s, tw, tid);
+    fft_run_pass<LOG2M, NT, false, 0>(s, stw, tid);
+    fft_run_pass<LOG2M, NT, false, 1>(s, stw, tid);
+    fft_run_pass<LOG2M, NT, false, 2>(s, stw, tid);
+    fft_run_pass<LOG2M, NT, false, 3>(s, stw, tid);
 
     // ---- untangle the real spectrum, multiply by the cached kernel spectrum, re-tangle.
     // Slot p holds Z[k], k = fft_freq(p); its partner Z[M-k] sits in slot fft_pos(M-k).
@@ -207,22 +242,22 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
     __syncthreads();
 
     // ---- inverse passes (digit reversed -> natural), mirror order
-    fft_run_pass<LOG2M, NT, true, 3>(s, tw, tid);
-    fft_run_pass<LOG2M, NT, true, 2>(s, tw, tid);
-    fft_run_pass<LOG2M, NT, true, 1>(s, tw, tid);
-    fft_run_pass<LOG2M, NT, true, 0>(s, tw, tid);
+    fft_run_pass<LOG2M, NT, true, 3>(s, stw, tid);
+    fft_run_pass<LOG2M, NT, true, 2>(s, stw, tid);
+    fft_run_pass<LOG2M, NT, true, 1>(s, stw, tid);
+    fft_run_pass<LOG2M, NT, true, 0>(s, stw, tid);
 
     // ---- epilogue: first l samples, GELU
     if (vec) {
         for (int j = tid; j < l / 2; j += NT) {
             const float2 v = s[fft_pad(j)];
-            *reinterpret_cast<float2 *>(gr + 2 * j) = make_float2(gelu_erf(v.x), gelu_erf(v.y));
+            *reinterpret_cast<float2 *>(gr + 2 * j) = make_float2(gelu_fast(v.x), gelu_fast(v.y));
         }
     } else {
         for (int j = tid; 2 * j < l; j += NT) {
             const float2 v = s[fft_pad(j)];
-            gr[2 * j] = gelu_erf(v.x);
-            if (2 * j + 1 < l) gr[2 * j + 1] = gelu_erf(v.y);
+            gr[2 * j] = gelu_fast(v.x);
+            if (2 * j + 1 < l) gr[2 * j + 1] = gelu_fast(v.y);
         }
     }
 }

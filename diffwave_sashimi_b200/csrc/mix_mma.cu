@@ -181,19 +181,33 @@ sashimi_mix_mma_kernel(MixArgs a) {
     const size_t boff = (size_t)b * H * l;
 
     // ---- load g (split) and x (fp32); l and t0 are even so float2 accesses stay in range pairwise
-    for (int i = tid; i < H * (TT / 2); i += MIX_THREADS) {
-        const int r = i / (TT / 2), c = 2 * (i - r * (TT / 2));
-        float2 gv = make_float2(0.f, 0.f), xv = make_float2(0.f, 0.f);
-        const size_t gi = boff + (size_t)r * l + t0 + c;
-        if (t0 + c + 1 < l) {
-            gv = *reinterpret_cast<const float2 *>(a.g + gi);
-            xv = *reinterpret_cast<const float2 *>(a.x + gi);
-        } else if (t0 + c < l) {
-            gv.x = a.g[gi];
-            xv.x = a.x[gi];
+    {
+        constexpr int ITEMS = H * (TT / 2), U = 4;          // U independent (g, x) loads in flight per thread
+        static_assert(ITEMS % (MIX_THREADS * U) == 0, "tile load tiling");
+        for (int i0 = tid; i0 < ITEMS; i0 += MIX_THREADS * U) {
+            float2 gv[U], xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * MIX_THREADS;
+                const int r = i / (TT / 2), c = 2 * (i - r * (TT / 2));
+                const size_t gi = boff + (size_t)r * l + t0 + c;
+                gv[u] = xv[u] = make_float2(0.f, 0.f);
+                if (t0 + c + 1 < l) {
+                    gv[u] = *reinterpret_cast<const float2 *>(a.g + gi);
+                    xv[u] = *reinterpret_cast<const float2 *>(a.x + gi);
+                } else if (t0 + c < l) {
+                    gv[u].x = a.g[gi];
+                    xv[u].x = a.x[gi];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * MIX_THREADS;
+                const int r = i / (TT / 2), c = 2 * (i - r * (TT / 2));
+                split_store2(Ghi, Glo, (size_t)r * TTP + c, gv[u].x, gv[u].y);
+                *reinterpret_cast<float2 *>(X1 + (size_t)r * XS + c) = xv[u];
+            }
         }
-        split_store2(Ghi, Glo, (size_t)r * TTP + c, gv.x, gv.y);
-        *reinterpret_cast<float2 *>(X1 + (size_t)r * XS + c) = xv;
     }
     __syncthreads();
 
@@ -259,8 +273,8 @@ sashimi_mix_mma_kernel(MixArgs a) {
 #pragma unroll
                 for (int n = 0; n < NT; ++n) {
                     const int c = col0 + n * 8 + 2 * tq;
-                    split_store2(Hhi, Hlo, (size_t)m * TTP + c, gelu_erf(acc[i][n][half * 2] + bv),
-                                 gelu_erf(acc[i][n][half * 2 + 1] + bv));
+                    split_store2(Hhi, Hlo, (size_t)m * TTP + c, gelu_fast(acc[i][n][half * 2] + bv),
+                                 gelu_fast(acc[i][n][half * 2 + 1] + bv));
                 }
             }
     }
@@ -316,6 +330,7 @@ static int launch_mma(const MixArgs &a, int B, cudaStream_t st) {
     auto k = sashimi_mix_mma_kernel<H, FM, TT, WM, WN>;
     static_assert(C::SMEM <= 227 * 1024, "tile does not fit shared memory");
     if (C::SMEM > 48 * 1024) DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     dim3 grid(ceil_div(a.l, TT), B);
     k<<<grid, MIX_THREADS, C::SMEM, st>>>(a);
     DWB_LAUNCH_CHECK();
@@ -340,12 +355,11 @@ int mix_mma_launch(const MixArgs &a, int B, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------
 // pools on the same split-bf16 path                               (models/sashimi.py:23-58)
 // ---------------------------------------------------------------------------------------
-constexpr int POOL_TT = 32;
-
 // down(s): x'[h*s+j][c] = x[b, h, (t0+c)*s + j];  out = W x' + bias  (K = Hi*s -> Ho), + stats
+template <int TT>
 __global__ void __launch_bounds__(MIX_THREADS)
 down_pool_mma_kernel(PoolArgs a) {
-    constexpr int TT = POOL_TT, TTP = TT + 8, XS = TT + 4, NT = TT / 8;
+    constexpr int TTP = TT + 8, XS = TT + 4, NT = TT / 8;
     extern __shared__ __align__(16) unsigned char smraw[];
     const int Hi = a.Hi, Ho = a.Ho, s = a.s, li = a.li, lo = li / s, K = Hi * s;
     float *Os = reinterpret_cast<float *>(smraw);                                  // [Ho][XS]
@@ -457,10 +471,14 @@ static int launch_pool(KernelT k, const PoolArgs &a, dim3 grid, size_t sm, cudaS
     return DWB_OK;
 }
 
+static size_t down_pool_smem(const PoolArgs &a, int TT) {
+    return (size_t)a.Ho * (TT + 4) * 4 + (size_t)2 * a.Hi * a.s * (TT + 8) * 2 + (2 * MIX_THREADS + 2 * TT) * 4;
+}
+
 int down_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st) {
-    constexpr int TT = POOL_TT;
-    const size_t sm = (size_t)a.Ho * (TT + 4) * 4 + (size_t)2 * a.Hi * a.s * (TT + 8) * 2 + (2 * MIX_THREADS + 2 * TT) * 4;
-    return launch_pool(down_pool_mma_kernel, a, dim3(ceil_div(a.li / a.s, TT), B), sm, st);
+    if (down_pool_smem(a, 32) <= 110 * 1024)      // two CTAs per SM
+        return launch_pool(down_pool_mma_kernel<32>, a, dim3(ceil_div(a.li / a.s, 32), B), down_pool_smem(a, 32), st);
+    return launch_pool(down_pool_mma_kernel<16>, a, dim3(ceil_div(a.li / a.s, 16), B), down_pool_smem(a, 16), st);
 }
 
 int up_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st) {
