@@ -71,6 +71,8 @@ struct Op {
 struct WaveLayer {
     int dilation;
     float *Wd_t, *bd, *Wr_t, *br, *Ws_t, *bs;
+    uint4 *Wd_f[2], *Wr_f[2], *Ws_f[2];
+    bool mma;
     int part_off;
     int64_t cond_off;
 };
@@ -450,6 +452,22 @@ static int finalize_wavenet(dwb_plan *p, cudaStream_t st) {
         TRY(folded(p, pre + "dilated_conv_layer.conv", 2 * C, C, 3, true, &w.Wd_t, &w.bd, st));
         TRY(folded(p, pre + "res_conv", C, C, 1, true, &w.Wr_t, &w.br, st));
         TRY(folded(p, pre + "skip_conv", S, C, 1, true, &w.Ws_t, &w.bs, st));
+        w.mma = p->use_mma && wave_mma_supported(C, S);
+        if (w.mma) {
+            auto pack = [&](const float *Wt, int M, int K, uint4 **f) -> int {
+                for (int q = 0; q < 2; ++q) {
+                    void *d;
+                    TRY(dev_alloc(p, (size_t)M * K * 2, &d));
+                    f[q] = (uint4 *)d;
+                }
+                TRY(frag_pack(Wt, M, K, (uint32_t *)f[0], (uint32_t *)f[1], st));
+                p->launches += 1;
+                return DWB_OK;
+            };
+            TRY(pack(w.Wd_t, 2 * C, 3 * C, w.Wd_f));
+            TRY(pack(w.Wr_t, C, C, w.Wr_f));
+            TRY(pack(w.Ws_t, S, C, w.Ws_f));
+        }
         w.part_off = n * C;
         w.cond_off = cond_off;
         p->wl.push_back(w);
@@ -595,7 +613,12 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
             a.Wd_t = w.Wd_t; a.bd = w.bd; a.Wr_t = w.Wr_t; a.br = w.br; a.Ws_t = w.Ws_t; a.bs = w.bs;
             a.skip = p->skip_acc; a.first = n == 0;
             a.C = C; a.S = S; a.L = L; a.dilation = w.dilation;
-            TRY(wave_block_launch(a, B, st));
+            if (w.mma) {
+                a.Wd_fh = w.Wd_f[0]; a.Wd_fl = w.Wd_f[1]; a.Wr_fh = w.Wr_f[0]; a.Wr_fl = w.Wr_f[1];
+                a.Ws_fh = w.Ws_f[0]; a.Ws_fl = w.Ws_f[1];
+                TRY(wave_block_mma_launch(a, B, st));
+            } else
+                TRY(wave_block_launch(a, B, st));
             p->launches += 1;
             PROF(DWB_PROF_WAVEBLOCK);
             cur ^= 1;

@@ -52,6 +52,7 @@ struct WaveBlockArgs {
     const float *Wd_t, *bd;        // [3C][2C] tap-major rows (t-d, t, t+d), (2C)
     const float *Wr_t, *br;        // [C][C], (C)
     const float *Ws_t, *bs;        // [C][S], (S)
+    const uint4 *Wd_fh, *Wd_fl, *Wr_fh, *Wr_fl, *Ws_fh, *Ws_fl;   // split-bf16 A fragments, or null
     float *h_out;                  // (B,C,L)
     float *skip;                   // (B,S,L) accumulated in place
     int first;                     // 1: skip is written, not accumulated
@@ -75,6 +76,8 @@ int down_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
 int up_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
 int head_launch(const HeadArgs &a, int B, cudaStream_t st);
 int wave_block_launch(const WaveBlockArgs &a, int B, cudaStream_t st);
+bool wave_mma_supported(int C, int S);
+int wave_block_mma_launch(const WaveBlockArgs &a, int B, cudaStream_t st);
 
 int fftconv_launch(const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
                    const float *kf, float *g, int B, int H, int l, cudaStream_t st);

@@ -168,6 +168,29 @@ def test_tensor_core_mixing_vs_oracle_fp64(dwb, d, L, B, pool, monkeypatch):
     assert e2 < 1e-4 and em < 1e-4 and s2 < 2e-5
 
 
+@pytest.mark.parametrize("C,S,N,cycle,L,B", [(64, 32, 7, 7, 500, 2), (128, 256, 4, 4, 1000, 1), (48, 80, 3, 3, 130, 3)])
+def test_wavenet_tensor_core_vs_oracle_fp64(dwb, C, S, N, cycle, L, B, monkeypatch):
+    """WaveNet blocks on the split-bf16 mma path: dilations reach past the 64-sample tile (2^6) so the
+    three taps come from different tiles and the zero padding at both ends is exercised."""
+    from oracle.refshim import MODEL_CFGS
+    cfg = dict(MODEL_CFGS["wnet_h128_d30"], res_channels=C, skip_channels=S, num_res_layers=N, dilation_cycle=cycle)
+    sd = dwb.init.seeded_state_dict(cfg, seed=2)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 1, L, generator=g)
+    t = torch.tensor([[11.0], [199.0], [0.0]])[:B]
+    ref = O.forward(cfg, sd, x, t)
+    net = _model(dwb, cfg, sd)
+    with torch.no_grad():
+        eps = net((x.cuda(), t.cuda())).cpu()
+    monkeypatch.setenv("DWB_MIX", "simt")
+    net2 = _model(dwb, cfg, sd)
+    with torch.no_grad():
+        eps2 = net2((x.cuda(), t.cuda())).cpu()
+    monkeypatch.delenv("DWB_MIX")
+    print(f"wnet C={C}: mma rel_l2 {rel_l2(eps, ref):.2e} simt rel_l2 {rel_l2(eps2, ref):.2e}")
+    assert rel_l2(eps, ref) < 1e-4 and rel_max(eps, ref) < 1e-4 and rel_l2(eps2, ref) < 2e-5
+
+
 def test_batch_elements_are_independent(dwb):
     from oracle.refshim import MODEL_CFGS
     cfg = dict(MODEL_CFGS["unet_d64"])
