@@ -50,6 +50,7 @@ SIGNATURES = {
     "dwb_plan_launch_count": [_P, ctypes.POINTER(_I64)],
     "dwb_plan_s4_blocks": [_P, ctypes.POINTER(_I)],
     "dwb_plan_s4_kernel": [_P, _I, _P, _I64, ctypes.POINTER(_I), ctypes.POINTER(_I)],
+    "dwb_plan_mix_block": [_P, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "dwb_plan_work": [_P, _I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
     "dwb_plan_profile": [_P, _P, _P, _P, _I, _P, _I, _I, _I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64), _P],
     "dwb_cauchy_sym_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],

@@ -60,6 +60,9 @@ struct Op {
     float *Wo_t = nullptr, *bo = nullptr, *W1_t = nullptr, *b1 = nullptr, *W2_t = nullptr, *b2 = nullptr;
     uint4 *Wo_f[2] = {nullptr, nullptr}, *W1_f[2] = {nullptr, nullptr}, *W2_f[2] = {nullptr, nullptr};
     bool mma = false;
+    bool umma = false;             // tcgen05 path (mix_umma.cu)
+    uint8_t *Wimg = nullptr;
+    float *bimg = nullptr;
     int F = 0;
     int part_off = 0;      // offset of this block's fc_t rows in the stacked embedding output
     int64_t cond_off = 0;  // float offset (per cond batch element) of this block's conditioning features
@@ -99,6 +102,7 @@ struct dwb_plan {
     std::vector<void *> owned;
     int64_t launches = 0;
     bool use_mma = true;           // DWB_MIX=simt in the environment selects the exact-fp32 SIMT channel mixing
+    bool use_umma = true;          // DWB_MIX=mma keeps the legacy mma.sync path instead of tcgen05
 
     // embedding
     float *eW1 = nullptr, *eb1 = nullptr, *eW2 = nullptr, *eb2 = nullptr, *Wt_all = nullptr, *bt_all = nullptr;
@@ -389,7 +393,15 @@ static int finalize_sashimi(dwb_plan *p, cudaStream_t st) {
                 TRY(folded(p, o.prefix + "layer.output_linear.0", 2 * H, H, 1, false, &o.Wo_t, &o.bo, st));
                 TRY(folded(p, o.prefix + "ff.ff.0.conv", o.F, H, 1, true, &o.W1_t, &o.b1, st));
                 TRY(folded(p, o.prefix + "ff.ff.2.conv", H, o.F, 1, true, &o.W2_t, &o.b2, st));
-                o.mma = p->use_mma && mix_mma_supported(H, o.F, l);
+                o.umma = p->use_mma && p->use_umma && mix_umma_supported(H, o.F, l);
+                if (o.umma) {
+                    void *d;
+                    TRY(dev_alloc(p, mix_umma_image_bytes(H), &d)); o.Wimg = (uint8_t *)d;
+                    TRY(dev_alloc(p, (size_t)5 * H * sizeof(float), &d)); o.bimg = (float *)d;
+                    TRY(mix_umma_pack(H, o.Wo_t, o.W1_t, o.W2_t, o.bo, o.b1, o.b2, o.Wimg, o.bimg, st));
+                    p->launches += 1;
+                }
+                o.mma = !o.umma && p->use_mma && mix_mma_supported(H, o.F, l);
                 if (o.mma) {
                     auto pack = [&](const float *Wt, int M, int K, uint4 **f) -> int {
                         for (int q = 0; q < 2; ++q) {
@@ -576,7 +588,8 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
                 a.H = o.H; a.F = o.F; a.l = o.l;
                 a.Wo_fh = o.Wo_f[0]; a.Wo_fl = o.Wo_f[1]; a.W1_fh = o.W1_f[0]; a.W1_fl = o.W1_f[1];
                 a.W2_fh = o.W2_f[0]; a.W2_fl = o.W2_f[1];
-                TRY(o.mma ? mix_mma_launch(a, B, st) : mix_launch(a, B, st));
+                a.Wimg = o.Wimg; a.bimg = o.bimg;
+                TRY(o.umma ? mix_umma_launch(a, B, st) : (o.mma ? mix_mma_launch(a, B, st) : mix_launch(a, B, st)));
                 p->launches += 2;
                 PROF(DWB_PROF_MIX0 + std::min(stage_of(p, o.l), 3));
             } else {
@@ -682,7 +695,10 @@ int dwb_plan_create(const dwb_config *cfg, int device, dwb_plan **out) {
     DWB_CUDA(cudaGetDeviceProperties(&prop, device));
     DWB_REQUIRE(prop.major == 10, DWB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libdwb is built for sm_100a only", device, prop.major, prop.minor);
     dwb_plan *p = new dwb_plan();
-    if (const char *e = getenv("DWB_MIX")) p->use_mma = std::string(e) != "simt";
+    if (const char *e = getenv("DWB_MIX")) {
+        p->use_mma = std::string(e) != "simt";
+        p->use_umma = std::string(e) != "mma";
+    }
     p->cfg = *cfg;
     p->device = device;
     *out = p;
@@ -908,6 +924,32 @@ int dwb_plan_s4_kernel(dwb_plan *p, int block, float *k_out, int64_t capacity, i
                 return DWB_OK;
             }
             ++n;
+        }
+    set_error("block %d out of range", block);
+    return DWB_ERR_INVALID;
+}
+
+int dwb_plan_mix_block(dwb_plan *p, int block, int exact, const float *g, const float *x, const float *skip, float *out,
+                       float *stats_out, int B, void *stream) {
+    DWB_REQUIRE(p && p->finalized, DWB_ERR_STATE, "plan is not finalized");
+    DWB_REQUIRE(g && x && out && stats_out && B >= 1 && B <= 65535, DWB_ERR_INVALID, "dwb_plan_mix_block: bad arguments");
+    DWB_CUDA(cudaSetDevice(p->device));
+    int n = 0;
+    for (auto &o : p->ops)
+        if (o.kind == OP_BLOCK) {
+            if (n++ != block) continue;
+            MixArgs a{};
+            a.g = g; a.x = x; a.skip = skip; a.cond = nullptr; a.cond_stride_b = 0;
+            a.Wo_t = o.Wo_t; a.bo = o.bo; a.W1_t = o.W1_t; a.b1 = o.b1; a.W2_t = o.W2_t; a.b2 = o.b2;
+            a.ln2_m = o.ln2_m; a.ln2_s = o.ln2_s; a.out = out; a.stats_out = stats_out;
+            a.H = o.H; a.F = o.F; a.l = o.l;
+            a.Wo_fh = o.Wo_f[0]; a.Wo_fl = o.Wo_f[1]; a.W1_fh = o.W1_f[0]; a.W1_fl = o.W1_f[1];
+            a.W2_fh = o.W2_f[0]; a.W2_fl = o.W2_f[1];
+            a.Wimg = o.Wimg; a.bimg = o.bimg;
+            p->launches += 1;
+            if (exact) return mix_launch(a, B, (cudaStream_t)stream);
+            return o.umma ? mix_umma_launch(a, B, (cudaStream_t)stream)
+                          : (o.mma ? mix_mma_launch(a, B, (cudaStream_t)stream) : mix_launch(a, B, (cudaStream_t)stream));
         }
     set_error("block %d out of range", block);
     return DWB_ERR_INVALID;

@@ -15,6 +15,9 @@ struct MixArgs {
     const float *W2_t, *b2;        // [F][H],  (H)
     // split-bf16 mma A fragments of the same weights (mix_mma.cu), or null
     const uint4 *Wo_fh, *Wo_fl, *W1_fh, *W1_fl, *W2_fh, *W2_fl;
+    // tcgen05 path (mix_umma.cu): packed shared-memory image of the three weights + biases, or null
+    const uint8_t *Wimg;
+    const float *bimg;
     float ln2_m, ln2_s;
     float *out, *stats_out;        // (B,H,l), (B,l,2)
     int H, F, l;
@@ -71,6 +74,11 @@ int mix_mma_launch(const MixArgs &a, int B, cudaStream_t st);
 bool pool_mma_supported(int Hi, int Ho, int s, bool up);
 int down_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st);
 int up_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st);
+bool mix_umma_supported(int H, int F, int l);
+size_t mix_umma_image_bytes(int H);
+int mix_umma_pack(int H, const float *Wo_t, const float *W1_t, const float *W2_t, const float *bo, const float *b1,
+                  const float *b2, uint8_t *img, float *bimg, cudaStream_t st);
+int mix_umma_launch(const MixArgs &a, int B, cudaStream_t st);
 int frag_pack(const float *Wt, int M, int K, uint32_t *fhi, uint32_t *flo, cudaStream_t st);
 int down_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
 int up_pool_launch(const PoolArgs &a, int B, cudaStream_t st);

@@ -1,0 +1,508 @@
+// DiffWaveBlock channel mixing on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+// TMEM), split-bf16 operands, fp32 accumulate.                  models/sashimi.py:157-182
+//
+//   q = Wo g + bo ; y = q[:H] * sigmoid(q[H:]) (+cond) ; x1 = x + y          (s4.py:1435, sashimi.py:177)
+//   x2 = x1 + W2 gelu(W1 LN2(x1) + b1) + b2 (+skip) ; stats(x2)              (sashimi.py:179-182)
+//
+// Orientation.  One CTA owns a tile of 128 consecutive time steps of one clip and ALL channels.
+// The three contractions are issued as  D[time][out_ch] = sum_k Act[time][k] * W[out_ch][k]:
+// time is the MMA M dimension (128 = the TMEM lanes), output channels are TMEM columns.  An
+// epilogue thread therefore owns ONE time step and sees every channel of it in its own TMEM lane:
+// the TransposedLN statistics over channels, the GLU pairing (q[h], q[H+h]) and both residual adds
+// are thread-local, and x1 simply stays in the TMEM columns that the third contraction later
+// accumulates into (x2 = x1 + W2 hidden falls out of the MMA, no separate add).
+//
+// Operands.  fp32 values are split v = hi + lo (two bf16) and each product is three MMAs
+// (hi*hi + lo*hi + hi*lo), ~2^-17 relative: single-pass bf16/tf32 would eat the whole 1e-3 parity
+// budget.  Activations are written by the epilogue threads straight into
+// the K-major SW128 layout the MMA reads (one 16-byte chunk = 8 channels of one time step);
+// weights are packed once at finalize into the exact shared-memory image (split, swizzled, in
+// consumption order) and streamed per tile with 1-D bulk async copies through a small ring.
+//
+// Roles: warps [0, 4*CS) epilogue (CS threads per time step, each a contiguous column group),
+// warp 4*CS = weight producer (one lane), warp 4*CS+1 = TMEM owner + MMA issuer (one lane).
+#include "common.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace dwb {
+using namespace umma;
+
+constexpr int UM_TT = 128;                // time steps per tile = MMA M
+constexpr int UM_STAGE = 32768;           // weight ring stage
+constexpr int UM_SLOT = 32768;            // activation operand slot: [128 x 64] hi (16 KB) + lo (16 KB)
+
+template <int H, int CS>
+struct UCfg {
+    static constexpr int F = 2 * H;
+    static constexpr int EPI = 128 * CS;                 // epilogue threads
+    static constexpr int NTHREADS = EPI + 64;
+    static constexpr int KC1 = H / 64;                   // K chunks of G1 / G2
+    static constexpr int NC1 = 2 * H / 128;              // N chunks (128 columns) of G1 / G2
+    static constexpr int KC3 = F / 64;                   // K chunks of G3
+    static constexpr int NR3 = H < 128 ? H : 128;        // rows per weight block of G3
+    static constexpr int NC3 = H / NR3;
+    static constexpr int BPS3 = UM_STAGE / (NR3 * 256);  // G3 weight blocks per ring stage
+    static constexpr int NSTG = 2 * NC1 * KC1 + (KC3 * NC3) / BPS3;
+    static constexpr int NSLOT = (H == 64) ? 2 : 4;
+    static constexpr int NS = (H == 64) ? 1 : 2;         // ring depth
+    static constexpr int TMEM_COLS = (3 * H <= 256) ? 256 : 512;
+    static constexpr int R3 = 2 * H;                     // first TMEM column of x1 / acc3
+    static constexpr int HID_ARRIVE = 128 * (CS >= 2 ? CS / 2 : 1);
+    static constexpr int NBAR = 2 * NS + 2 + KC3 + 2 * NC1 + 1;
+    // shared memory carve-up (bytes from the 1024-aligned base)
+    static constexpr int OFF_SLOT = 0;
+    static constexpr int OFF_RING = OFF_SLOT + NSLOT * UM_SLOT;
+    static constexpr int OFF_BIAS = OFF_RING + NS * UM_STAGE;          // bo' (2H) b1 (F) b2 (H)
+    static constexpr int OFF_EX = OFF_BIAS + 5 * H * 4;                // 2 exchanges x CS x 128 x (mean, M2)
+    static constexpr int OFF_BAR = OFF_EX + 2 * CS * 128 * 8;
+    static constexpr int OFF_TPTR = OFF_BAR + NBAR * 8;
+    static constexpr int SMEM = OFF_TPTR + 16 + 1024;                  // + alignment slack
+    static constexpr size_t IMG_BYTES = (size_t)NSTG * UM_STAGE;
+    static_assert(H % 64 == 0 && (KC3 * NC3) % BPS3 == 0, "tiling");
+    static_assert(3 * H <= 512, "TMEM budget: acc (2H) + x1/acc3 (H) columns");
+    static constexpr int hid_slot(int kc) { return H == 64 ? kc : (kc + 2) % 4; }
+};
+
+// running (mean, M2) over n values + a chunk of 16 -> n + 16 values (Chan et al. pairwise update)
+__device__ __forceinline__ void stat_merge16(const float (&v)[16], int n, float &mean, float &M2) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    const float cm = s * (1.0f / 16.0f);
+    float c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float d = v[i] - cm;
+        c2 = fmaf(d, d, c2);
+    }
+    if (n == 0) {
+        mean = cm;
+        M2 = c2;
+    } else {
+        const float delta = cm - mean, tot = (float)(n + 16);
+        mean = fmaf(delta, 16.0f / tot, mean);
+        M2 += c2 + delta * delta * ((float)n * 16.0f / tot);
+    }
+}
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+template <int H, int CS>
+__global__ void __launch_bounds__(UCfg<H, CS>::NTHREADS, (H == 64) ? 2 : 1)
+sashimi_mix_umma_kernel(MixArgs a) {
+    using C = UCfg<H, CS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *slots = sm + C::OFF_SLOT, *ring = sm + C::OFF_RING;
+    float *bias_s = reinterpret_cast<float *>(sm + C::OFF_BIAS);
+    float2 *ex = reinterpret_cast<float2 *>(sm + C::OFF_EX);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + C::OFF_BAR);
+    uint32_t *tptr = reinterpret_cast<uint32_t *>(sm + C::OFF_TPTR);
+    uint64_t *wfull = bars, *wempty = bars + C::NS, *g_ready = bars + 2 * C::NS, *z_ready = g_ready + 1,
+             *hid_ready = z_ready + 1, *acc1_ready = hid_ready + C::KC3, *acc2_ready = acc1_ready + C::NC1,
+             *acc3_ready = acc2_ready + C::NC1;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, t0 = blockIdx.x * UM_TT, l = a.l;
+
+    if (tid == 0) {
+        for (int i = 0; i < C::NS; ++i) {
+            mbar_init(wfull + i, 1);
+            mbar_init(wempty + i, 1);
+        }
+        mbar_init(g_ready, C::EPI);
+        mbar_init(z_ready, C::EPI);
+        for (int i = 0; i < C::KC3; ++i) mbar_init(hid_ready + i, C::HID_ARRIVE);
+        for (int i = 0; i < C::NC1; ++i) {
+            mbar_init(acc1_ready + i, 1);
+            mbar_init(acc2_ready + i, 1);
+        }
+        mbar_init(acc3_ready, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 5 * H; i += C::NTHREADS) bias_s[i] = a.bimg[i];
+    if (warp == 4 * CS + 1) tmem_alloc(tptr, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tptr;
+
+    if (warp == 4 * CS) {
+        // ================= weight producer: the packed image, one ring stage at a time =========
+        if (lane == 0) {
+            for (int i = 0; i < C::NSTG; ++i) {
+                const int s = i % C::NS, n = i / C::NS;
+                mbar_wait(wempty + s, (n & 1) ^ 1);
+                mbar_arrive_expect_tx(wfull + s, UM_STAGE);
+                bulk_g2s(ring + (size_t)s * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + s);
+            }
+        }
+    } else if (warp == 4 * CS + 1) {
+        // ================= MMA issuer ==========================================================
+        if (lane == 0) {
+            const uint32_t slot0 = smem_u32(slots), ring0 = smem_u32(ring);
+            // one [128 x NR] x K=64 block: 3 split terms x 4 k-steps
+            auto issue_block = [&](uint32_t d, uint32_t abase, uint32_t bbase, int NR, bool acc0) {
+                const uint32_t idesc = idesc_bf16(128, NR);
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t ao = abase + (term == 1 ? UM_SLOT / 2 : 0);
+                    const uint32_t bo = bbase + (term == 2 ? NR * 128 : 0);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_bf16_ss(d, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
+                                    (acc0 || term > 0 || ks > 0) ? 1u : 0u);
+                }
+            };
+            int i = 0;
+            for (int gemm = 0; gemm < 2; ++gemm) {
+                mbar_wait(gemm == 0 ? g_ready : z_ready, 0);
+                tc_fence_after();
+                for (int nc = 0; nc < C::NC1; ++nc) {
+                    for (int kc = 0; kc < C::KC1; ++kc, ++i) {
+                        const int s = i % C::NS;
+                        mbar_wait(wfull + s, (i / C::NS) & 1);
+                        tc_fence_after();
+                        issue_block(tmem + nc * 128, slot0 + kc * UM_SLOT, ring0 + s * UM_STAGE, 128, kc > 0);
+                        mma_commit(wempty + s);
+                    }
+                    mma_commit((gemm == 0 ? acc1_ready : acc2_ready) + nc);
+                }
+            }
+            for (int kc = 0; kc < C::KC3; ++kc) {
+                mbar_wait(hid_ready + kc, 0);
+                tc_fence_after();
+                for (int nc = 0; nc < C::NC3; ++nc) {
+                    const int j = kc * C::NC3 + nc, s = i % C::NS;
+                    if (j % C::BPS3 == 0) {
+                        mbar_wait(wfull + s, (i / C::NS) & 1);
+                        tc_fence_after();
+                    }
+                    issue_block(tmem + C::R3 + nc * 128, slot0 + C::hid_slot(kc) * UM_SLOT,
+                                ring0 + s * UM_STAGE + (j % C::BPS3) * C::NR3 * 256, C::NR3, true);
+                    if (j % C::BPS3 == C::BPS3 - 1) {
+                        mma_commit(wempty + s);
+                        ++i;
+                    }
+                }
+            }
+            mma_commit(acc3_ready);
+        }
+    } else {
+        // ================= epilogue threads: one time step each, column group cg ================
+        const int q = warp & 3, cg = warp >> 2;
+        const int r = 32 * q + lane, t = t0 + r;
+        const bool valid = t < l;
+        const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
+        const size_t brow = (size_t)b * H * l + (valid ? t : 0);
+        const float *gp = a.g + brow, *xp = a.x + brow;
+        float *op = a.out + brow;
+        const float *bo_s = bias_s, *b1_s = bias_s + 2 * H, *b2_s = bias_s + 4 * H;
+
+        // ---- load g, split, store as the A operand of G1
+        {
+            constexpr int PER = H / CS;                    // channels per thread
+#pragma unroll
+            for (int c16 = 0; c16 < PER / 16; ++c16) {
+                const int h0 = cg * PER + c16 * 16;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = valid ? __ldg(gp + (size_t)(h0 + i) * l) : 0.f;
+                uint8_t *slot = slots + (h0 >> 6) * UM_SLOT;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint4 hi, lo;
+                    split8(v + 8 * hh, hi, lo);
+                    const uint32_t off = sw128_off(r, ((h0 & 63) >> 3) + hh);
+                    *reinterpret_cast<uint4 *>(slot + off) = hi;
+                    *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(g_ready);
+        }
+
+        // ---- E1: GLU + residual -> x1 (TMEM R3), LN2 statistics
+        float mean = 0.f, M2 = 0.f;
+        {
+            constexpr int PP = 64 / CS;                    // GLU pairs per thread per N chunk
+            int n = 0;
+#pragma unroll
+            for (int nc = 0; nc < C::NC1; ++nc) {
+                mbar_wait(acc1_ready + nc, 0);
+                tc_fence_after();
+#pragma unroll
+                for (int sc = 0; sc < PP / 16; ++sc) {
+                    const int p0 = cg * PP + sc * 16, h0 = nc * 64 + p0;
+                    float xv[16], av[16], gv[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) xv[i] = valid ? __ldg(xp + (size_t)(h0 + i) * l) : 0.f;
+                    tmem_ld16(tl + nc * 128 + p0, av);
+                    tmem_ld16(tl + nc * 128 + 64 + p0, gv);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float y = (av[i] + bo_s[nc * 128 + p0 + i]) * sigmoid_fast(gv[i] + bo_s[nc * 128 + 64 + p0 + i]);
+                        if (a.cond && valid) y += __ldg(a.cond + ((size_t)(a.cond_stride_b ? b : 0) * H + h0 + i) * l + t);
+                        xv[i] += y;
+                    }
+                    stat_merge16(xv, n, mean, M2);
+                    n += 16;
+                    tmem_st16(tl + C::R3 + h0, xv);
+                }
+            }
+            tmem_wait_st();
+        }
+        if (CS > 1) {
+            ex[cg * 128 + r] = make_float2(mean, M2);
+            asm volatile("bar.sync 1, %0;" ::"n"(C::EPI) : "memory");
+            float ms = 0.f;
+#pragma unroll
+            for (int c = 0; c < CS; ++c) ms += ex[c * 128 + r].x;
+            const float mt = ms * (1.0f / CS);
+            float m2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CS; ++c) {
+                const float2 e = ex[c * 128 + r];
+                const float d = e.x - mt;
+                m2 += e.y + d * d * (float)(H / CS);
+            }
+            mean = mt;
+            M2 = m2;
+        }
+        // ---- z = LN2(x1), split, store as the A operand of G2 (the slots of g: G1 has completed)
+        {
+            const float rstd = valid ? rsqrtf(M2 * (1.0f / H)) : 0.f;
+            const float sc_a = a.ln2_s * rstd, sh = a.ln2_m - mean;
+            constexpr int PP = 64 / CS;
+#pragma unroll
+            for (int nc = 0; nc < C::NC1; ++nc)
+#pragma unroll
+                for (int sc = 0; sc < PP / 16; ++sc) {
+                    const int p0 = cg * PP + sc * 16, h0 = nc * 64 + p0;
+                    float v[16];
+                    tmem_ld16(tl + C::R3 + h0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = sc_a * (v[i] + sh);
+                    uint8_t *slot = slots + (h0 >> 6) * UM_SLOT;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint4 hi, lo;
+                        split8(v + 8 * hh, hi, lo);
+                        const uint32_t off = sw128_off(r, ((h0 & 63) >> 3) + hh);
+                        *reinterpret_cast<uint4 *>(slot + off) = hi;
+                        *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
+                    }
+                }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(z_ready);
+        }
+
+        // ---- E2: hidden = gelu(W1 z + b1), split, store as the A operand of G3
+        {
+            constexpr int PER = 128 / CS;                  // f columns per thread per N chunk
+#pragma unroll
+            for (int nc = 0; nc < C::NC1; ++nc) {
+                mbar_wait(acc2_ready + nc, 0);
+                tc_fence_after();
+#pragma unroll
+                for (int sc = 0; sc < PER / 16; ++sc) {
+                    const int col = cg * PER + sc * 16, f0 = nc * 128 + col;
+                    float v[16];
+                    tmem_ld16(tl + nc * 128 + col, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i] + b1_s[f0 + i]);
+                    const int kc = f0 >> 6;
+                    uint8_t *slot = slots + C::hid_slot(kc) * UM_SLOT;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint4 hi, lo;
+                        split8(v + 8 * hh, hi, lo);
+                        const uint32_t off = sw128_off(r, ((f0 & 63) >> 3) + hh);
+                        *reinterpret_cast<uint4 *>(slot + off) = hi;
+                        *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
+                    }
+                    // last 16 columns this thread contributes to K chunk kc
+                    if (((f0 + 16) & 63) == 0 || sc == PER / 16 - 1) {
+                        fence_proxy_async_smem();
+                        tc_fence_before();
+                        mbar_arrive(hid_ready + kc);
+                    }
+                }
+            }
+        }
+
+        // ---- E3: x2 = acc3 (= x1 + W2 hidden) + b2 (+skip); store; statistics for the next norm
+        {
+            constexpr int PER = H / CS;
+            mbar_wait(acc3_ready, 0);
+            tc_fence_after();
+            int n = 0;
+            mean = 0.f;
+            M2 = 0.f;
+#pragma unroll
+            for (int sc = 0; sc < PER / 16; ++sc) {
+                const int h0 = cg * PER + sc * 16;
+                float v[16], sk[16];
+                if (a.skip) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) sk[i] = valid ? __ldg(a.skip + brow + (size_t)(h0 + i) * l) : 0.f;
+                }
+                tmem_ld16(tl + C::R3 + h0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] += b2_s[h0 + i];
+                    if (a.skip) v[i] += sk[i];
+                }
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) op[(size_t)(h0 + i) * l] = v[i];
+                }
+                stat_merge16(v, n, mean, M2);
+                n += 16;
+            }
+            if (CS > 1) {
+                float2 *ex3 = ex + CS * 128;
+                ex3[cg * 128 + r] = make_float2(mean, M2);
+                asm volatile("bar.sync 1, %0;" ::"n"(C::EPI) : "memory");
+                float ms = 0.f;
+#pragma unroll
+                for (int c = 0; c < CS; ++c) ms += ex3[c * 128 + r].x;
+                const float mt = ms * (1.0f / CS);
+                float m2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < CS; ++c) {
+                    const float2 e = ex3[c * 128 + r];
+                    const float d = e.x - mt;
+                    m2 += e.y + d * d * (float)(H / CS);
+                }
+                mean = mt;
+                M2 = m2;
+            }
+            if (cg == 0 && valid)
+                *reinterpret_cast<float2 *>(a.stats_out + ((size_t)b * l + t) * 2) = make_float2(mean, rsqrtf(M2 * (1.0f / H)));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4 * CS + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, C::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// finalize: folded fp32 weights (transposed [K][M]) -> the streamed shared-memory image
+// ---------------------------------------------------------------------------------------
+template <int H>
+__global__ void umma_pack_kernel(const float *__restrict__ Wo_t, const float *__restrict__ W1_t,
+                                 const float *__restrict__ W2_t, const float *__restrict__ bo, const float *__restrict__ b1,
+                                 const float *__restrict__ b2, uint8_t *__restrict__ img, float *__restrict__ bimg) {
+    using C = UCfg<H, 1>;
+    constexpr int F = 2 * H;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one 16-byte chunk of one part pair
+    if (idx < (size_t)5 * H) {
+        float v;
+        if (idx < (size_t)2 * H) {
+            const int nc = idx / 128, i = idx % 128;
+            v = bo[i < 64 ? nc * 64 + i : H + nc * 64 + (i - 64)];
+        } else if (idx < (size_t)4 * H)
+            v = b1[idx - 2 * H];
+        else
+            v = b2[idx - 4 * H];
+        bimg[idx] = v;
+    }
+    // enumerate (block, row, logical chunk j): hi and lo chunks are written together
+    const size_t g12 = (size_t)2 * C::NC1 * C::KC1 * 128 * 8;             // chunks in G1 + G2 (hi part)
+    const size_t g3 = (size_t)C::KC3 * C::NC3 * C::NR3 * 8;
+    if (idx >= g12 + g3) return;
+    const float *Wt;
+    int M, n, k0;
+    size_t base;            // byte offset of the block
+    int NR, row, j;
+    if (idx < g12) {
+        const int blk = idx / (128 * 8), rem = idx % (128 * 8);
+        row = rem / 8;
+        j = rem % 8;
+        const int gemm = blk / (C::NC1 * C::KC1), bb = blk % (C::NC1 * C::KC1), nc = bb / C::KC1, kc = bb % C::KC1;
+        Wt = gemm == 0 ? Wo_t : W1_t;
+        M = F;
+        n = gemm == 0 ? (row < 64 ? nc * 64 + row : H + nc * 64 + (row - 64)) : nc * 128 + row;
+        k0 = kc * 64 + j * 8;
+        base = (size_t)blk * UM_STAGE;
+        NR = 128;
+    } else {
+        const size_t i3 = idx - g12;
+        const int blk = i3 / (C::NR3 * 8), rem = i3 % (C::NR3 * 8);
+        row = rem / 8;
+        j = rem % 8;
+        const int kc = blk / C::NC3, nc = blk % C::NC3;
+        Wt = W2_t;
+        M = H;
+        n = nc * C::NR3 + row;
+        k0 = kc * 64 + j * 8;
+        base = (size_t)2 * C::NC1 * C::KC1 * UM_STAGE + (size_t)blk * C::NR3 * 256;
+        NR = C::NR3;
+    }
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float w0 = Wt[(size_t)(k0 + 2 * e) * M + n], w1 = Wt[(size_t)(k0 + 2 * e + 1) * M + n];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(w0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(w1 - __bfloat162float(h1));
+        hp[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lp[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const size_t off = base + (size_t)row * 128 + ((j ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4 *>(img + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4 *>(img + off + (size_t)NR * 128) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+}
+
+bool mix_umma_supported(int H, int F, int l) { return F == 2 * H && (H == 64 || H == 128) && l >= 1; }
+
+size_t mix_umma_image_bytes(int H) {
+    return H == 64 ? UCfg<64, 2>::IMG_BYTES : (H == 128 ? UCfg<128, 2>::IMG_BYTES : 0);
+}
+
+int mix_umma_pack(int H, const float *Wo_t, const float *W1_t, const float *W2_t, const float *bo, const float *b1,
+                  const float *b2, uint8_t *img, float *bimg, cudaStream_t st) {
+    const size_t total = (size_t)(24 * H * H) / 32 + 5 * H;     // >= chunk pairs (24 H^2 bytes / 32) and bias entries
+    const unsigned grid = (unsigned)ceil_div64((int64_t)total, 256);
+    if (H == 64) umma_pack_kernel<64><<<grid, 256, 0, st>>>(Wo_t, W1_t, W2_t, bo, b1, b2, img, bimg);
+    else if (H == 128) umma_pack_kernel<128><<<grid, 256, 0, st>>>(Wo_t, W1_t, W2_t, bo, b1, b2, img, bimg);
+    else {
+        set_error("mix_umma_pack: H=%d unsupported", H);
+        return DWB_ERR_UNSUPPORTED;
+    }
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+template <int H, int CS>
+static int launch_umma(const MixArgs &a, int B, cudaStream_t st) {
+    using C = UCfg<H, CS>;
+    auto k = sashimi_mix_umma_kernel<H, CS>;
+    static_assert(C::SMEM <= 227 * 1024, "tile does not fit shared memory");
+    DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    dim3 grid(ceil_div(a.l, UM_TT), B);
+    k<<<grid, C::NTHREADS, C::SMEM, st>>>(a);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+int mix_umma_launch(const MixArgs &a, int B, cudaStream_t st) {
+    DWB_REQUIRE(a.Wimg && a.bimg, DWB_ERR_STATE, "mix_umma: weights were not packed");
+    switch (a.H) {
+        case 64: return launch_umma<64, 2>(a, B, st);
+        case 128: return launch_umma<128, 2>(a, B, st);
+    }
+    set_error("mix_umma: H=%d unsupported", a.H);
+    return DWB_ERR_UNSUPPORTED;
+}
+
+}  // namespace dwb

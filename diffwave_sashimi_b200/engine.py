@@ -270,6 +270,20 @@ class Engine:
         return {c: (ms[i] / iters, cnt[i] // iters) for i, c in enumerate(_lib.PROF_CATEGORIES) if cnt[i]}
 
     # ---- introspection ------------------------------------------------------------------
+    def mix_block(self, block, g, x, skip=None, exact=False):
+        """Channel-mixing half of DiffWaveBlock `block` on caller tensors (B,H,l): returns (out, stats).
+        exact=True forces the fp32 SIMT kernel (the parity reference of the tensor-core paths)."""
+        g = g.to(self.device, torch.float32).contiguous()
+        x = x.to(self.device, torch.float32).contiguous()
+        sk = None if skip is None else skip.to(self.device, torch.float32).contiguous()
+        B, H, l = x.shape
+        out = torch.empty_like(x)
+        stats = torch.empty(B, l, 2, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().dwb_plan_mix_block(self._plan, block, 1 if exact else 0, ptr(g), ptr(x), ptr(sk), ptr(out),
+                                           ptr(stats), B, stream_ptr(self.device)))
+        return out, stats
+
     def launch_count(self):
         n = ctypes.c_int64(0)
         check(lib().dwb_plan_launch_count(self._plan, ctypes.byref(n)))

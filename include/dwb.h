@@ -123,6 +123,12 @@ int dwb_plan_launch_count(dwb_plan *plan, int64_t *count);
 /* number of S4 blocks, and a copy of block i's generated time-domain kernel k (2,H,l) f32 */
 int dwb_plan_s4_blocks(dwb_plan *plan, int *n_blocks);
 int dwb_plan_s4_kernel(dwb_plan *plan, int block, float *k_out, int64_t capacity, int *H, int *l);
+/* Channel-mixing half of DiffWaveBlock `block` (models/sashimi.py:157-182 after the S4 convolution)
+ * on caller tensors: g, x (B,H,l) -> out (B,H,l), stats_out (B,l,2) = (mean, rstd over channels)
+ * of out; skip (B,H,l) or NULL.  exact != 0 forces the fp32 SIMT kernel, 0 takes the plan's path
+ * (tcgen05 where the width supports it). */
+int dwb_plan_mix_block(dwb_plan *plan, int block, int exact, const float *g, const float *x, const float *skip,
+                       float *out, float *stats_out, int B, void *stream);
 /* algorithmic HBM bytes and flops of one forward per clip (SURVEY.md §8(d) formulas) */
 int dwb_plan_work(dwb_plan *plan, int L, double *bytes_per_clip_step, double *flops_per_clip_step);
 
