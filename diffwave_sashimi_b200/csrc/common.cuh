@@ -47,12 +47,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // far inside the 1e-3 parity budget; the exact-fp32 SIMT path keeps erff.
 __device__ __forceinline__ float gelu_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float t;                                          // MUFU.RCP: 1 ulp, no IEEE slow path / branch
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
     float p = fmaf(t, 1.061405429f, -1.453152027f);
     p = fmaf(t, p, 1.421413741f);
     p = fmaf(t, p, -0.284496736f);
     p = fmaf(t, p, 0.254829592f);
-    const float e = (p * t) * __expf(-z * z);       // erfc(|x|/sqrt 2)
+    float e;                                          // exp(-z^2) = 2^(-z^2 log2 e)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+    e *= p * t;                                       // erfc(|x|/sqrt 2)
     const float h = 0.5f * x * e;                    // x < 0: 0.5 x (1 + erf) = 0.5 x erfc
     return x >= 0.f ? x - h : h;
 }

@@ -18,6 +18,7 @@ struct MixArgs {
     // tcgen05 path (mix_umma.cu): packed shared-memory image of the three weights + biases, or null
     const uint8_t *Wimg;
     const float *bimg;
+    long long *trace;              // debug: per-CTA phase timestamps (16 clock64 values per CTA), or null
     float ln2_m, ln2_s;
     float *out, *stats_out;        // (B,H,l), (B,l,2)
     int H, F, l;

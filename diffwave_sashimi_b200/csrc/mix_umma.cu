@@ -76,14 +76,10 @@ __device__ __forceinline__ void stat_merge16(const float (&v)[16], int n, float 
         const float d = v[i] - cm;
         c2 = fmaf(d, d, c2);
     }
-    if (n == 0) {
-        mean = cm;
-        M2 = c2;
-    } else {
-        const float delta = cm - mean, tot = (float)(n + 16);
-        mean = fmaf(delta, 16.0f / tot, mean);
-        M2 += c2 + delta * delta * ((float)n * 16.0f / tot);
-    }
+    // n == 0 with (mean, M2) = (0, 0) reduces to (cm, c2)
+    const float delta = cm - mean, w = __fdividef(16.0f, (float)(n + 16));
+    mean = fmaf(delta, w, mean);
+    M2 += c2 + delta * delta * ((float)n * w);
 }
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -105,6 +101,23 @@ sashimi_mix_umma_kernel(MixArgs a) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, t0 = blockIdx.x * UM_TT, l = a.l;
+    long long *trace = a.trace ? a.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+#define UM_TRACE(slot) do { if (trace && tid == 0) trace[slot] = clock64(); } while (0)
+#define UM_TRACE_MMA(slot) do { if (trace) trace[slot] = clock64(); } while (0)
+    UM_TRACE(0);
+
+    // epilogue threads: one time step each (row r of the tile), column group cg
+    const bool is_epi = warp < 4 * CS;
+    const int q = warp & 3, cg = warp >> 2;
+    const int r = 32 * q + lane, t = t0 + r;
+    const bool valid = is_epi && t < l;
+    const size_t brow = (size_t)b * H * l + (valid ? t : 0);
+    constexpr int PER = H / CS;                        // channels per epilogue thread
+    float gin[PER];                                    // g of this thread's channels: in flight across the setup
+    if (is_epi) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) gin[i] = valid ? __ldg(a.g + brow + (size_t)(cg * PER + i) * l) : 0.f;
+    }
 
     if (tid == 0) {
         for (int i = 0; i < C::NS; ++i) {
@@ -127,6 +140,7 @@ sashimi_mix_umma_kernel(MixArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tptr;
+    UM_TRACE(1);
 
     if (warp == 4 * CS) {
         // ================= weight producer: the packed image, one ring stage at a time =========
@@ -156,10 +170,14 @@ sashimi_mix_umma_kernel(MixArgs a) {
                 }
             };
             int i = 0;
+#pragma unroll 1
             for (int gemm = 0; gemm < 2; ++gemm) {
                 mbar_wait(gemm == 0 ? g_ready : z_ready, 0);
                 tc_fence_after();
+                UM_TRACE_MMA(12 + gemm);
+#pragma unroll 1
                 for (int nc = 0; nc < C::NC1; ++nc) {
+#pragma unroll 1
                     for (int kc = 0; kc < C::KC1; ++kc, ++i) {
                         const int s = i % C::NS;
                         mbar_wait(wfull + s, (i / C::NS) & 1);
@@ -170,9 +188,11 @@ sashimi_mix_umma_kernel(MixArgs a) {
                     mma_commit((gemm == 0 ? acc1_ready : acc2_ready) + nc);
                 }
             }
+#pragma unroll 1
             for (int kc = 0; kc < C::KC3; ++kc) {
                 mbar_wait(hid_ready + kc, 0);
                 tc_fence_after();
+#pragma unroll 1
                 for (int nc = 0; nc < C::NC3; ++nc) {
                     const int j = kc * C::NC3 + nc, s = i % C::NS;
                     if (j % C::BPS3 == 0) {
@@ -188,62 +208,74 @@ sashimi_mix_umma_kernel(MixArgs a) {
                 }
             }
             mma_commit(acc3_ready);
+            UM_TRACE_MMA(14);
         }
     } else {
-        // ================= epilogue threads: one time step each, column group cg ================
-        const int q = warp & 3, cg = warp >> 2;
-        const int r = 32 * q + lane, t = t0 + r;
-        const bool valid = t < l;
+        // ================= epilogue threads ======================================================
         const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
-        const size_t brow = (size_t)b * H * l + (valid ? t : 0);
-        const float *gp = a.g + brow, *xp = a.x + brow;
+        const float *xp = a.x + brow;
         float *op = a.out + brow;
         const float *bo_s = bias_s, *b1_s = bias_s + 2 * H, *b2_s = bias_s + 4 * H;
+        constexpr int PP = 64 / CS;                        // GLU pairs per thread per N chunk
 
-        // ---- load g, split, store as the A operand of G1
+        // ---- g: split, store as the A operand of G1
         {
-            constexpr int PER = H / CS;                    // channels per thread
 #pragma unroll
-            for (int c16 = 0; c16 < PER / 16; ++c16) {
-                const int h0 = cg * PER + c16 * 16;
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = valid ? __ldg(gp + (size_t)(h0 + i) * l) : 0.f;
+            for (int c8 = 0; c8 < PER / 8; ++c8) {
+                const int h0 = cg * PER + c8 * 8;
+                uint4 hi, lo;
+                split8(gin + 8 * c8, hi, lo);
                 uint8_t *slot = slots + (h0 >> 6) * UM_SLOT;
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint4 hi, lo;
-                    split8(v + 8 * hh, hi, lo);
-                    const uint32_t off = sw128_off(r, ((h0 & 63) >> 3) + hh);
-                    *reinterpret_cast<uint4 *>(slot + off) = hi;
-                    *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
-                }
+                const uint32_t off = sw128_off(r, (h0 & 63) >> 3);
+                *reinterpret_cast<uint4 *>(slot + off) = hi;
+                *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
             }
             fence_proxy_async_smem();
             mbar_arrive(g_ready);
+            UM_TRACE(2);
+        }
+        // ---- x of this thread's channels -> TMEM R3 while G1 runs (E1 turns it into x1 in place)
+        {
+            float xin[PER];
+#pragma unroll
+            for (int nc = 0; nc < C::NC1; ++nc)
+#pragma unroll
+                for (int i = 0; i < PP; ++i)
+                    xin[nc * PP + i] = valid ? __ldg(xp + (size_t)(nc * 64 + cg * PP + i) * l) : 0.f;
+#pragma unroll
+            for (int nc = 0; nc < C::NC1; ++nc)
+#pragma unroll
+                for (int sc = 0; sc < PP / 16; ++sc) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = xin[nc * PP + sc * 16 + i];
+                    tmem_st16(tl + C::R3 + nc * 64 + cg * PP + sc * 16, v);
+                }
+            tmem_wait_st();
+            UM_TRACE(3);
         }
 
         // ---- E1: GLU + residual -> x1 (TMEM R3), LN2 statistics
         float mean = 0.f, M2 = 0.f;
         {
-            constexpr int PP = 64 / CS;                    // GLU pairs per thread per N chunk
             int n = 0;
-#pragma unroll
+#pragma unroll 1
             for (int nc = 0; nc < C::NC1; ++nc) {
                 mbar_wait(acc1_ready + nc, 0);
                 tc_fence_after();
-#pragma unroll
+                if (nc == 0) UM_TRACE(4);
+#pragma unroll 1
                 for (int sc = 0; sc < PP / 16; ++sc) {
                     const int p0 = cg * PP + sc * 16, h0 = nc * 64 + p0;
                     float xv[16], av[16], gv[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) xv[i] = valid ? __ldg(xp + (size_t)(h0 + i) * l) : 0.f;
                     tmem_ld16(tl + nc * 128 + p0, av);
                     tmem_ld16(tl + nc * 128 + 64 + p0, gv);
+                    tmem_ld16(tl + C::R3 + h0, xv);
                     tmem_wait_ld();
+                    const float *ba = bo_s + nc * 128 + p0;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float y = (av[i] + bo_s[nc * 128 + p0 + i]) * sigmoid_fast(gv[i] + bo_s[nc * 128 + 64 + p0 + i]);
+                        float y = (av[i] + ba[i]) * sigmoid_fast(gv[i] + ba[64 + i]);
                         if (a.cond && valid) y += __ldg(a.cond + ((size_t)(a.cond_stride_b ? b : 0) * H + h0 + i) * l + t);
                         xv[i] += y;
                     }
@@ -253,6 +285,7 @@ sashimi_mix_umma_kernel(MixArgs a) {
                 }
             }
             tmem_wait_st();
+            UM_TRACE(5);
         }
         if (CS > 1) {
             ex[cg * 128 + r] = make_float2(mean, M2);
@@ -275,47 +308,48 @@ sashimi_mix_umma_kernel(MixArgs a) {
         {
             const float rstd = valid ? rsqrtf(M2 * (1.0f / H)) : 0.f;
             const float sc_a = a.ln2_s * rstd, sh = a.ln2_m - mean;
-            constexpr int PP = 64 / CS;
+#pragma unroll 1
+            for (int it = 0; it < PER / 16; ++it) {
+                const int nc = it / (PP / 16), sc = it % (PP / 16);
+                const int h0 = nc * 64 + cg * PP + sc * 16;
+                float v[16];
+                tmem_ld16(tl + C::R3 + h0, v);
+                tmem_wait_ld();
 #pragma unroll
-            for (int nc = 0; nc < C::NC1; ++nc)
+                for (int i = 0; i < 16; ++i) v[i] = sc_a * (v[i] + sh);
+                uint8_t *slot = slots + (h0 >> 6) * UM_SLOT;
 #pragma unroll
-                for (int sc = 0; sc < PP / 16; ++sc) {
-                    const int p0 = cg * PP + sc * 16, h0 = nc * 64 + p0;
-                    float v[16];
-                    tmem_ld16(tl + C::R3 + h0, v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = sc_a * (v[i] + sh);
-                    uint8_t *slot = slots + (h0 >> 6) * UM_SLOT;
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint4 hi, lo;
-                        split8(v + 8 * hh, hi, lo);
-                        const uint32_t off = sw128_off(r, ((h0 & 63) >> 3) + hh);
-                        *reinterpret_cast<uint4 *>(slot + off) = hi;
-                        *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
-                    }
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint4 hi, lo;
+                    split8(v + 8 * hh, hi, lo);
+                    const uint32_t off = sw128_off(r, ((h0 & 63) >> 3) + hh);
+                    *reinterpret_cast<uint4 *>(slot + off) = hi;
+                    *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
                 }
+            }
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(z_ready);
+            UM_TRACE(6);
         }
 
         // ---- E2: hidden = gelu(W1 z + b1), split, store as the A operand of G3
         {
-            constexpr int PER = 128 / CS;                  // f columns per thread per N chunk
-#pragma unroll
+            constexpr int PERF = 128 / CS;                 // f columns per thread per N chunk
+#pragma unroll 1
             for (int nc = 0; nc < C::NC1; ++nc) {
                 mbar_wait(acc2_ready + nc, 0);
                 tc_fence_after();
-#pragma unroll
-                for (int sc = 0; sc < PER / 16; ++sc) {
-                    const int col = cg * PER + sc * 16, f0 = nc * 128 + col;
+                if (nc == 0) UM_TRACE(7);
+#pragma unroll 1
+                for (int sc = 0; sc < PERF / 16; ++sc) {
+                    const int col = cg * PERF + sc * 16, f0 = nc * 128 + col;
                     float v[16];
                     tmem_ld16(tl + nc * 128 + col, v);
                     tmem_wait_ld();
+                    const float *bb = b1_s + f0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i] + b1_s[f0 + i]);
+                    for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i] + bb[i]);
                     const int kc = f0 >> 6;
                     uint8_t *slot = slots + C::hid_slot(kc) * UM_SLOT;
 #pragma unroll
@@ -327,7 +361,7 @@ sashimi_mix_umma_kernel(MixArgs a) {
                         *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
                     }
                     // last 16 columns this thread contributes to K chunk kc
-                    if (((f0 + 16) & 63) == 0 || sc == PER / 16 - 1) {
+                    if (((f0 + 16) & 63) == 0 || sc == PERF / 16 - 1) {
                         fence_proxy_async_smem();
                         tc_fence_before();
                         mbar_arrive(hid_ready + kc);
@@ -338,26 +372,28 @@ sashimi_mix_umma_kernel(MixArgs a) {
 
         // ---- E3: x2 = acc3 (= x1 + W2 hidden) + b2 (+skip); store; statistics for the next norm
         {
-            constexpr int PER = H / CS;
+            float sk[PER];
+            if (a.skip) {
+#pragma unroll
+                for (int i = 0; i < PER; ++i) sk[i] = valid ? __ldg(a.skip + brow + (size_t)(cg * PER + i) * l) : 0.f;
+            }
+            UM_TRACE(8);
             mbar_wait(acc3_ready, 0);
             tc_fence_after();
+            UM_TRACE(9);
             int n = 0;
             mean = 0.f;
             M2 = 0.f;
 #pragma unroll
             for (int sc = 0; sc < PER / 16; ++sc) {
                 const int h0 = cg * PER + sc * 16;
-                float v[16], sk[16];
-                if (a.skip) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) sk[i] = valid ? __ldg(a.skip + brow + (size_t)(h0 + i) * l) : 0.f;
-                }
+                float v[16];
                 tmem_ld16(tl + C::R3 + h0, v);
                 tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     v[i] += b2_s[h0 + i];
-                    if (a.skip) v[i] += sk[i];
+                    if (a.skip) v[i] += sk[sc * 16 + i];
                 }
                 if (valid) {
 #pragma unroll
@@ -388,8 +424,10 @@ sashimi_mix_umma_kernel(MixArgs a) {
                 *reinterpret_cast<float2 *>(a.stats_out + ((size_t)b * l + t) * 2) = make_float2(mean, rsqrtf(M2 * (1.0f / H)));
         }
     }
+    UM_TRACE(10);
     tc_fence_before();
     __syncthreads();
+    UM_TRACE(11);
     if (warp == 4 * CS + 1) {
         tc_fence_after();
         tmem_dealloc(tmem, C::TMEM_COLS);

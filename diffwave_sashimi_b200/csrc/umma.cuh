@@ -31,12 +31,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"     // hardware sleep up to the hint (ns)
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(20000u)
         : "memory");
 }
 
