@@ -21,6 +21,11 @@
 //
 // Roles: warps [0, 4*CS) epilogue (CS threads per time step, each a contiguous column group),
 // warp 4*CS = weight producer (one lane), warp 4*CS+1 = TMEM owner + MMA issuer (one lane).
+#include <stdlib.h>
+
+#include <algorithm>
+#include <string>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "umma.cuh"
@@ -115,8 +120,9 @@ sashimi_mix_umma_kernel(MixArgs a) {
     constexpr int PER = H / CS;                        // channels per epilogue thread
     float gin[PER];                                    // g of this thread's channels: in flight across the setup
     if (is_epi) {
+        const float *gp = a.g + brow + cg * PER * l;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) gin[i] = valid ? __ldg(a.g + brow + (size_t)(cg * PER + i) * l) : 0.f;
+        for (int i = 0; i < PER; ++i, gp += l) gin[i] = valid ? __ldg(gp) : 0.f;
     }
 
     if (tid == 0) {
@@ -238,10 +244,11 @@ sashimi_mix_umma_kernel(MixArgs a) {
         {
             float xin[PER];
 #pragma unroll
-            for (int nc = 0; nc < C::NC1; ++nc)
+            for (int nc = 0; nc < C::NC1; ++nc) {
+                const float *xq = xp + (nc * 64 + cg * PP) * l;
 #pragma unroll
-                for (int i = 0; i < PP; ++i)
-                    xin[nc * PP + i] = valid ? __ldg(xp + (size_t)(nc * 64 + cg * PP + i) * l) : 0.f;
+                for (int i = 0; i < PP; ++i, xq += l) xin[nc * PP + i] = valid ? __ldg(xq) : 0.f;
+            }
 #pragma unroll
             for (int nc = 0; nc < C::NC1; ++nc)
 #pragma unroll
@@ -276,7 +283,7 @@ sashimi_mix_umma_kernel(MixArgs a) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         float y = (av[i] + ba[i]) * sigmoid_fast(gv[i] + ba[64 + i]);
-                        if (a.cond && valid) y += __ldg(a.cond + ((size_t)(a.cond_stride_b ? b : 0) * H + h0 + i) * l + t);
+                        if (a.cond && valid) y += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i) * l);
                         xv[i] += y;
                     }
                     stat_merge16(xv, n, mean, M2);
@@ -374,8 +381,9 @@ sashimi_mix_umma_kernel(MixArgs a) {
         {
             float sk[PER];
             if (a.skip) {
+                const float *sp = a.skip + brow + cg * PER * l;
 #pragma unroll
-                for (int i = 0; i < PER; ++i) sk[i] = valid ? __ldg(a.skip + brow + (size_t)(cg * PER + i) * l) : 0.f;
+                for (int i = 0; i < PER; ++i, sp += l) sk[i] = valid ? __ldg(sp) : 0.f;
             }
             UM_TRACE(8);
             mbar_wait(acc3_ready, 0);
@@ -396,8 +404,9 @@ sashimi_mix_umma_kernel(MixArgs a) {
                     if (a.skip) v[i] += sk[sc * 16 + i];
                 }
                 if (valid) {
+                    float *oq = op + h0 * l;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) op[(size_t)(h0 + i) * l] = v[i];
+                    for (int i = 0; i < 16; ++i, oq += l) *oq = v[i];
                 }
                 stat_merge16(v, n, mean, M2);
                 n += 16;
@@ -431,6 +440,418 @@ sashimi_mix_umma_kernel(MixArgs a) {
     if (warp == 4 * CS + 1) {
         tc_fence_after();
         tmem_dealloc(tmem, C::TMEM_COLS);
+    }
+}
+
+// =========================================================================================
+// Persistent variant: one CTA per SM walks a strided list of tiles.  NG independent groups of
+// epilogue warps (each with its own MMA-issuer warp, barriers, operand slots and TMEM columns)
+// keep NG tiles in flight, so the waits of one group (HBM loads, MMA round trips) are filled by
+// the other's arithmetic; barriers, TMEM and (H = 64) the whole 96 KB weight image are set up
+// once per CTA instead of once per tile, and the next tile's g is already in flight while the
+// current tile finishes.  H = 128 has room for one group only (its operands need 128 KB) and
+// keeps streaming the 384 KB weight image through the ring.
+// =========================================================================================
+template <int H, int CS>
+struct PCfg {
+    using U = UCfg<H, CS>;
+    static constexpr int NG = (H == 64) ? 2 : 1;
+    static constexpr bool RESIDENT = (H == 64);
+    static constexpr int GW = 4 * CS, EPI = 128 * CS;
+    static constexpr int NTHREADS = NG * EPI + NG * 32 + 32;
+    static constexpr int NS = RESIDENT ? U::NSTG : 2;          // weight buffers (RESIDENT: one per stage)
+    static constexpr int GCOLS = 512 / NG;                     // TMEM columns per group
+    static constexpr int XCOL = 3 * H;                         // spare columns: statistics exchange
+    static constexpr int NBAR_G = 2 + U::KC3 + 2 * U::NC1 + 1;
+    static constexpr int NBAR = NG * NBAR_G + 2 * NS;
+    static constexpr int OFF_SLOT = 0;
+    static constexpr int OFF_W = OFF_SLOT + NG * U::NSLOT * UM_SLOT;
+    static constexpr int OFF_BIAS = OFF_W + NS * UM_STAGE;
+    static constexpr int OFF_BAR = OFF_BIAS + 5 * H * 4;
+    static constexpr int OFF_TPTR = OFF_BAR + NBAR * 8;
+    static constexpr int SMEM = OFF_TPTR + 16 + 1024;
+    static_assert(XCOL + 2 * CS <= GCOLS, "no spare TMEM columns for the statistics exchange");
+    static_assert(SMEM <= 227 * 1024, "persistent tile set does not fit shared memory");
+};
+
+template <int H, int CS>
+__global__ void __launch_bounds__(PCfg<H, CS>::NTHREADS, 1)
+sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
+    using P = PCfg<H, CS>;
+    using C = UCfg<H, CS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *wbuf = sm + P::OFF_W;
+    float *bias_s = reinterpret_cast<float *>(sm + P::OFF_BIAS);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + P::OFF_BAR);
+    uint32_t *tptr = reinterpret_cast<uint32_t *>(sm + P::OFF_TPTR);
+    uint64_t *wfull = bars + P::NG * P::NBAR_G, *wempty = wfull + P::NS;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int l = a.l, ntx = ceil_div(l, UM_TT), ntiles = B * ntx;
+    const int stride = gridDim.x * P::NG;
+    long long *trace = a.trace ? a.trace + (size_t)blockIdx.x * 16 : nullptr;
+
+    if (tid == 0) {
+        for (int g = 0; g < P::NG; ++g) {
+            uint64_t *gb = bars + g * P::NBAR_G;
+            mbar_init(gb + 0, P::EPI);                                    // g_ready
+            mbar_init(gb + 1, P::EPI);                                    // z_ready
+            for (int i = 0; i < C::KC3; ++i) mbar_init(gb + 2 + i, C::HID_ARRIVE);
+            for (int i = 0; i < 2 * C::NC1 + 1; ++i) mbar_init(gb + 2 + C::KC3 + i, 1);   // acc1[], acc2[], acc3
+        }
+        for (int i = 0; i < P::NS; ++i) {
+            mbar_init(wfull + i, 1);
+            mbar_init(wempty + i, 1);
+        }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 5 * H; i += P::NTHREADS) bias_s[i] = a.bimg[i];
+    constexpr int EPI_WARPS = P::NG * P::GW;
+    if (warp == EPI_WARPS) tmem_alloc(tptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = *tptr;
+
+    if (warp == EPI_WARPS + P::NG) {
+        // ================= weight producer =====================================================
+        if (lane == 0) {
+            if (P::RESIDENT) {
+                for (int i = 0; i < C::NSTG; ++i) {
+                    mbar_arrive_expect_tx(wfull + i, UM_STAGE);
+                    bulk_g2s(wbuf + (size_t)i * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + i);
+                }
+            } else {
+                int cnt = 0;
+                for (int tile = blockIdx.x * P::NG; tile < ntiles; tile += stride)
+                    for (int i = 0; i < C::NSTG; ++i, ++cnt) {
+                        const int s = cnt % P::NS;
+                        mbar_wait(wempty + s, ((cnt / P::NS) & 1) ^ 1);
+                        mbar_arrive_expect_tx(wfull + s, UM_STAGE);
+                        bulk_g2s(wbuf + (size_t)s * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + s);
+                    }
+            }
+        }
+    } else if (warp >= EPI_WARPS) {
+        // ================= MMA issuer of group grp ==============================================
+        const int grp = warp - EPI_WARPS;
+        if (lane == 0) {
+            uint64_t *gb = bars + grp * P::NBAR_G;
+            uint64_t *g_ready = gb, *z_ready = gb + 1, *hid_ready = gb + 2, *acc1_ready = hid_ready + C::KC3,
+                     *acc2_ready = acc1_ready + C::NC1, *acc3_ready = acc2_ready + C::NC1;
+            const uint32_t slot0 = smem_u32(sm + P::OFF_SLOT + grp * C::NSLOT * UM_SLOT), w0 = smem_u32(wbuf);
+            const uint32_t tmem = tmem0 + grp * P::GCOLS;
+            auto issue_block = [&](uint32_t d, uint32_t abase, uint32_t bbase, int NR, bool acc0) {
+                const uint32_t idesc = idesc_bf16(128, NR);
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t ao = abase + (term == 1 ? UM_SLOT / 2 : 0);
+                    const uint32_t bo = bbase + (term == 2 ? NR * 128 : 0);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_bf16_ss(d, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
+                                    (acc0 || term > 0 || ks > 0) ? 1u : 0u);
+                }
+            };
+            int cnt = 0;     // weight stages consumed so far (ring position when streaming)
+            uint32_t ph = 0;
+#pragma unroll 1
+            for (int tile = blockIdx.x * P::NG + grp; tile < ntiles; tile += stride, ph ^= 1) {
+                int i = 0;   // stage index inside the tile
+#pragma unroll 1
+                for (int gemm = 0; gemm < 2; ++gemm) {
+                    mbar_wait(gemm == 0 ? g_ready : z_ready, ph);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int nc = 0; nc < C::NC1; ++nc) {
+#pragma unroll 1
+                        for (int kc = 0; kc < C::KC1; ++kc, ++i, ++cnt) {
+                            const int s = P::RESIDENT ? i : cnt % P::NS;
+                            mbar_wait(wfull + s, P::RESIDENT ? 0u : (uint32_t)((cnt / P::NS) & 1));
+                            tc_fence_after();
+                            issue_block(tmem + nc * 128, slot0 + kc * UM_SLOT, w0 + s * UM_STAGE, 128, kc > 0);
+                            if (!P::RESIDENT) mma_commit(wempty + s);
+                        }
+                        mma_commit((gemm == 0 ? acc1_ready : acc2_ready) + nc);
+                    }
+                }
+#pragma unroll 1
+                for (int kc = 0; kc < C::KC3; ++kc) {
+                    mbar_wait(hid_ready + kc, ph);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int nc = 0; nc < C::NC3; ++nc) {
+                        const int j = kc * C::NC3 + nc;
+                        const int s = P::RESIDENT ? i : cnt % P::NS;
+                        if (j % C::BPS3 == 0) {
+                            mbar_wait(wfull + s, P::RESIDENT ? 0u : (uint32_t)((cnt / P::NS) & 1));
+                            tc_fence_after();
+                        }
+                        issue_block(tmem + C::R3 + nc * 128, slot0 + C::hid_slot(kc) * UM_SLOT,
+                                    w0 + s * UM_STAGE + (j % C::BPS3) * C::NR3 * 256, C::NR3, true);
+                        if (j % C::BPS3 == C::BPS3 - 1) {
+                            if (!P::RESIDENT) mma_commit(wempty + s);
+                            ++i;
+                            ++cnt;
+                        }
+                    }
+                }
+                mma_commit(acc3_ready);
+            }
+        }
+    } else {
+        // ================= epilogue threads of group grp =========================================
+        const int grp = warp / P::GW, cg = (warp % P::GW) >> 2, q = warp & 3;
+        const int r = 32 * q + lane;
+        uint64_t *gb = bars + grp * P::NBAR_G;
+        uint64_t *g_ready = gb, *z_ready = gb + 1, *hid_ready = gb + 2, *acc1_ready = hid_ready + C::KC3,
+                 *acc2_ready = acc1_ready + C::NC1, *acc3_ready = acc2_ready + C::NC1;
+        uint8_t *slots = sm + P::OFF_SLOT + grp * C::NSLOT * UM_SLOT;
+        const uint32_t tl = tmem0 + grp * P::GCOLS + ((uint32_t)(32 * q) << 16);
+        const float *bo_s = bias_s, *b1_s = bias_s + 2 * H, *b2_s = bias_s + 4 * H;
+        constexpr int PER = H / CS, PP = 64 / CS;
+        const int etid = tid - grp * P::EPI;         // thread index inside the group
+        const bool tracer = trace && grp == 0 && etid == 0;
+#define PT(slot) do { if (tracer && it == 1) trace[slot] = clock64(); } while (0)
+
+        // statistics exchange between the CS column groups of a time step (partners share the TMEM lane)
+        auto exchange = [&](float &mean, float &M2) {
+            if (CS > 1) {
+                tmem_st2(tl + P::XCOL + 2 * cg, mean, M2);
+                tmem_wait_st();
+                tc_fence_before();
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(P::EPI) : "memory");
+                tc_fence_after();
+                float pm[CS], p2[CS];
+#pragma unroll
+                for (int c = 0; c < CS; ++c) tmem_ld2(tl + P::XCOL + 2 * c, pm[c], p2[c]);
+                tmem_wait_ld();
+                float ms = 0.f;
+#pragma unroll
+                for (int c = 0; c < CS; ++c) ms += pm[c];
+                const float mt = ms * (1.0f / CS);
+                float m2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < CS; ++c) {
+                    const float d = pm[c] - mt;
+                    m2 += p2[c] + d * d * (float)(H / CS);
+                }
+                mean = mt;
+                M2 = m2;
+            }
+        };
+
+        int tile = blockIdx.x * P::NG + grp;
+        float gin[PER];
+        {
+            const int b = tile / ntx, t = (tile - b * ntx) * UM_TT + r;
+            const bool valid = tile < ntiles && t < l;
+            const size_t brow = (size_t)b * H * l + (valid ? t : 0);
+            const float *gp = a.g + brow + cg * PER * l;
+#pragma unroll
+            for (int i = 0; i < PER; ++i, gp += l) gin[i] = valid ? __ldg(gp) : 0.f;
+        }
+        uint32_t ph = 0;
+        int it = 0;
+        if (grp > 0 && stagger_ns > 0) __nanosleep(stagger_ns);     // start the groups out of phase
+#pragma unroll 1
+        for (; tile < ntiles; tile += stride, ph ^= 1, ++it) {
+            const int b = tile / ntx, t = (tile - b * ntx) * UM_TT + r;
+            const bool valid = t < l;
+            const size_t brow = (size_t)b * H * l + (valid ? t : 0);
+            const float *xp = a.x + brow;
+            float *op = a.out + brow;
+            PT(0);
+            // ---- g: split, store as the A operand of G1
+#pragma unroll
+            for (int c8 = 0; c8 < PER / 8; ++c8) {
+                const int h0 = cg * PER + c8 * 8;
+                uint4 hi, lo;
+                split8(gin + 8 * c8, hi, lo);
+                uint8_t *slot = slots + (h0 >> 6) * UM_SLOT;
+                const uint32_t off = sw128_off(r, (h0 & 63) >> 3);
+                *reinterpret_cast<uint4 *>(slot + off) = hi;
+                *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(g_ready);
+            PT(1);
+            // ---- x -> TMEM R3 while G1 runs
+            {
+                float xin[PER];
+#pragma unroll
+                for (int nc = 0; nc < C::NC1; ++nc) {
+                    const float *xq = xp + (nc * 64 + cg * PP) * l;
+#pragma unroll
+                    for (int i = 0; i < PP; ++i, xq += l) xin[nc * PP + i] = valid ? __ldg(xq) : 0.f;
+                }
+#pragma unroll
+                for (int nc = 0; nc < C::NC1; ++nc)
+#pragma unroll
+                    for (int sc = 0; sc < PP / 16; ++sc) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = xin[nc * PP + sc * 16 + i];
+                        tmem_st16(tl + C::R3 + nc * 64 + cg * PP + sc * 16, v);
+                    }
+                tmem_wait_st();
+            }
+            PT(2);
+            // ---- E1: GLU + residual -> x1 (TMEM R3), LN2 statistics
+            float mean = 0.f, M2 = 0.f;
+            {
+                int n = 0;
+#pragma unroll 1
+                for (int nc = 0; nc < C::NC1; ++nc) {
+                    mbar_wait(acc1_ready + nc, ph);
+                    tc_fence_after();
+                    if (nc == 0) PT(3);
+#pragma unroll 1
+                    for (int sc = 0; sc < PP / 16; ++sc) {
+                        const int p0 = cg * PP + sc * 16, h0 = nc * 64 + p0;
+                        float xv[16], av[16], gv[16];
+                        tmem_ld16(tl + nc * 128 + p0, av);
+                        tmem_ld16(tl + nc * 128 + 64 + p0, gv);
+                        tmem_ld16(tl + C::R3 + h0, xv);
+                        tmem_wait_ld();
+                        const float *ba = bo_s + nc * 128 + p0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float y = (av[i] + ba[i]) * sigmoid_fast(gv[i] + ba[64 + i]);
+                            if (a.cond && valid) y += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i) * l);
+                            xv[i] += y;
+                        }
+                        stat_merge16(xv, n, mean, M2);
+                        n += 16;
+                        tmem_st16(tl + C::R3 + h0, xv);
+                    }
+                }
+                tmem_wait_st();
+            }
+            PT(4);
+            exchange(mean, M2);
+            // ---- z = LN2(x1), split, store as the A operand of G2
+            {
+                const float rstd = valid ? rsqrtf(M2 * (1.0f / H)) : 0.f;
+                const float sc_a = a.ln2_s * rstd, sh = a.ln2_m - mean;
+#pragma unroll 1
+                for (int k = 0; k < PER / 16; ++k) {
+                    const int nc = k / (PP / 16), sc = k % (PP / 16);
+                    const int h0 = nc * 64 + cg * PP + sc * 16;
+                    float v[16];
+                    tmem_ld16(tl + C::R3 + h0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = sc_a * (v[i] + sh);
+                    uint8_t *slot = slots + (h0 >> 6) * UM_SLOT;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint4 hi, lo;
+                        split8(v + 8 * hh, hi, lo);
+                        const uint32_t off = sw128_off(r, ((h0 & 63) >> 3) + hh);
+                        *reinterpret_cast<uint4 *>(slot + off) = hi;
+                        *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
+                    }
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(z_ready);
+            }
+            PT(5);
+            // ---- E2: hidden = gelu(W1 z + b1), split, store as the A operand of G3
+            {
+                constexpr int PERF = 128 / CS;
+#pragma unroll 1
+                for (int nc = 0; nc < C::NC1; ++nc) {
+                    mbar_wait(acc2_ready + nc, ph);
+                    tc_fence_after();
+                    if (nc == 0) PT(6);
+#pragma unroll 1
+                    for (int sc = 0; sc < PERF / 16; ++sc) {
+                        const int col = cg * PERF + sc * 16, f0 = nc * 128 + col;
+                        float v[16];
+                        tmem_ld16(tl + nc * 128 + col, v);
+                        tmem_wait_ld();
+                        const float *bb = b1_s + f0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i] + bb[i]);
+                        const int kc = f0 >> 6;
+                        uint8_t *slot = slots + C::hid_slot(kc) * UM_SLOT;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint4 hi, lo;
+                            split8(v + 8 * hh, hi, lo);
+                            const uint32_t off = sw128_off(r, ((f0 & 63) >> 3) + hh);
+                            *reinterpret_cast<uint4 *>(slot + off) = hi;
+                            *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
+                        }
+                        if (((f0 + 16) & 63) == 0 || sc == PERF / 16 - 1) {
+                            fence_proxy_async_smem();
+                            tc_fence_before();
+                            mbar_arrive(hid_ready + kc);
+                        }
+                    }
+                }
+            }
+            PT(7);
+            // ---- the next tile's g goes in flight now and lands while E3 runs
+            {
+                const int nt = tile + stride;
+                const int nb = nt / ntx, ntm = (nt - nb * ntx) * UM_TT + r;
+                const bool nvalid = nt < ntiles && ntm < l;
+                const size_t nrow = (size_t)nb * H * l + (nvalid ? ntm : 0);
+                const float *gp = a.g + nrow + cg * PER * l;
+#pragma unroll
+                for (int i = 0; i < PER; ++i, gp += l) gin[i] = nvalid ? __ldg(gp) : 0.f;
+            }
+            // ---- E3: x2 = acc3 (= x1 + W2 hidden) + b2 (+skip); store; statistics for the next norm
+            {
+                mbar_wait(acc3_ready, ph);
+                tc_fence_after();
+                PT(8);
+                int n = 0;
+                mean = 0.f;
+                M2 = 0.f;
+#pragma unroll 1
+                for (int sc = 0; sc < PER / 16; ++sc) {
+                    const int h0 = cg * PER + sc * 16;
+                    float v[16];
+                    tmem_ld16(tl + C::R3 + h0, v);
+                    if (a.skip) {
+                        float sk[16];
+                        const float *sp = a.skip + brow + h0 * l;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i, sp += l) sk[i] = valid ? __ldg(sp) : 0.f;
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += sk[i];
+                    } else
+                        tmem_wait_ld();
+                    const float *bb = b2_s + h0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += bb[i];
+                    if (valid) {
+                        float *oq = op + h0 * l;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i, oq += l) *oq = v[i];
+                    }
+                    stat_merge16(v, n, mean, M2);
+                    n += 16;
+                }
+                exchange(mean, M2);
+                if (cg == 0 && valid)
+                    *reinterpret_cast<float2 *>(a.stats_out + ((size_t)b * l + t) * 2) = make_float2(mean, rsqrtf(M2 * (1.0f / H)));
+            }
+            PT(9);
+        }
+#undef PT
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EPI_WARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem0, 512);
     }
 }
 
@@ -533,8 +954,41 @@ static int launch_umma(const MixArgs &a, int B, cudaStream_t st) {
     return DWB_OK;
 }
 
+template <int H, int CS>
+static int launch_umma_pers(const MixArgs &a, int B, cudaStream_t st) {
+    using P = PCfg<H, CS>;
+    auto k = sashimi_mix_umma_pers_kernel<H, CS>;
+    static int sms[16] = {};
+    int dev = 0;
+    DWB_CUDA(cudaGetDevice(&dev));
+    if (!sms[dev & 15]) {
+        DWB_CUDA(cudaDeviceGetAttribute(&sms[dev & 15], cudaDevAttrMultiProcessorCount, dev));
+        DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+    }
+    const int ntiles = B * ceil_div(a.l, UM_TT);
+    const int grid = std::min(sms[dev & 15], ceil_div(ntiles, P::NG));
+    static const int stagger = [] { const char *e = getenv("DWB_UMMA_STAGGER"); return e ? atoi(e) : 0; }();
+    k<<<grid, P::NTHREADS, P::SMEM, st>>>(a, B, stagger);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
 int mix_umma_launch(const MixArgs &a, int B, cudaStream_t st) {
     DWB_REQUIRE(a.Wimg && a.bimg, DWB_ERR_STATE, "mix_umma: weights were not packed");
+    DWB_REQUIRE((int64_t)a.H * a.l < (int64_t)1 << 31, DWB_ERR_UNSUPPORTED, "mix_umma: H*l = %lld needs 64-bit channel offsets",
+                (long long)a.H * a.l);
+    // measured (B200, unet d64, B = 32): H = 64 is fastest as two per-tile CTAs per SM (2.53 ms per forward vs
+    // 2.72 persistent); H = 128 fits one tile per SM either way and gains from the persistent loop (1.65 vs 1.71).
+    // DWB_UMMA=tile / pers forces one variant for both widths.
+    static const int mode = [] {
+        const char *e = getenv("DWB_UMMA");
+        return !e ? 0 : (std::string(e) == "tile" ? 1 : (std::string(e) == "pers" ? 2 : 0));
+    }();
+    const bool pers = mode == 2 || (mode == 0 && a.H == 128);
+    if (pers) switch (a.H) {
+        case 64: return launch_umma_pers<64, 2>(a, B, st);
+        case 128: return launch_umma_pers<128, 2>(a, B, st);
+    }
     switch (a.H) {
         case 64: return launch_umma<64, 2>(a, B, st);
         case 128: return launch_umma<128, 2>(a, B, st);

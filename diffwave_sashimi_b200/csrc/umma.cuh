@@ -88,6 +88,19 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
         : "memory");
 }
 
+// 2 columns (the cross-column-group statistics exchange: partners share a TMEM lane)
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float &v0, float &v1) {
+    uint32_t r0, r1;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+    v0 = __uint_as_float(r0);
+    v1 = __uint_as_float(r1);
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, float v0, float v1) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};\n" ::"r"(taddr), "r"(__float_as_uint(v0)),
+                 "r"(__float_as_uint(v1))
+                 : "memory");
+}
+
 // ---- descriptors --------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major SW128, dense 8-row groups (SBO = 1024 B)
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
