@@ -376,14 +376,14 @@ static int finalize_sashimi(dwb_plan *p, cudaStream_t st) {
                 TRY(dev_alloc(p, (size_t)2 * H * l * sizeof(float), &k32));
                 const int lg = fft_log2m_for(l);
                 DWB_REQUIRE(lg > 0, DWB_ERR_UNSUPPORTED, "stage length %d exceeds the in-shared-memory FFT (max %d)", l, 1 << FFT_MAX_LOG2M);
-                TRY(dev_alloc(p, (size_t)H * ((1 << lg) + 1) * 2 * sizeof(float), &kf));
+                TRY(dev_alloc(p, (size_t)H * fft_table_floats(lg) * sizeof(float), &kf));
                 TRY(s4_generate((const float *)C->dev, (const float *)B->dev, (const float *)P->dev, (const float *)iwr->dev,
                                 (const float *)wim->dev, (const float *)ldt->dev, om ? (const float *)om->dev : nullptr, H, N, l,
                                 khat, k64, (float *)k32, st, &p->launches));
                 TRY(fftconv_prepare_f64(k64, (const float *)D->dev, H, l, (float *)kf, st));
                 p->launches += 1;
-                const float2 *tw, *twp;
-                TRY(fft_twiddles(lg, st, &tw, &twp));
+                const float2 *tw;
+                TRY(fft_twiddles(lg, st, &tw));
                 o.k32 = (float *)k32; o.kf = (float *)kf;
                 TRY(scalar_of(p, o.prefix + "norm1.m", &o.ln1_m, st));
                 TRY(scalar_of(p, o.prefix + "norm1.s", &o.ln1_s, st));

@@ -2,10 +2,10 @@
 // builder (s4_kernelgen.cu), which must agree on the digit-reversed order of the spectrum.
 //
 // The length-n real convolution is done as one M = n/2 point complex FFT per (batch, channel)
-// row, in place in shared memory: decimation-in-frequency forward passes (natural -> digit
-// reversed), the real-FFT untangle + spectrum product + re-tangle directly in digit-reversed
-// order, then decimation-in-time inverse passes (digit reversed -> natural).  No reordering
-// pass ever runs; the cached spectrum is simply stored in the order the forward passes leave.
+// row, in place in shared memory: decimation-in-frequency forward passes (natural -> bit
+// reversed), the real-FFT untangle + spectrum product + re-tangle directly in bit-reversed
+// order, then decimation-in-time inverse passes (bit reversed -> natural).  No reordering
+// pass ever runs; the cached pointwise table is simply stored in the order the forward passes leave.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -29,31 +29,19 @@ __host__ __device__ inline int fft_log2m_for(int l) {
     return 0;
 }
 
-// slot in shared memory (before padding) where the forward passes leave X[k]:
-// k = q0 + R0 (q1 + R1 (q2 + ...)),  pos = q0 M/R0 + q1 M/(R0 R1) + ...
-__host__ __device__ inline int fft_pos(int k, int log2M) {
-    int pos = 0, shift = log2M;
-    const int np = fft_num_passes(log2M);
-    for (int p = 0; p < np; ++p) {
-        const int lr = fft_radix_log2(log2M, p);
-        shift -= lr;
-        pos |= (k & ((1 << lr) - 1)) << shift;
-        k >>= lr;
-    }
-    return pos;
+// bit reversal of the low `bits` bits
+__host__ __device__ constexpr int fft_brev(int q, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((q >> i) & 1) << (bits - 1 - i);
+    return r;
 }
-// inverse map: which frequency sits in slot pos
-__host__ __device__ inline int fft_freq(int pos, int log2M) {
-    int k = 0, shift = log2M, kshift = 0;
-    const int np = fft_num_passes(log2M);
-    for (int p = 0; p < np; ++p) {
-        const int lr = fft_radix_log2(log2M, p);
-        shift -= lr;
-        k |= ((pos >> shift) & ((1 << lr) - 1)) << kshift;
-        kshift += lr;
-    }
-    return k;
-}
+// Slot (before padding) where the forward passes leave X[k]: every pass stores its output digit
+// bit-reversed, so the overall order is the plain bit reversal of k.  The partner of slot p in the
+// real-FFT untangle, the slot of X[M - k], is then p ^ ((1 << msb(p)) - 1): no table, no digit math.
+__host__ __device__ constexpr int fft_pos(int k, int log2M) { return fft_brev(k, log2M); }
+__host__ __device__ constexpr int fft_freq(int pos, int log2M) { return fft_brev(pos, log2M); }
+// floats per channel of the cached pointwise table used by fftconv: M/2 + 1 entries of 8
+__host__ __device__ constexpr long long fft_table_floats(int log2M) { return 8LL * ((1LL << (log2M - 1)) + 1); }
 
 // shared-memory padding: one float2 of slack per 16 so that the stride-16 and stride-1
 // passes (16 consecutive elements per thread) are bank-conflict free

@@ -4,13 +4,26 @@
 //
 // Reference: models/sashimi.py:148-152 (norm1 + fc_t), models/s4.py:1391-1411 (two-sided kernel,
 // rfft/irfft product at n = 2l, D skip), :1430 (GELU).  The reference calls cuFFT three times per
-// layer per step and regenerates rfft(k) every time; here the spectrum is cached
+// layer per step and regenerates rfft(k) every time; here the kernel spectrum is cached
 // (s4_kernelgen.cu) with D folded in, n is padded to a power of two >= 2l (wrapped kernel
 // layout, identical result), and no cuFFT is involved.
 //
+// Shared-memory traffic and barriers, not flops, bound this kernel, so the passes are fused at
+// both ends and in the middle:
+//   * pass 0 forward reads its 16 inputs straight from HBM (LN apply + t-embedding in registers;
+//     the upper half of the zero-padded transform is never materialised: x[8..15] = 0 is folded
+//     into the butterfly) and the last inverse pass writes GELU(y) straight to HBM (only the
+//     first l outputs are computed);
+//   * when the last forward pass has radix 2/4/8 it is done in registers together with the
+//     real-FFT untangle + spectrum product + re-tangle and the first inverse pass: the outputs
+//     are stored bit-reversed per pass, so the partner X[M-k] of slot p sits in slot
+//     p ^ ((1 << msb(p)) - 1) and whole radix groups pair up (g, partner(g));
+//   * untangle, product and re-tangle are one 2x2 complex map per pair whose four coefficients are
+//     precomputed at weight load (kcoef_kernel): 16 FMA per pair instead of ~40 flops + 3 loads.
+//
 // HBM traffic per row: read x (4l B) + write g (4l B); stats (8l B per batch element) and the
-// spectrum (8(M+1) B per channel) are shared by H resp. B rows and stay in L2 (rows of one
-// channel are adjacent in the grid).
+// coefficient table (16(M+2) B per channel) are shared by H resp. B rows and stay in L2 (rows of
+// one channel are adjacent in the grid).
 #include <mutex>
 
 #include "common.cuh"
@@ -19,7 +32,8 @@
 namespace dwb {
 
 // ---- in-register radix-R DFT, natural order in and out --------------------------------
-template <int R, bool INV>
+// ZHI: inputs x[R/2..R) are zero and are not read
+template <int R, bool INV, bool ZHI = false>
 struct Radix {
     static __device__ __forceinline__ void run(float2 *x) {
         // omega_16^q = exp(-2 pi i q / 16), q = 0..7
@@ -27,26 +41,30 @@ struct Radix {
                                  0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
         constexpr float WI[8] = {0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
                                  -1.0f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
-        float2 e[R / 2], o[R / 2];
+        if constexpr (R == 2 && ZHI) {
+            x[1] = x[0];
+        } else {
+            float2 e[R / 2], o[R / 2];
 #pragma unroll
-        for (int i = 0; i < R / 2; ++i) {
-            e[i] = x[2 * i];
-            o[i] = x[2 * i + 1];
-        }
-        Radix<R / 2, INV>::run(e);
-        Radix<R / 2, INV>::run(o);
+            for (int i = 0; i < (ZHI ? R / 4 : R / 2); ++i) {
+                e[i] = x[2 * i];
+                o[i] = x[2 * i + 1];
+            }
+            Radix<R / 2, INV, ZHI>::run(e);
+            Radix<R / 2, INV, ZHI>::run(o);
 #pragma unroll
-        for (int q = 0; q < R / 2; ++q) {
-            constexpr int step = 16 / R;
-            const float wr = WR[q * step], wi = INV ? -WI[q * step] : WI[q * step];
-            const float2 t = make_float2(o[q].x * wr - o[q].y * wi, o[q].x * wi + o[q].y * wr);
-            x[q] = make_float2(e[q].x + t.x, e[q].y + t.y);
-            x[q + R / 2] = make_float2(e[q].x - t.x, e[q].y - t.y);
+            for (int q = 0; q < R / 2; ++q) {
+                constexpr int step = 16 / R;
+                const float wr = WR[q * step], wi = INV ? -WI[q * step] : WI[q * step];
+                const float2 t = make_float2(o[q].x * wr - o[q].y * wi, o[q].x * wi + o[q].y * wr);
+                x[q] = make_float2(e[q].x + t.x, e[q].y + t.y);
+                x[q + R / 2] = make_float2(e[q].x - t.x, e[q].y - t.y);
+            }
         }
     }
 };
-template <bool INV>
-struct Radix<1, INV> {
+template <bool INV, bool ZHI>
+struct Radix<1, INV, ZHI> {
     static __device__ __forceinline__ void run(float2 *) {}
 };
 
@@ -64,51 +82,102 @@ __device__ __forceinline__ void twiddle_powers(float2 w1, float2 (&w)[R]) {
     }
 }
 
+// x[q] *= w1^q, q < R, keeping at most R/2 powers live (w^1..w^{R/2-1}, then w^{R/2} times those)
+template <int R>
+__device__ __forceinline__ void apply_twiddles(float2 (&x)[R], float2 w1) {
+    if constexpr (R >= 8) {
+        float2 w[R / 2];
+        twiddle_powers<R / 2>(w1, w);
+#pragma unroll
+        for (int q = 1; q < R / 2; ++q) x[q] = cmul(x[q], w[q]);
+        const float2 wh = cmul(w[R / 4], w[R / 4]);
+        x[R / 2] = cmul(x[R / 2], wh);
+#pragma unroll
+        for (int q = 1; q < R / 2; ++q) x[R / 2 + q] = cmul(x[R / 2 + q], cmul(wh, w[q]));
+    } else {
+        float2 w[R];
+        twiddle_powers<R>(w1, w);
+#pragma unroll
+        for (int q = 1; q < R; ++q) x[q] = cmul(x[q], w[q]);
+    }
+}
+
 // ---- one in-place pass over the shared array ---------------------------------------------
-// forward (DIF): u_q = sum_p x[j + p sub] w_R^{pq};  store u_q W_S^{jq} at j + q sub
-// inverse (DIT): y_q = s[j + q sub] conj(W_S^{jq});  x_p = sum_q y_q w_R^{-pq} at j + p sub
-template <int LOG2R, bool INV, int LOG2M, int NT>
-__device__ __forceinline__ void fft_pass(float2 *s, const float2 *__restrict__ tw, int log2S, int tid) {
-    constexpr int R = 1 << LOG2R, M = 1 << LOG2M;
-    const int log2sub = log2S - LOG2R;
-    const int sub = 1 << log2sub;
+// forward (DIF): u_q = sum_p x[j + p sub] w_R^{pq};  store u_q W_S^{jq} at j + brev(q) sub
+// inverse (DIT): y_q = s[j + brev(q) sub] conj(W_S^{jq});  x_p = sum_q y_q w_R^{-pq} at j + p sub
+template <int LR, bool INV, int LOG2M, int LOG2S, int NT>
+__device__ __forceinline__ void fft_pass(float2 *s, const float2 *__restrict__ stw, int tid) {
+    constexpr int R = 1 << LR, M = 1 << LOG2M, log2sub = LOG2S - LR, sub = 1 << log2sub;
     for (int bi = tid; bi < M / R; bi += NT) {
         const int j = bi & (sub - 1);
-        const int base = ((bi >> log2sub) << log2S) + j;
+        const int base = ((bi >> log2sub) << LOG2S) + j;
         float2 x[R];
-#pragma unroll
-        for (int p = 0; p < R; ++p) x[p] = s[fft_pad(base + (p << log2sub))];
-        float2 w[R];
+        float2 w1 = make_float2(1.f, 0.f);
         if (log2sub > 0) {
-            float2 w1 = tw[j << (LOG2M - log2S)];   // W_S^j = W_M^{j M / S}, shared-memory table
+            w1 = stw[j << (LOG2M - LOG2S)];          // W_S^j = W_M^{j M / S}
             if (INV) w1.y = -w1.y;
-            twiddle_powers<R>(w1, w);
         }
-        if (INV && log2sub > 0) {
+        if (!INV) {
 #pragma unroll
-            for (int q = 1; q < R; ++q) x[q] = cmul(x[q], w[q]);
+            for (int p = 0; p < R; ++p) x[p] = s[fft_pad(base + (p << log2sub))];
+            Radix<R, false>::run(x);
+            if (log2sub > 0) apply_twiddles<R>(x, w1);
+#pragma unroll
+            for (int q = 0; q < R; ++q) s[fft_pad(base + (fft_brev(q, LR) << log2sub))] = x[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) x[q] = s[fft_pad(base + (fft_brev(q, LR) << log2sub))];
+            if (log2sub > 0) apply_twiddles<R>(x, w1);
+            Radix<R, true>::run(x);
+#pragma unroll
+            for (int p = 0; p < R; ++p) s[fft_pad(base + (p << log2sub))] = x[p];
         }
-        Radix<R, INV>::run(x);
-        if (!INV && log2sub > 0) {
-#pragma unroll
-            for (int q = 1; q < R; ++q) x[q] = cmul(x[q], w[q]);
-        }
-#pragma unroll
-        for (int p = 0; p < R; ++p) s[fft_pad(base + (p << log2sub))] = x[p];
     }
     __syncthreads();
 }
 
-template <int LOG2M, int NT, bool INV, int PASS>
-__device__ __forceinline__ void fft_run_pass(float2 *s, const float2 *__restrict__ tw, int tid) {
-    constexpr int lr = fft_radix_log2(LOG2M, PASS);
-    if constexpr (lr > 0) {
-        // span of pass p = M / (R_0 ... R_{p-1})
-        int log2S = LOG2M;
-#pragma unroll
-        for (int q = 0; q < PASS; ++q) log2S -= fft_radix_log2(LOG2M, q);
-        fft_pass<lr, INV, LOG2M, NT>(s, tw, log2S, tid);
+// middle passes p = FIRST .. LAST (forward ascending, inverse descending); span of pass p = M / 16^p
+template <int LOG2M, int NT, bool INV, int P, int LAST>
+__device__ __forceinline__ void fft_mid_passes(float2 *s, const float2 *__restrict__ stw, int tid) {
+    if constexpr (P <= LAST) {
+        constexpr int LR = fft_radix_log2(LOG2M, P), LOG2S = LOG2M - 4 * P;
+        if constexpr (!INV) {
+            fft_pass<LR, false, LOG2M, LOG2S, NT>(s, stw, tid);
+            fft_mid_passes<LOG2M, NT, false, P + 1, LAST>(s, stw, tid);
+        } else {
+            fft_mid_passes<LOG2M, NT, true, P + 1, LAST>(s, stw, tid);
+            fft_pass<LR, true, LOG2M, LOG2S, NT>(s, stw, tid);
+        }
     }
+}
+
+// ---- real-FFT untangle + spectrum product + re-tangle of one pair ------------------------------
+// a = Z[k] (slot p, k < M/2), b = Z[M-k] (slot p2);  c0 = (alpha, beta), c1 = (gamma, delta):
+//   Z'[k] = alpha a + beta conj(b),  Z'[M-k] = conj(gamma a + delta conj(b))
+__device__ __forceinline__ void pair_map(float2 &a, float2 &b, const float4 c0, const float4 c1) {
+    const float2 oa = make_float2(c0.x * a.x - c0.y * a.y + c0.z * b.x + c0.w * b.y,
+                                  c0.x * a.y + c0.y * a.x + c0.w * b.x - c0.z * b.y);
+    const float2 ob = make_float2(c1.x * a.x - c1.y * a.y + c1.z * b.x + c1.w * b.y,
+                                  -(c1.x * a.y + c1.y * a.x + c1.w * b.x - c1.z * b.y));
+    a = oa;
+    b = ob;
+}
+// generic (shared-memory) form for leader entry idx in [0, M/2]
+template <int LOG2M>
+__device__ __forceinline__ void pointwise_smem(float2 *s, int idx, const float4 c, const float4 c1) {
+    constexpr int M = 1 << LOG2M;
+    if (idx == 0) {                          // k = 0: DC and Nyquist, both real
+        const float2 a = s[0];
+        const float p0 = 2.f * (a.x + a.y) * c.x, pM = 2.f * (a.x - a.y) * c.y;
+        s[0] = make_float2(p0 + pM, p0 - pM);
+        return;
+    }
+    const int p = (idx == M / 2) ? 1 : 2 * idx;                    // slot 1 is k = M/2, self-paired
+    const int p2 = p ^ ((1 << (31 - __clz(p))) - 1);
+    float2 a = s[fft_pad(p)], b = s[fft_pad(p2)];
+    pair_map(a, b, c, c1);
+    s[fft_pad(p)] = a;
+    if (p2 != p) s[fft_pad(p2)] = b;
 }
 
 template <int LOG2M>
@@ -118,19 +187,22 @@ struct FftCfg {
     static constexpr int NTW = M / 16;                         // W_M^j, j < M/16: enough for every twiddled pass
     static constexpr int SDATA = M + M / 16 + 1;               // padded data array (float2)
     static constexpr int SMEM = (SDATA + NTW) * (int)sizeof(float2);
+    static constexpr int NP = fft_num_passes(LOG2M);
+    static constexpr int RL = fft_radix_log2(LOG2M, NP - 1);   // log2 radix of the last forward pass
+    static constexpr bool FUSED = RL != 4;                     // last pass done in registers with the pointwise stage
 };
 
 template <int LOG2M>
 __global__ void __launch_bounds__(FftCfg<LOG2M>::NT)
 fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
-               long long part_stride_b, float ln_m, float ln_s, const float2 *__restrict__ kf,
-               const float2 *__restrict__ tw /* W_n^i, i < M */, const float2 *__restrict__ twpos /* W_n^{freq(p)} */,
-               float *__restrict__ g, int B, int H, int l) {
-    constexpr int M = 1 << LOG2M, NT = FftCfg<LOG2M>::NT;
+               long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
+               const float2 *__restrict__ tw /* W_n^i, i < M */, float *__restrict__ g, int B, int H, int l) {
+    using Cfg = FftCfg<LOG2M>;
+    constexpr int M = 1 << LOG2M, NT = Cfg::NT, NP = Cfg::NP, RL = Cfg::RL;
+    constexpr int log2sub0 = LOG2M - 4, sub0 = 1 << log2sub0;      // pass 0: radix 16, span M
     extern __shared__ float2 s[];
-    float2 *stw = s + FftCfg<LOG2M>::SDATA;
+    float2 *stw = s + Cfg::SDATA;
     const int tid = threadIdx.x;
-    for (int j = tid; j < FftCfg<LOG2M>::NTW; j += NT) stw[j] = tw[2 * j];
     const int row = blockIdx.x;
     const int h = row / B, b = row - h * B;
     const size_t off = ((size_t)b * H + h) * (size_t)l;
@@ -138,151 +210,210 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
     float *gr = g + off;
     const float pt = part_t ? part_t[(size_t)b * part_stride_b + h] : 0.f;
     const float *st = stats ? stats + (size_t)b * l * 2 : nullptr;
-
-    // ---- prologue: y = (ln_s rstd)(x - mean + ln_m) + part_t, packed z[j] = y[2j] + i y[2j+1]
+    const float4 *kcr = kc + (size_t)h * (M + 2);                  // (M/2 + 1) entries of two float4
+    const float lns = st ? ln_s : 1.f, lnm = st ? ln_m : 0.f;
     const bool vec = ((l & 1) == 0);
-    if (vec && st) {
-        // hot case: batches of 4 independent (x, stats) loads in flight per thread
-        const int half = l >> 1;
-        const float2 *x2 = reinterpret_cast<const float2 *>(xr);
-        const float4 *s4 = reinterpret_cast<const float4 *>(st);
-        for (int j0 = tid; j0 < M; j0 += 4 * NT) {
-            float2 xv[4];
-            float4 sv[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u * NT;
-                if (j < half) {
-                    xv[u] = x2[j];
-                    sv[u] = s4[j];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u * NT;
-                if (j < M) {
-                    float2 v = make_float2(0.f, 0.f);
-                    if (j < half) {
-                        v.x = (ln_s * sv[u].y) * (xv[u].x - sv[u].x + ln_m) + pt;
-                        v.y = (ln_s * sv[u].w) * (xv[u].y - sv[u].z + ln_m) + pt;
-                    }
-                    s[fft_pad(j)] = v;
-                }
-            }
-        }
-    } else
-    for (int j = tid; j < M; j += NT) {
-        float2 v = make_float2(0.f, 0.f);
-        const int t0 = 2 * j;
+    const int half = l >> 1;
+
+    // packed input z[i] = y[2i] + i y[2i+1] as raw (x pair, statistics of the two time steps)
+    auto load_in = [&](int i, float2 &xv, float4 &sv) {
+        xv = make_float2(0.f, 0.f);
+        sv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (vec) {
-            if (t0 < l) {
-                const float2 xv = *reinterpret_cast<const float2 *>(xr + t0);
-                v.x = xv.x + pt;
-                v.y = xv.y + pt;
+            if (i < half) {
+                xv = reinterpret_cast<const float2 *>(xr)[i];
+                sv = st ? reinterpret_cast<const float4 *>(st)[i] : make_float4(0.f, 1.f, 0.f, 1.f);
             }
         } else {
-            if (t0 < l) v.x = st ? (ln_s * st[2 * t0 + 1]) * (xr[t0] - st[2 * t0] + ln_m) + pt : xr[t0] + pt;
-            if (t0 + 1 < l)
-                v.y = st ? (ln_s * st[2 * t0 + 3]) * (xr[t0 + 1] - st[2 * t0 + 2] + ln_m) + pt : xr[t0 + 1] + pt;
+            const int t0 = 2 * i;
+            if (t0 < l) {
+                xv.x = xr[t0];
+                sv.x = st ? st[2 * t0] : 0.f;
+                sv.y = st ? st[2 * t0 + 1] : 1.f;
+            }
+            if (t0 + 1 < l) {
+                xv.y = xr[t0 + 1];
+                sv.z = st ? st[2 * t0 + 2] : 0.f;
+                sv.w = st ? st[2 * t0 + 3] : 1.f;
+            }
         }
-        s[fft_pad(j)] = v;
-    }
-    __syncthreads();
+    };
+    // y = (ln_s rstd)(x - mean + ln_m) + part_t inside the row, 0 in the zero padding
+    auto apply_in = [&](int i, float2 xv, float4 sv) {
+        const int t0 = 2 * i;
+        return make_float2((lns * sv.y) * (xv.x - sv.x + lnm) + (t0 < l ? pt : 0.f),
+                           (lns * sv.w) * (xv.y - sv.z + lnm) + (t0 + 1 < l ? pt : 0.f));
+    };
 
-    // ---- forward passes (natural -> digit reversed)
-    fft_run_pass<LOG2M, NT, false, 0>(s, stw, tid);
-    fft_run_pass<LOG2M, NT, false, 1>(s, stw, tid);
-    fft_run_pass<LOG2M, NT, false, 2>(s, stw, tid);
-    fft_run_pass<LOG2M, NT, false, 3>(s, stw, tid);
-
-    // ---- untangle the real spectrum, multiply by the cached kernel spectrum, re-tangle.
-    // Slot p holds Z[k], k = fft_freq(p); its partner Z[M-k] sits in slot fft_pos(M-k).
-    // Leaders are the slots whose k < M/2: bit (lrl-1) of p clear (the last pass's digit is the
-    // most significant digit of k).  Leader index 0 is k = 0 (DC + Nyquist, both real).
+    // ---- pass 0 forward, fused with the prologue: inputs i = j + p sub0; p >= 8 lies in the zero padding
     {
-        constexpr int np = fft_num_passes(LOG2M);
-        constexpr int lrl = fft_radix_log2(LOG2M, np - 1);
-        const float2 *kfr = kf + (size_t)h * (M + 1);
-        for (int idx = tid; idx <= M / 2; idx += NT) {
-            if (idx == 0) {
-                const float2 a = s[0];
-                const float y0 = 2.f * (a.x + a.y), yM = 2.f * (a.x - a.y);
-                const float p0 = y0 * kfr[0].x, pM = yM * kfr[M].x;
-                s[0] = make_float2(p0 + pM, p0 - pM);
-                continue;
-            }
-            int p, p2;
-            float2 w;
-            if (idx == M / 2) {          // k = M/2, self-paired, W_n^{M/2} = -i
-                p = p2 = 1 << (lrl - 1);
-                w = make_float2(0.f, -1.f);
-            } else {
-                p = ((idx >> (lrl - 1)) << lrl) | (idx & ((1 << (lrl - 1)) - 1));
-                const int k = fft_freq(p, LOG2M);
-                p2 = fft_pos(M - k, LOG2M);
-                w = twpos[p];
-            }
-            const float2 A = s[fft_pad(p)], Bv = s[fft_pad(p2)];
-            const float2 K1 = kfr[p], K2 = kfr[p2];
-            const float2 S = make_float2(A.x + Bv.x, A.y - Bv.y);
-            const float2 Dm = make_float2(A.x - Bv.x, A.y + Bv.y);
-            const float2 WD = cmul(w, Dm);
-            const float2 T = make_float2(WD.y, -WD.x);                     // -i W Dm
-            const float2 Yk = cadd(S, T);
-            const float2 Yk2 = make_float2(S.x - T.x, -(S.y - T.y));       // conj(S - T)
-            const float2 P1 = cmul(Yk, K1), P2 = cmul(Yk2, K2);
-            const float2 S2 = make_float2(P1.x + P2.x, P1.y - P2.y);
-            const float2 D2 = make_float2(P1.x - P2.x, P1.y + P2.y);
-            const float2 CD = cmul_conj(D2, w);                            // conj(W) D2
-            const float2 T2 = make_float2(-CD.y, CD.x);                    // i conj(W) D2
-            s[fft_pad(p)] = cadd(S2, T2);
-            s[fft_pad(p2)] = make_float2(S2.x - T2.x, -(S2.y - T2.y));     // conj(S2 - T2)
+        float2 xv[8];
+        float4 sv[8];
+        int bi = tid;
+        if (bi < sub0) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) load_in(bi + (p << log2sub0), xv[p], sv[p]);
         }
+        for (int j = tid; j < Cfg::NTW; j += NT) stw[j] = tw[2 * j];
+        __syncthreads();
+        for (; bi < sub0; bi += NT) {
+            float2 xx[16];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) xx[p] = apply_in(bi + (p << log2sub0), xv[p], sv[p]);
+            if constexpr (sub0 > NT) {            // next butterfly's loads go in flight under this one's arithmetic
+                if (bi + NT < sub0) {
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) load_in(bi + NT + (p << log2sub0), xv[p], sv[p]);
+                }
+            }
+            Radix<16, false, true>::run(xx);
+            if (log2sub0 > 0) apply_twiddles<16>(xx, stw[bi]);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) s[fft_pad(bi + (fft_brev(q, 4) << log2sub0))] = xx[q];
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
-    // ---- inverse passes (digit reversed -> natural), mirror order
-    fft_run_pass<LOG2M, NT, true, 3>(s, stw, tid);
-    fft_run_pass<LOG2M, NT, true, 2>(s, stw, tid);
-    fft_run_pass<LOG2M, NT, true, 1>(s, stw, tid);
-    fft_run_pass<LOG2M, NT, true, 0>(s, stw, tid);
+    // ---- middle forward passes; the last one stays separate only when the centre is not fused
+    fft_mid_passes<LOG2M, NT, false, 1, Cfg::FUSED ? NP - 2 : NP - 1>(s, stw, tid);
 
-    // ---- epilogue: first l samples, GELU
-    if (vec) {
-        for (int j = tid; j < l / 2; j += NT) {
-            const float2 v = s[fft_pad(j)];
-            *reinterpret_cast<float2 *>(gr + 2 * j) = make_float2(gelu_fast(v.x), gelu_fast(v.y));
+    // ---- centre: (last forward pass +) untangle, product, re-tangle (+ first inverse pass)
+    if constexpr (Cfg::FUSED) {
+        constexpr int R = 1 << RL, NITEM = M / (2 * R);
+        // item = radix groups (ga, gb = partner(ga)); its coefficients are entries (R g + c)/2, c even: R float4 per group.
+        // They come from L2, so the next item's set is loaded while the current item is being computed.
+        auto partner = [](int ga) { return ga == 0 ? 1 : ga ^ ((1 << (31 - __clz(ga))) - 1); };
+        auto load_coef = [&](int item, float4 (&ca)[R], float4 (&cb)[R]) {
+            const float4 *ka = kcr + (size_t)R * (2 * item), *kb = kcr + (size_t)R * partner(2 * item);
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                ca[i] = __ldg(ka + i);
+                cb[i] = __ldg(kb + i);
+            }
+        };
+        float4 ca[R], cb[R];
+        if (tid < NITEM) load_coef(tid, ca, cb);
+        for (int item = tid; item < NITEM; item += NT) {
+            const int ga = 2 * item, gb = partner(ga);
+            float2 xa[R], xb[R];
+#pragma unroll
+            for (int c = 0; c < R; ++c) {
+                xa[c] = s[fft_pad(R * ga + c)];
+                xb[c] = s[fft_pad(R * gb + c)];
+            }
+            float4 na[R], nb[R];
+            if (item + NT < NITEM) load_coef(item + NT, na, nb);
+            Radix<R, false>::run(xa);     // xa[q] = output digit q, whose slot is R ga + brev(q)
+            Radix<R, false>::run(xb);
+            if (item == 0) {
+                // groups 0 and 1 pair inside themselves: slot 0 = DC/Nyquist (entry 0), slot 1 = k = M/2 paired
+                // with itself (entry M/2), even slots c >= 2 of group 0 with c ^ ((1 << msb(c)) - 1), group 1 like
+                // any other group but with itself.  Everything in registers; digit q sits in slot brev(q).
+                const float4 s0 = __ldg(kcr + M), s1 = __ldg(kcr + M + 1);
+                {
+                    const float2 a = xa[0];
+                    const float p0 = 2.f * (a.x + a.y) * ca[0].x, pM = 2.f * (a.x - a.y) * ca[0].y;
+                    xa[0] = make_float2(p0 + pM, p0 - pM);
+                    float2 d = xa[R / 2];
+                    pair_map(xa[R / 2], d, s0, s1);
+                }
+#pragma unroll
+                for (int c = 2; c < R; c += 2) {
+                    int msb = 0;
+                    while ((2 << msb) <= c) ++msb;
+                    const int c2 = c ^ ((1 << msb) - 1);
+                    pair_map(xa[fft_brev(c, RL)], xa[fft_brev(c2, RL)], ca[c], ca[c + 1]);
+                }
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) {
+                    const int e = fft_brev(q, RL) >> 1;
+                    pair_map(xb[q], xb[q ^ (R - 1)], cb[2 * e], cb[2 * e + 1]);
+                }
+            } else {
+                // slot (ga, c) pairs with (gb, c ^ (R-1)); in digit order q <-> q ^ (R-1); leaders have q < R/2
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) {
+                    const int e = fft_brev(q, RL) >> 1;
+                    pair_map(xa[q], xb[q ^ (R - 1)], ca[2 * e], ca[2 * e + 1]);
+                    pair_map(xb[q], xa[q ^ (R - 1)], cb[2 * e], cb[2 * e + 1]);
+                }
+            }
+            Radix<R, true>::run(xa);      // first inverse pass: input digit q is already in place
+            Radix<R, true>::run(xb);
+#pragma unroll
+            for (int p = 0; p < R; ++p) {
+                s[fft_pad(R * ga + p)] = xa[p];
+                s[fft_pad(R * gb + p)] = xb[p];
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                ca[i] = na[i];
+                cb[i] = nb[i];
+            }
         }
+        __syncthreads();
     } else {
-        for (int j = tid; 2 * j < l; j += NT) {
-            const float2 v = s[fft_pad(j)];
-            gr[2 * j] = gelu_fast(v.x);
-            if (2 * j + 1 < l) gr[2 * j + 1] = gelu_fast(v.y);
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;      // coefficients come from L2: one iteration ahead
+        if (tid <= M / 2) {
+            c0 = __ldg(kcr + 2 * tid);
+            c1 = __ldg(kcr + 2 * tid + 1);
+        }
+        for (int idx = tid; idx <= M / 2; idx += NT) {
+            float4 n0 = c0, n1 = c1;
+            if (idx + NT <= M / 2) {
+                n0 = __ldg(kcr + 2 * (idx + NT));
+                n1 = __ldg(kcr + 2 * (idx + NT) + 1);
+            }
+            pointwise_smem<LOG2M>(s, idx, c0, c1);
+            c0 = n0;
+            c1 = n1;
+        }
+        __syncthreads();
+    }
+
+    // ---- middle inverse passes (mirror order)
+    fft_mid_passes<LOG2M, NT, true, 1, Cfg::FUSED ? NP - 2 : NP - 1>(s, stw, tid);
+
+    // ---- last inverse pass (pass 0), fused with the epilogue: only outputs p < 8 can fall inside the row
+    for (int bi = tid; bi < sub0; bi += NT) {
+        float2 xx[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) xx[q] = s[fft_pad(bi + (fft_brev(q, 4) << log2sub0))];
+        if (log2sub0 > 0) {
+            const float2 w1 = stw[bi];
+            apply_twiddles<16>(xx, make_float2(w1.x, -w1.y));
+        }
+        Radix<16, true>::run(xx);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int i = bi + (p << log2sub0);
+            if (vec) {
+                if (i < half) reinterpret_cast<float2 *>(gr)[i] = make_float2(gelu_fast(xx[p].x), gelu_fast(xx[p].y));
+            } else {
+                if (2 * i < l) gr[2 * i] = gelu_fast(xx[p].x);
+                if (2 * i + 1 < l) gr[2 * i + 1] = gelu_fast(xx[p].y);
+            }
         }
     }
 }
 
-// ---- twiddle tables: immutable, per (device, log2M), created on first use -----------------
-__global__ void twiddle_kernel(float2 *tw, float2 *twpos, int log2M) {
+// ---- twiddle table W_n^i, i < M: immutable, per (device, log2M), created on first use -------
+__global__ void twiddle_kernel(float2 *tw, int log2M) {
     const int M = 1 << log2M, n = 2 * M;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     double sn, cs;
     sincospi(-2.0 * (double)i / (double)n, &sn, &cs);
     tw[i] = make_float2((float)cs, (float)sn);
-    const int k = fft_freq(i, log2M);
-    sincospi(-2.0 * (double)k / (double)n, &sn, &cs);
-    twpos[i] = make_float2((float)cs, (float)sn);
 }
 
 struct TwiddleCache {
     std::mutex mu;
     float2 *tw[16][FFT_MAX_LOG2M + 1] = {};
-    float2 *twpos[16][FFT_MAX_LOG2M + 1] = {};
 };
 static TwiddleCache g_tw;
 
-int fft_twiddles(int log2M, cudaStream_t st, const float2 **tw, const float2 **twpos) {
+int fft_twiddles(int log2M, cudaStream_t st, const float2 **tw) {
     int dev = 0;
     DWB_CUDA(cudaGetDevice(&dev));
     DWB_REQUIRE(dev >= 0 && dev < 16, DWB_ERR_UNSUPPORTED, "device index %d out of range", dev);
@@ -293,24 +424,20 @@ int fft_twiddles(int log2M, cudaStream_t st, const float2 **tw, const float2 **t
         DWB_REQUIRE(cs == cudaStreamCaptureStatusNone, DWB_ERR_STATE,
                     "fft twiddle table for M=2^%d must be created before stream capture", log2M);
         const int M = 1 << log2M;
-        float2 *a = nullptr, *bq = nullptr;
+        float2 *a = nullptr;
         DWB_CUDA(cudaMalloc(&a, (size_t)M * sizeof(float2)));
-        DWB_CUDA(cudaMalloc(&bq, (size_t)M * sizeof(float2)));
-        twiddle_kernel<<<ceil_div(M, 256), 256, 0, st>>>(a, bq, log2M);
+        twiddle_kernel<<<ceil_div(M, 256), 256, 0, st>>>(a, log2M);
         DWB_LAUNCH_CHECK();
         DWB_CUDA(cudaStreamSynchronize(st));
         g_tw.tw[dev][log2M] = a;
-        g_tw.twpos[dev][log2M] = bq;
     }
     *tw = g_tw.tw[dev][log2M];
-    *twpos = g_tw.twpos[dev][log2M];
     return DWB_OK;
 }
 
 template <int LOG2M>
 static int launch_fftconv(const float *x, const float *stats, const float *part_t, long long psb, float ln_m,
-                          float ln_s, const float *kf, const float2 *tw, const float2 *twpos, float *g, int B, int H,
-                          int l, cudaStream_t st) {
+                          float ln_s, const float *kc, const float2 *tw, float *g, int B, int H, int l, cudaStream_t st) {
     using Cfg = FftCfg<LOG2M>;
     static bool attr_set[16] = {};
     int dev = 0;
@@ -319,22 +446,21 @@ static int launch_fftconv(const float *x, const float *stats, const float *part_
         DWB_CUDA(cudaFuncSetAttribute(fftconv_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_set[dev & 15] = true;
     }
-    fftconv_kernel<LOG2M><<<B * H, Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float2 *)kf, tw,
-                                                            twpos, g, B, H, l);
+    fftconv_kernel<LOG2M><<<B * H, Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw, g, B, H, l);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
 }
 
 int fftconv_launch(const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
-                   const float *kf, float *g, int B, int H, int l, cudaStream_t st) {
+                   const float *kc, float *g, int B, int H, int l, cudaStream_t st) {
     const int lg = fft_log2m_for(l);
     DWB_REQUIRE(lg > 0, DWB_ERR_UNSUPPORTED, "fftconv: stage length %d unsupported (max %d)", l, 1 << FFT_MAX_LOG2M);
-    const float2 *tw, *twpos;
-    int rc = fft_twiddles(lg, st, &tw, &twpos);
+    const float2 *tw;
+    int rc = fft_twiddles(lg, st, &tw);
     if (rc != DWB_OK) return rc;
 #define DWB_FFT_CASE(LG) \
     case LG:             \
-        return launch_fftconv<LG>(x, stats, part_t, psb, ln_m, ln_s, kf, tw, twpos, g, B, H, l, st);
+        return launch_fftconv<LG>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
     switch (lg) {
         DWB_FFT_CASE(4) DWB_FFT_CASE(5) DWB_FFT_CASE(6) DWB_FFT_CASE(7) DWB_FFT_CASE(8) DWB_FFT_CASE(9)
         DWB_FFT_CASE(10) DWB_FFT_CASE(11) DWB_FFT_CASE(12) DWB_FFT_CASE(13) DWB_FFT_CASE(14)

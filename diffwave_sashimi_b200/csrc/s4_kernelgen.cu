@@ -169,12 +169,13 @@ irdft_kernel(const double *__restrict__ khat /* (R,nk,2) */, int l, double *__re
 // ---------------------------------------------------------------------------------------
 // 3. spectrum of the wrapped two-sided kernel, in fftconv's layout
 //    kk[s] = k0[s] (s < l), kk[n - s] = k1[s-1] (s = 1..l);  K[f] = sum_j kk[j] e^{-2 pi i f j / n}
-//    stored value: (K[f] + D[h]) / (4 M), M = n/2, at slot fft_pos(f) for f < M, Nyquist at slot M.
+//    Kd[f] = (K[f] + D[h]) / (4 M), M = n/2, f = 0..M in natural order (fp64), then kcoef_kernel turns
+//    each conjugate pair (k, M-k) into the 2x2 complex map fftconv applies (untangle, product, re-tangle).
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(DFT_THREADS)
 kf_kernel(const T *__restrict__ k /* (2,H,l) */, const float *__restrict__ D /* (H) or null */, int H, int l,
-          int log2M, float *__restrict__ kf /* (H, M+1, 2) */) {
+          int log2M, double2 *__restrict__ Kd /* (H, M+1) */) {
     __shared__ double s0[DFT_CHUNK], s1[DFT_CHUNK];
     const int h = blockIdx.y;
     const int M = 1 << log2M, n = 2 * M;
@@ -214,10 +215,66 @@ kf_kernel(const T *__restrict__ k /* (2,H,l) */, const float *__restrict__ D /* 
     if (f > M) return;
     const double scale = 1.0 / (4.0 * (double)M);
     const double d = D ? (double)D[h] : 0.0;
-    const int slot = (f == M) ? M : fft_pos(f, log2M);
-    float *o = kf + ((size_t)h * (M + 1) + slot) * 2;
-    o[0] = (float)((ar + d) * scale);
-    o[1] = (float)(ai * scale);
+    Kd[(size_t)h * (M + 1) + f] = make_double2((ar + d) * scale, ai * scale);
+}
+
+// Pointwise table of fftconv.cu: entry e of channel h (8 floats: alpha, beta, gamma, delta) for the
+// leader slot p = 2e (e = M/2: slot 1, the self-paired k = M/2; e = 0: (K'[0], K'[M]) for DC/Nyquist).
+// With a = Z[k], b = Z[M-k] of the packed transform, w = e^{-2 pi i k / n}, u = 1 - i w, v = 1 + i w:
+//   Y[k] = u a + v conj(b) (real-FFT untangle, factor 1/2 in the scale), P = K'[k] Y[k], ... re-tangle gives
+//   Z'[k]   = alpha a + beta conj(b),   Z'[M-k] = conj(gamma a + delta conj(b))
+//   alpha = K1 |u|^2 + conj(K2) |v|^2      beta  = K1 v conj(u) + conj(K2) u conj(v)
+//   gamma = K1 u conj(v) + conj(K2) v conj(u)   delta = K1 |v|^2 + conj(K2) |u|^2,   K1 = K'[k], K2 = K'[M-k]
+__global__ void kcoef_kernel(const double2 *__restrict__ Kd, int log2M, float *__restrict__ kc) {
+    const int M = 1 << log2M, n = 2 * M;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, h = blockIdx.y;
+    if (e > M / 2) return;
+    const double2 *K = Kd + (size_t)h * (M + 1);
+    float *o = kc + ((size_t)h * (M / 2 + 1) + e) * 8;
+    if (e == 0) {
+        o[0] = (float)K[0].x;
+        o[1] = (float)K[M].x;
+        for (int i = 2; i < 8; ++i) o[i] = 0.f;
+        return;
+    }
+    const int p = (e == M / 2) ? 1 : 2 * e;
+    const int k = fft_freq(p, log2M);
+    const double2 K1 = K[k], K2 = make_double2(K[M - k].x, -K[M - k].y);      // K2 = conj(K'[M-k])
+    double ws, wc;
+    sincospi(-2.0 * (double)k / (double)n, &ws, &wc);
+    const double2 u = make_double2(1.0 + ws, -wc), v = make_double2(1.0 - ws, wc);   // 1 -+ i w
+    auto mul = [](double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); };
+    auto conj = [](double2 a) { return make_double2(a.x, -a.y); };
+    const double u2 = u.x * u.x + u.y * u.y, v2 = v.x * v.x + v.y * v.y;
+    const double2 vu = mul(v, conj(u)), uv = mul(u, conj(v));
+    const double2 t1 = mul(K1, vu), t2 = mul(K2, uv), t3 = mul(K1, uv), t4 = mul(K2, vu);
+    o[0] = (float)(K1.x * u2 + K2.x * v2);
+    o[1] = (float)(K1.y * u2 + K2.y * v2);
+    o[2] = (float)(t1.x + t2.x);
+    o[3] = (float)(t1.y + t2.y);
+    o[4] = (float)(t3.x + t4.x);
+    o[5] = (float)(t3.y + t4.y);
+    o[6] = (float)(K1.x * v2 + K2.x * u2);
+    o[7] = (float)(K1.y * v2 + K2.y * u2);
+}
+
+template <typename T>
+static int fftconv_prepare_any(const T *k, const float *D, int H, int l, float *kc, cudaStream_t st) {
+    const int log2M = fft_log2m_for(l);
+    DWB_REQUIRE(log2M > 0, DWB_ERR_UNSUPPORTED, "fftconv: stage length %d unsupported (max %d)", l, 1 << FFT_MAX_LOG2M);
+    const int M = 1 << log2M;
+    double2 *Kd = nullptr;
+    DWB_CUDA(cudaMalloc(&Kd, (size_t)H * (M + 1) * sizeof(double2)));
+    kf_kernel<T><<<dim3(ceil_div(M + 1, DFT_THREADS), H), DFT_THREADS, 0, st>>>(k, D, H, l, log2M, Kd);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        kcoef_kernel<<<dim3(ceil_div(M / 2 + 1, 256), H), 256, 0, st>>>(Kd, log2M, kc);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(Kd);
+    if (e != cudaSuccess) return cuda_fail(e, "fftconv_prepare", __FILE__, __LINE__);
+    return DWB_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -320,12 +377,7 @@ int s4_generate(const float *C, const float *Bp, const float *P, const float *in
 }
 
 int fftconv_prepare_f64(const double *k64, const float *D, int H, int l, float *kf, cudaStream_t st) {
-    int log2M = fft_log2m_for(l);
-    DWB_REQUIRE(log2M > 0, DWB_ERR_UNSUPPORTED, "fftconv: stage length %d unsupported (max %d)", l, 1 << FFT_MAX_LOG2M);
-    dim3 grid(ceil_div((1 << log2M) + 1, DFT_THREADS), H);
-    kf_kernel<double><<<grid, DFT_THREADS, 0, st>>>(k64, D, H, l, log2M, kf);
-    DWB_LAUNCH_CHECK();
-    return DWB_OK;
+    return fftconv_prepare_any<double>(k64, D, H, l, kf, st);
 }
 }  // namespace dwb
 
@@ -362,10 +414,6 @@ extern "C" int dwb_fftconv_size(int l, int *nfft) {
 
 extern "C" int dwb_fftconv_prepare(const float *k, const float *D, int H, int l, float *kf, void *stream) {
     DWB_REQUIRE(k && kf, DWB_ERR_INVALID, "dwb_fftconv_prepare: null pointer");
-    int log2M = fft_log2m_for(l);
-    DWB_REQUIRE(log2M > 0, DWB_ERR_UNSUPPORTED, "fftconv: stage length %d unsupported (max %d)", l, 1 << FFT_MAX_LOG2M);
-    dim3 grid(ceil_div((1 << log2M) + 1, DFT_THREADS), H);
-    kf_kernel<float><<<grid, DFT_THREADS, 0, (cudaStream_t)stream>>>(k, D, H, l, log2M, kf);
-    DWB_LAUNCH_CHECK();
-    return DWB_OK;
+    DWB_REQUIRE(H >= 1 && l >= 1, DWB_ERR_INVALID, "dwb_fftconv_prepare: bad sizes H=%d l=%d", H, l);
+    return dwb::fftconv_prepare_any<float>(k, D, H, l, kf, (cudaStream_t)stream);
 }

@@ -72,7 +72,7 @@ def fftconv_prepare(k, D):
     k = _cuda(k, torch.float32)
     _, H, l = k.shape
     n = fftconv_size(l)
-    kf = torch.empty(H, n // 2 + 1, 2, dtype=torch.float32, device=k.device)
+    kf = torch.empty(H, n // 4 + 1, 8, dtype=torch.float32, device=k.device)
     Dd = _cuda(D.reshape(-1), torch.float32) if D is not None else None
     with torch.cuda.device(k.device):
         check(lib().dwb_fftconv_prepare(ptr(k), ptr(Dd), H, l, ptr(kf), stream_ptr(k.device)))

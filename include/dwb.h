@@ -162,8 +162,10 @@ int dwb_s4_kernel_gen(const float *C, const float *Bp, const float *P, const flo
                       const float *w_imag, const float *log_dt, const float *omega,
                       int H, int N, int l, float *k_out, void *stream);
 
-/* Cache the spectrum for the long convolution: kf (H, nfft/2+1, 2) f32 in the kernel's internal
- * order and scale from k (2,H,l) and D (H).  nfft = dwb_fftconv_size(l). */
+/* Cache the spectrum for the long convolution: kf (H, nfft/4+1, 8) f32, the kernel's internal
+ * pointwise table (per conjugate pair of the packed real FFT: untangle, multiply by the spectrum of
+ * the wrapped two-sided kernel + D, re-tangle, as one 2x2 complex map) from k (2,H,l) and D (H).
+ * nfft = dwb_fftconv_size(l).  Synchronises the stream. */
 int dwb_fftconv_size(int l, int *nfft);
 int dwb_fftconv_prepare(const float *k, const float *D, int H, int l, float *kf, void *stream);
 
