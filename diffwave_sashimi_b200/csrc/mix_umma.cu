@@ -855,6 +855,415 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
     }
 }
 
+// =========================================================================================
+// H = 256 (F = 512): the operands of one 128-step tile no longer fit the per-tile scheme
+// (z alone is 128 KB, the weights 1.5 MB).  Same orientation and epilogues, but
+//   * G1/G2 run in N chunks of 128 columns through ONE accumulator region R1 (the MMA issuer waits
+//     for the epilogue to drain it: r1a/r1b barriers),
+//   * the hidden activations never touch shared memory: the epilogue writes them (split bf16,
+//     packed pairs) straight into TMEM and G3 takes its A operand from there (tcgen05.mma TS form),
+//     double-buffered per 64-wide K chunk (HBUF 0/1, released by tcgen05.commit),
+//   * biases come through L1 (uniform __ldg), the column-group statistics exchange through idle
+//     HBUF columns, so shared memory holds only z (4 slots) and a 3-stage weight ring.
+// TMEM: [0,256) x1 / acc3 | [256,384) R1 | [384,448) HBUF0 | [448,512) HBUF1.
+// Weight image = 48 stages of 32 KB in consumption order:
+//   G1 (nc, kc) x16 | G2(0) x4 | for nc = 0..3: { G2(nc+1) x4 (nc < 3) | G3(2nc) x2 | G3(2nc+1) x2 }.
+// =========================================================================================
+struct U256 {
+    static constexpr int H = 256, F = 512, CS = 2, EPI = 256, NTHREADS = EPI + 64;
+    static constexpr int NC1 = 4, KC1 = 4, KC3 = 8, NB3 = 2, NSTG = 48, NS = 3, NSLOT = 4;
+    static constexpr int R3 = 0, R1 = 256, HBUF = 384;
+    static constexpr int OFF_SLOT = 0;
+    static constexpr int OFF_RING = NSLOT * UM_SLOT;
+    static constexpr int OFF_BAR = OFF_RING + NS * UM_STAGE;
+    static constexpr int NBAR = 2 * NS + 2 + 2 + KC3 + 2 + 2 * NC1 + 1;
+    static constexpr int OFF_TPTR = OFF_BAR + NBAR * 8;
+    static constexpr int SMEM = OFF_TPTR + 16 + 1024;
+    static constexpr size_t IMG_BYTES = (size_t)NSTG * UM_STAGE;
+    static_assert(SMEM <= 227 * 1024, "H=256 tile does not fit shared memory");
+    // stage i of the image -> (gemm, first output row of the 128-row block before permutation, K chunk)
+    __host__ __device__ static void stage_info(int i, int &gemm, int &nblk, int &kc) {
+        if (i < 16) { gemm = 0; nblk = i / 4; kc = i % 4; return; }
+        if (i < 20) { gemm = 1; nblk = 0; kc = i - 16; return; }
+        const int j = i - 20;
+        if (j < 24) {
+            const int nc = j / 8, r = j % 8;
+            if (r < 4) { gemm = 1; nblk = nc + 1; kc = r; }
+            else { gemm = 2; kc = 2 * nc + (r - 4) / 2; nblk = (r - 4) % 2; }
+        } else {
+            const int r = j - 24;
+            gemm = 2; kc = 6 + r / 2; nblk = r % 2;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(U256::NTHREADS, 1)
+sashimi_mix_umma256_kernel(MixArgs a) {
+    using C = U256;
+    constexpr int H = C::H;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *slots = sm + C::OFF_SLOT, *ring = sm + C::OFF_RING;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + C::OFF_BAR);
+    uint32_t *tptr = reinterpret_cast<uint32_t *>(sm + C::OFF_TPTR);
+    uint64_t *wfull = bars, *wempty = wfull + C::NS, *g_ready = wempty + C::NS, *z_ready = g_ready + 1, *r1a = z_ready + 1,
+             *r1b = r1a + 1, *hid_ready = r1b + 1, *hfree = hid_ready + C::KC3, *acc1_ready = hfree + 2,
+             *acc2_ready = acc1_ready + C::NC1, *acc3_ready = acc2_ready + C::NC1;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, t0 = blockIdx.x * UM_TT, l = a.l;
+    if (tid == 0) {
+        for (int i = 0; i < C::NS; ++i) {
+            mbar_init(wfull + i, 1);
+            mbar_init(wempty + i, 1);
+        }
+        mbar_init(g_ready, C::EPI);
+        mbar_init(z_ready, C::EPI);
+        mbar_init(r1a, C::EPI);
+        mbar_init(r1b, C::EPI);
+        for (int i = 0; i < C::KC3; ++i) mbar_init(hid_ready + i, 128);
+        mbar_init(hfree, 1);
+        mbar_init(hfree + 1, 1);
+        for (int i = 0; i < 2 * C::NC1 + 1; ++i) mbar_init(acc1_ready + i, 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc(tptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tptr;
+
+    if (warp == 8) {
+        // ================= weight producer =====================================================
+        if (lane == 0) {
+            for (int i = 0; i < C::NSTG; ++i) {
+                const int s = i % C::NS, n = i / C::NS;
+                mbar_wait(wempty + s, (n & 1) ^ 1);
+                mbar_arrive_expect_tx(wfull + s, UM_STAGE);
+                bulk_g2s(ring + (size_t)s * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + s);
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer ==========================================================
+        if (lane == 0) {
+            const uint32_t slot0 = smem_u32(slots), ring0 = smem_u32(ring);
+            constexpr uint32_t idesc = idesc_bf16(128, 128);
+            int i = 0;                                    // weight stage counter
+            auto next_stage = [&]() {
+                const int s = i % C::NS;
+                mbar_wait(wfull + s, (i / C::NS) & 1);
+                tc_fence_after();
+                return ring0 + s * UM_STAGE;
+            };
+            auto done_stage = [&]() {
+                mma_commit(wempty + (i % C::NS));
+                ++i;
+            };
+            // D[R1] = A[slots, all K] x stage blocks (SS form)
+            auto gemm_ss = [&](uint64_t *ready) {
+#pragma unroll 1
+                for (int kc = 0; kc < C::KC1; ++kc) {
+                    const uint32_t bbase = next_stage(), abase = slot0 + kc * UM_SLOT;
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t ao = abase + (term == 1 ? UM_SLOT / 2 : 0), bo = bbase + (term == 2 ? UM_STAGE / 2 : 0);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_bf16_ss(tmem + C::R1, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
+                                        (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    done_stage();
+                }
+                mma_commit(ready);
+            };
+            // R3[nb] += HBUF[kc & 1] x stage (TS form: A from TMEM)
+            auto gemm_ts = [&](int kc) {
+#pragma unroll 1
+                for (int nb = 0; nb < C::NB3; ++nb) {
+                    const uint32_t bbase = next_stage(), abase = tmem + C::HBUF + 64 * (kc & 1);
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t ao = abase + (term == 1 ? 32 : 0), bo = bbase + (term == 2 ? UM_STAGE / 2 : 0);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_bf16_ts(tmem + C::R3 + nb * 128, ao + ks * 8, smem_desc_sw128(bo + ks * 32), idesc, 1u);
+                    }
+                    done_stage();
+                }
+                mma_commit(hfree + (kc & 1));
+            };
+            mbar_wait(g_ready, 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int nc = 0; nc < C::NC1; ++nc) {
+                if (nc > 0) {
+                    mbar_wait(r1a, (nc - 1) & 1);
+                    tc_fence_after();
+                }
+                gemm_ss(acc1_ready + nc);
+            }
+            mbar_wait(z_ready, 0);
+            tc_fence_after();
+            gemm_ss(acc2_ready + 0);
+#pragma unroll 1
+            for (int nc = 0; nc < C::NC1; ++nc) {
+                if (nc + 1 < C::NC1) {
+                    mbar_wait(r1b, nc & 1);
+                    tc_fence_after();
+                    gemm_ss(acc2_ready + nc + 1);
+                }
+#pragma unroll 1
+                for (int cg = 0; cg < 2; ++cg) {
+                    mbar_wait(hid_ready + 2 * nc + cg, 0);
+                    tc_fence_after();
+                    gemm_ts(2 * nc + cg);
+                }
+            }
+            mma_commit(acc3_ready);
+        }
+    } else {
+        // ================= epilogue threads: one time step each, column group cg ================
+        const int q = warp & 3, cg = warp >> 2;
+        const int r = 32 * q + lane, t = t0 + r;
+        const bool valid = t < l;
+        const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
+        const size_t brow = (size_t)b * H * l + (valid ? t : 0);
+        const float *bo_g = a.bimg, *b1_g = a.bimg + 2 * H, *b2_g = a.bimg + 4 * H;
+        // this thread's channels: h = nc * 64 + cg * 32 + i, nc < 4, i < 32 (the same set in every phase)
+
+        // ---- g -> slots (A operand of G1), two rounds of 64 loads in flight
+#pragma unroll 1
+        for (int rd = 0; rd < 2; ++rd) {
+            float v[64];
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const float *gp = a.g + brow + ((2 * rd + kk) * 64 + cg * 32) * l;
+#pragma unroll
+                for (int i = 0; i < 32; ++i, gp += l) v[kk * 32 + i] = valid ? __ldg(gp) : 0.f;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                uint8_t *slot = slots + (2 * rd + kk) * UM_SLOT;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint4 hi, lo;
+                    split8(v + kk * 32 + 8 * c8, hi, lo);
+                    const uint32_t off = sw128_off(r, cg * 4 + c8);
+                    *reinterpret_cast<uint4 *>(slot + off) = hi;
+                    *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
+                }
+            }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(g_ready);
+        // ---- x -> TMEM R3 while G1 runs
+#pragma unroll 1
+        for (int rd = 0; rd < 2; ++rd) {
+            float v[64];
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const float *xp = a.x + brow + ((2 * rd + kk) * 64 + cg * 32) * l;
+#pragma unroll
+                for (int i = 0; i < 32; ++i, xp += l) v[kk * 32 + i] = valid ? __ldg(xp) : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float w[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = v[c * 16 + i];
+                tmem_st16(tl + C::R3 + (2 * rd + c / 2) * 64 + cg * 32 + (c & 1) * 16, w);
+            }
+        }
+        tmem_wait_st();
+
+        auto exchange = [&](float &mean, float &M2) {       // through HBUF columns (idle outside E2 / G3)
+            tmem_st2(tl + C::HBUF + 2 * cg, mean, M2);
+            tmem_wait_st();
+            tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(C::EPI) : "memory");
+            tc_fence_after();
+            float m0, s0, m1, s1;
+            tmem_ld2(tl + C::HBUF, m0, s0);
+            tmem_ld2(tl + C::HBUF + 2, m1, s1);
+            tmem_wait_ld();
+            const float mt = 0.5f * (m0 + m1), d0 = m0 - mt, d1 = m1 - mt;
+            mean = mt;
+            M2 = s0 + s1 + (d0 * d0 + d1 * d1) * (float)(H / 2);
+        };
+
+        // ---- E1: GLU + residual -> x1 (R3), LN2 statistics
+        float mean = 0.f, M2 = 0.f;
+        {
+            int n = 0;
+#pragma unroll 1
+            for (int nc = 0; nc < C::NC1; ++nc) {
+                mbar_wait(acc1_ready + nc, 0);
+                tc_fence_after();
+#pragma unroll 1
+                for (int sc = 0; sc < 2; ++sc) {
+                    const int p0 = cg * 32 + sc * 16, h0 = nc * 64 + p0;
+                    float xv[16], av[16], gv[16];
+                    tmem_ld16(tl + C::R1 + p0, av);
+                    tmem_ld16(tl + C::R1 + 64 + p0, gv);
+                    tmem_ld16(tl + C::R3 + h0, xv);
+                    tmem_wait_ld();
+                    const float *ba = bo_g + nc * 128 + p0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float y = (av[i] + __ldg(ba + i)) * sigmoid_fast(gv[i] + __ldg(ba + 64 + i));
+                        if (a.cond && valid) y += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i) * l);
+                        xv[i] += y;
+                    }
+                    stat_merge16(xv, n, mean, M2);
+                    n += 16;
+                    tmem_st16(tl + C::R3 + h0, xv);
+                }
+                tc_fence_before();
+                mbar_arrive(r1a);                       // R1 drained: the next N chunk may be issued
+            }
+            tmem_wait_st();
+        }
+        exchange(mean, M2);
+        // ---- z = LN2(x1) -> slots (A operand of G2)
+        {
+            const float rstd = valid ? rsqrtf(M2 * (1.0f / H)) : 0.f;
+            const float sc_a = a.ln2_s * rstd, sh = a.ln2_m - mean;
+#pragma unroll 1
+            for (int k = 0; k < 8; ++k) {
+                const int nc = k >> 1, sc = k & 1;
+                const int h0 = nc * 64 + cg * 32 + sc * 16;
+                float v[16];
+                tmem_ld16(tl + C::R3 + h0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = sc_a * (v[i] + sh);
+                uint8_t *slot = slots + nc * UM_SLOT;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint4 hi, lo;
+                    split8(v + 8 * hh, hi, lo);
+                    const uint32_t off = sw128_off(r, ((h0 & 63) >> 3) + hh);
+                    *reinterpret_cast<uint4 *>(slot + off) = hi;
+                    *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(z_ready);
+        }
+        // ---- E2: hidden = gelu(W1 z + b1) -> TMEM HBUF[cg] (A operand of G3, K chunk 2 nc + cg)
+#pragma unroll 1
+        for (int nc = 0; nc < C::NC1; ++nc) {
+            mbar_wait(acc2_ready + nc, 0);
+            if (nc > 0) mbar_wait(hfree + cg, (nc - 1) & 1);       // G3 has consumed the previous contents
+            tc_fence_after();
+            const uint32_t hb = tl + C::HBUF + 64 * cg;
+#pragma unroll 1
+            for (int sc = 0; sc < 4; ++sc) {
+                const int col = cg * 64 + sc * 16, f0 = nc * 128 + col;
+                float v[16];
+                tmem_ld16(tl + C::R1 + col, v);
+                tmem_wait_ld();
+                const float *bb = b1_g + f0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i] + __ldg(bb + i));
+                uint4 h0, l0, h1, l1;
+                split8(v, h0, l0);
+                split8(v + 8, h1, l1);
+                tmem_st8(hb + sc * 8, h0, h1);
+                tmem_st8(hb + 32 + sc * 8, l0, l1);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(hid_ready + 2 * nc + cg);
+            mbar_arrive(r1b);
+        }
+        // ---- E3: x2 = acc3 (= x1 + W2 hidden) + b2 (+skip); store; statistics for the next norm
+        {
+            mbar_wait(acc3_ready, 0);
+            tc_fence_after();
+            int n = 0;
+            mean = 0.f;
+            M2 = 0.f;
+            float *op = a.out + brow;
+#pragma unroll 1
+            for (int k = 0; k < 8; ++k) {
+                const int h0 = (k >> 1) * 64 + cg * 32 + (k & 1) * 16;
+                float v[16];
+                tmem_ld16(tl + C::R3 + h0, v);
+                if (a.skip) {
+                    float sk[16];
+                    const float *sp = a.skip + brow + h0 * l;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i, sp += l) sk[i] = valid ? __ldg(sp) : 0.f;
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += sk[i];
+                } else
+                    tmem_wait_ld();
+                const float *bb = b2_g + h0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += __ldg(bb + i);
+                if (valid) {
+                    float *oq = op + h0 * l;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i, oq += l) *oq = v[i];
+                }
+                stat_merge16(v, n, mean, M2);
+                n += 16;
+            }
+            exchange(mean, M2);
+            if (cg == 0 && valid)
+                *reinterpret_cast<float2 *>(a.stats_out + ((size_t)b * l + t) * 2) = make_float2(mean, rsqrtf(M2 * (1.0f / H)));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// weight image of the H = 256 kernel (stage order: U256::stage_info) + biases (bo permuted | b1 | b2)
+__global__ void umma_pack256_kernel(const float *__restrict__ Wo_t, const float *__restrict__ W1_t,
+                                    const float *__restrict__ W2_t, const float *__restrict__ bo, const float *__restrict__ b1,
+                                    const float *__restrict__ b2, uint8_t *__restrict__ img, float *__restrict__ bimg) {
+    constexpr int H = 256, F = 512;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one (stage, row, 16-byte chunk)
+    if (idx < (size_t)5 * H) {
+        float v;
+        if (idx < (size_t)2 * H) {
+            const int nc = idx / 128, i = idx % 128;
+            v = bo[i < 64 ? nc * 64 + i : H + nc * 64 + (i - 64)];
+        } else if (idx < (size_t)4 * H)
+            v = b1[idx - 2 * H];
+        else
+            v = b2[idx - 4 * H];
+        bimg[idx] = v;
+    }
+    if (idx >= (size_t)U256::NSTG * 128 * 8) return;
+    const int stage = idx / (128 * 8), rem = idx % (128 * 8), row = rem / 8, j = rem % 8;
+    int gemm, nblk, kc;
+    U256::stage_info(stage, gemm, nblk, kc);
+    const float *Wt = gemm == 0 ? Wo_t : (gemm == 1 ? W1_t : W2_t);
+    const int M = gemm == 2 ? H : F;
+    const int n = gemm == 0 ? (row < 64 ? nblk * 64 + row : H + nblk * 64 + (row - 64)) : nblk * 128 + row;
+    const int k0 = kc * 64 + j * 8;
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float w0 = Wt[(size_t)(k0 + 2 * e) * M + n], w1 = Wt[(size_t)(k0 + 2 * e + 1) * M + n];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(w0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(w1 - __bfloat162float(h1));
+        hp[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lp[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const size_t off = (size_t)stage * UM_STAGE + (size_t)row * 128 + ((j ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4 *>(img + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4 *>(img + off + UM_STAGE / 2) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+}
+
 // ---------------------------------------------------------------------------------------
 // finalize: folded fp32 weights (transposed [K][M]) -> the streamed shared-memory image
 // ---------------------------------------------------------------------------------------
@@ -922,10 +1331,10 @@ __global__ void umma_pack_kernel(const float *__restrict__ Wo_t, const float *__
     *reinterpret_cast<uint4 *>(img + off + (size_t)NR * 128) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
 }
 
-bool mix_umma_supported(int H, int F, int l) { return F == 2 * H && (H == 64 || H == 128) && l >= 1; }
+bool mix_umma_supported(int H, int F, int l) { return F == 2 * H && (H == 64 || H == 128 || H == 256) && l >= 1; }
 
 size_t mix_umma_image_bytes(int H) {
-    return H == 64 ? UCfg<64, 2>::IMG_BYTES : (H == 128 ? UCfg<128, 2>::IMG_BYTES : 0);
+    return H == 64 ? UCfg<64, 2>::IMG_BYTES : (H == 128 ? UCfg<128, 2>::IMG_BYTES : (H == 256 ? U256::IMG_BYTES : 0));
 }
 
 int mix_umma_pack(int H, const float *Wo_t, const float *W1_t, const float *W2_t, const float *bo, const float *b1,
@@ -934,6 +1343,7 @@ int mix_umma_pack(int H, const float *Wo_t, const float *W1_t, const float *W2_t
     const unsigned grid = (unsigned)ceil_div64((int64_t)total, 256);
     if (H == 64) umma_pack_kernel<64><<<grid, 256, 0, st>>>(Wo_t, W1_t, W2_t, bo, b1, b2, img, bimg);
     else if (H == 128) umma_pack_kernel<128><<<grid, 256, 0, st>>>(Wo_t, W1_t, W2_t, bo, b1, b2, img, bimg);
+    else if (H == 256) umma_pack256_kernel<<<grid, 256, 0, st>>>(Wo_t, W1_t, W2_t, bo, b1, b2, img, bimg);
     else {
         set_error("mix_umma_pack: H=%d unsupported", H);
         return DWB_ERR_UNSUPPORTED;
@@ -984,6 +1394,13 @@ int mix_umma_launch(const MixArgs &a, int B, cudaStream_t st) {
         const char *e = getenv("DWB_UMMA");
         return !e ? 0 : (std::string(e) == "tile" ? 1 : (std::string(e) == "pers" ? 2 : 0));
     }();
+    if (a.H == 256) {
+        auto k = sashimi_mix_umma256_kernel;
+        DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U256::SMEM));
+        k<<<dim3(ceil_div(a.l, UM_TT), B), U256::NTHREADS, U256::SMEM, st>>>(a);
+        DWB_LAUNCH_CHECK();
+        return DWB_OK;
+    }
     const bool pers = mode == 2 || (mode == 0 && a.H == 128);
     if (pers) switch (a.H) {
         case 64: return launch_umma_pers<64, 2>(a, B, st);

@@ -15,7 +15,7 @@ sd = dwb.init.seeded_state_dict(cfg, seed=0)
 net = dwb.construct_model(dict(cfg)); net.load_state_dict(sd); net = net.cuda().eval()
 eng = net._engine_get()
 g = torch.Generator().manual_seed(3)
-blocks = [(0, 64, L), (1, 128, L // 4)]
+blocks = [(0, 64, L), (1, 128, L // 4), (2, 256, L // 16)]
 for blk, H, l in blocks:
     gg = torch.randn(B, H, l, generator=g).cuda()
     x = torch.randn(B, H, l, generator=g).cuda() * 1.5 + 0.3
