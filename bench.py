@@ -39,6 +39,9 @@ CFG = dict(_name_="sashimi", unconditional=True, in_channels=1, out_channels=1,
            unet=True, d_model=64, n_layers=6, pool=[4, 4], expand=2, ff=2, L=16000)
 T_STEPS, BETA_0, BETA_T, L = 200, 1e-4, 0.02, 16000
 METRIC = "audio clips/sec (16k-sample, T=200)"
+KERNEL_NAMES = {"fftconv_s0": "fftconv_kernel<14> (H=64, l=16000)", "fftconv_s1": "fftconv_kernel<12> (H=128, l=4000)",
+                "fftconv_s2": "fftconv_kernel<10> (H=256, l=1000)", "mix_s0": "sashimi_mix_umma_kernel<64> (l=16000)",
+                "mix_s1": "sashimi_mix_umma_pers_kernel<128> (l=4000)", "mix_s2": "sashimi_mix_umma256_kernel (l=1000)"}
 
 
 def peaks():
@@ -270,10 +273,19 @@ def main():
                 ent["frac_of_hbm"] = round(ent["achieved_GBs"] / hbm, 4)
             kern[name] = ent
         dom = max(kern, key=lambda k: kern[k]["share"])
-        roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 4),
-                "traffic": None, "peak_source": src, "kernel": "whole T-step loop (one CUDA-graph launch per step)",
-                "algorithmic_bytes_per_clip_step": bytes_cs, "flops_per_clip_step": flops_cs,
-                "dominant_kernel": dom, "kernels": kern}
+        d = kern[dom]
+        traffic = None                      # dram read+write bytes per launch from the committed ncu --set full capture
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom, {}).get(str(B))
+        roof = {"bound": "hbm", "kernel": KERNEL_NAMES.get(dom, dom), "achieved": d.get("achieved_GBs"), "peak": hbm, "unit": "GB/s",
+                "frac": d.get("frac_of_hbm"), "traffic": traffic, "peak_source": src,
+                "algorithmic_bytes_per_launch": d.get("algorithmic_bytes_per_launch"),
+                "us_per_launch": round(d["ms_per_forward"] / d["launches"] * 1e3, 2), "share_of_step": d["share"],
+                "whole_loop": {"achieved": round(achieved, 1), "frac": round(achieved / hbm, 4), "unit": "GB/s",
+                               "algorithmic_bytes_per_clip_step": bytes_cs, "flops_per_clip_step": flops_cs,
+                               "note": "SURVEY 8(d) bytes x T x B / step time (one CUDA-graph launch per step)"},
+                "kernels": kern}
         line = {"metric": METRIC, "value": round(value, 4), "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

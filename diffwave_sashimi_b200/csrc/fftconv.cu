@@ -54,9 +54,26 @@ struct Radix {
             Radix<R / 2, INV, ZHI>::run(o);
 #pragma unroll
             for (int q = 0; q < R / 2; ++q) {
+                // t = o[q] * omega_R^{+-q}; the trivial rotations (1, -+i, sqrt(1/2)(+-1 -+ i)) are spelled out:
+                // "x * 0.0f" cannot be folded by the compiler and would cost an FFMA each
                 constexpr int step = 16 / R;
-                const float wr = WR[q * step], wi = INV ? -WI[q * step] : WI[q * step];
-                const float2 t = make_float2(o[q].x * wr - o[q].y * wi, o[q].x * wi + o[q].y * wr);
+                const int k = q * step;              // omega_16 exponent, 0..7 (compile time after unrolling)
+                constexpr float h = 0.70710678118654752f;
+                float2 t;
+                if (k == 0) {
+                    t = o[q];
+                } else if (k == 4) {
+                    t = INV ? make_float2(-o[q].y, o[q].x) : make_float2(o[q].y, -o[q].x);
+                } else if (k == 2) {
+                    t = INV ? make_float2(h * (o[q].x - o[q].y), h * (o[q].x + o[q].y))
+                            : make_float2(h * (o[q].x + o[q].y), h * (o[q].y - o[q].x));
+                } else if (k == 6) {
+                    t = INV ? make_float2(-h * (o[q].x + o[q].y), h * (o[q].x - o[q].y))
+                            : make_float2(h * (o[q].y - o[q].x), -h * (o[q].x + o[q].y));
+                } else {
+                    const float wr = WR[k], wi = INV ? -WI[k] : WI[k];
+                    t = make_float2(o[q].x * wr - o[q].y * wi, o[q].x * wi + o[q].y * wr);
+                }
                 x[q] = make_float2(e[q].x + t.x, e[q].y + t.y);
                 x[q + R / 2] = make_float2(e[q].x - t.x, e[q].y - t.y);
             }
