@@ -8,6 +8,7 @@
 // pass ever runs; the cached pointwise table is simply stored in the order the forward passes leave.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 namespace dwb {
 
@@ -42,6 +43,20 @@ __host__ __device__ constexpr int fft_pos(int k, int log2M) { return fft_brev(k,
 __host__ __device__ constexpr int fft_freq(int pos, int log2M) { return fft_brev(pos, log2M); }
 // floats per channel of the cached pointwise table used by fftconv: M/2 + 1 entries of 8
 __host__ __device__ constexpr long long fft_table_floats(int log2M) { return 8LL * ((1LL << (log2M - 1)) + 1); }
+
+// Kernel variant per transform size.  The "split" variants (v2 scalar, v3 packed fp32) evaluate the M-point
+// transform of the half-empty packed row as two independent M/2-point transforms (even / odd output
+// frequencies), one after the other in half the shared memory, so two rows are resident per SM; their
+// pointwise table is laid out per half (see kcoef_kernel).  v1 handles every other size.
+// DWB_FFT=v1 forces v1 everywhere, DWB_FFT=v2 the scalar split kernel (A/B measurements); read once.
+inline int fft_forced_variant() {
+    static const int forced = [] {
+        const char *e = getenv("DWB_FFT");
+        return (e && e[0] == 'v' && (e[1] == '1' || e[1] == '2')) ? (e[1] - '0') : 0;
+    }();
+    return forced;
+}
+inline bool fft_use_v2(int log2M) { return fft_forced_variant() != 1 && log2M == 14; }
 
 // shared-memory padding: one float2 of slack per 16 so that the stride-16 and stride-1
 // passes (16 consecutive elements per thread) are bank-conflict free

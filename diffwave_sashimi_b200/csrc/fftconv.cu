@@ -25,99 +25,14 @@
 // coefficient table (16(M+2) B per channel) are shared by H resp. B rows and stay in L2 (rows of
 // one channel are adjacent in the grid).
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "fft_plan.cuh"
+#include "fft_radix.cuh"
+#include "kernels.h"
 
 namespace dwb {
-
-// ---- in-register radix-R DFT, natural order in and out --------------------------------
-// ZHI: inputs x[R/2..R) are zero and are not read
-template <int R, bool INV, bool ZHI = false>
-struct Radix {
-    static __device__ __forceinline__ void run(float2 *x) {
-        // omega_16^q = exp(-2 pi i q / 16), q = 0..7
-        constexpr float WR[8] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
-                                 0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
-        constexpr float WI[8] = {0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
-                                 -1.0f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
-        if constexpr (R == 2 && ZHI) {
-            x[1] = x[0];
-        } else {
-            float2 e[R / 2], o[R / 2];
-#pragma unroll
-            for (int i = 0; i < (ZHI ? R / 4 : R / 2); ++i) {
-                e[i] = x[2 * i];
-                o[i] = x[2 * i + 1];
-            }
-            Radix<R / 2, INV, ZHI>::run(e);
-            Radix<R / 2, INV, ZHI>::run(o);
-#pragma unroll
-            for (int q = 0; q < R / 2; ++q) {
-                // t = o[q] * omega_R^{+-q}; the trivial rotations (1, -+i, sqrt(1/2)(+-1 -+ i)) are spelled out:
-                // "x * 0.0f" cannot be folded by the compiler and would cost an FFMA each
-                constexpr int step = 16 / R;
-                const int k = q * step;              // omega_16 exponent, 0..7 (compile time after unrolling)
-                constexpr float h = 0.70710678118654752f;
-                float2 t;
-                if (k == 0) {
-                    t = o[q];
-                } else if (k == 4) {
-                    t = INV ? make_float2(-o[q].y, o[q].x) : make_float2(o[q].y, -o[q].x);
-                } else if (k == 2) {
-                    t = INV ? make_float2(h * (o[q].x - o[q].y), h * (o[q].x + o[q].y))
-                            : make_float2(h * (o[q].x + o[q].y), h * (o[q].y - o[q].x));
-                } else if (k == 6) {
-                    t = INV ? make_float2(-h * (o[q].x + o[q].y), h * (o[q].x - o[q].y))
-                            : make_float2(h * (o[q].y - o[q].x), -h * (o[q].x + o[q].y));
-                } else {
-                    const float wr = WR[k], wi = INV ? -WI[k] : WI[k];
-                    t = make_float2(o[q].x * wr - o[q].y * wi, o[q].x * wi + o[q].y * wr);
-                }
-                x[q] = make_float2(e[q].x + t.x, e[q].y + t.y);
-                x[q + R / 2] = make_float2(e[q].x - t.x, e[q].y - t.y);
-            }
-        }
-    }
-};
-template <bool INV, bool ZHI>
-struct Radix<1, INV, ZHI> {
-    static __device__ __forceinline__ void run(float2 *) {}
-};
-
-// w[q] = w1^q, q = 1..R-1, by squaring/products of depth log2 R (a serial chain w *= w1 puts R-1
-// dependent complex multiplies on the critical path of every butterfly)
-template <int R>
-__device__ __forceinline__ void twiddle_powers(float2 w1, float2 (&w)[R]) {
-    w[0] = make_float2(1.f, 0.f);
-    if (R > 1) w[1] = w1;
-#pragma unroll
-    for (int q = 2; q < R; ++q) {
-        int hb = 1;
-        while (hb * 2 <= q) hb *= 2;
-        w[q] = (q == hb) ? cmul(w[q / 2], w[q / 2]) : cmul(w[hb], w[q - hb]);
-    }
-}
-
-// x[q] *= w1^q, q < R, keeping at most R/2 powers live (w^1..w^{R/2-1}, then w^{R/2} times those)
-template <int R>
-__device__ __forceinline__ void apply_twiddles(float2 (&x)[R], float2 w1) {
-    if constexpr (R >= 8) {
-        float2 w[R / 2];
-        twiddle_powers<R / 2>(w1, w);
-#pragma unroll
-        for (int q = 1; q < R / 2; ++q) x[q] = cmul(x[q], w[q]);
-        const float2 wh = cmul(w[R / 4], w[R / 4]);
-        x[R / 2] = cmul(x[R / 2], wh);
-#pragma unroll
-        for (int q = 1; q < R / 2; ++q) x[R / 2 + q] = cmul(x[R / 2 + q], cmul(wh, w[q]));
-    } else {
-        float2 w[R];
-        twiddle_powers<R>(w1, w);
-#pragma unroll
-        for (int q = 1; q < R; ++q) x[q] = cmul(x[q], w[q]);
-    }
-}
 
 // ---- one in-place pass over the shared array ---------------------------------------------
 // forward (DIF): u_q = sum_p x[j + p sub] w_R^{pq};  store u_q W_S^{jq} at j + brev(q) sub
@@ -125,6 +40,7 @@ __device__ __forceinline__ void apply_twiddles(float2 (&x)[R], float2 w1) {
 template <int LR, bool INV, int LOG2M, int LOG2S, int NT>
 __device__ __forceinline__ void fft_pass(float2 *s, const float2 *__restrict__ stw, int tid) {
     constexpr int R = 1 << LR, M = 1 << LOG2M, log2sub = LOG2S - LR, sub = 1 << log2sub;
+#pragma unroll 1
     for (int bi = tid; bi < M / R; bi += NT) {
         const int j = bi & (sub - 1);
         const int base = ((bi >> log2sub) << LOG2S) + j;
@@ -168,17 +84,6 @@ __device__ __forceinline__ void fft_mid_passes(float2 *s, const float2 *__restri
     }
 }
 
-// ---- real-FFT untangle + spectrum product + re-tangle of one pair ------------------------------
-// a = Z[k] (slot p, k < M/2), b = Z[M-k] (slot p2);  c0 = (alpha, beta), c1 = (gamma, delta):
-//   Z'[k] = alpha a + beta conj(b),  Z'[M-k] = conj(gamma a + delta conj(b))
-__device__ __forceinline__ void pair_map(float2 &a, float2 &b, const float4 c0, const float4 c1) {
-    const float2 oa = make_float2(c0.x * a.x - c0.y * a.y + c0.z * b.x + c0.w * b.y,
-                                  c0.x * a.y + c0.y * a.x + c0.w * b.x - c0.z * b.y);
-    const float2 ob = make_float2(c1.x * a.x - c1.y * a.y + c1.z * b.x + c1.w * b.y,
-                                  -(c1.x * a.y + c1.y * a.x + c1.w * b.x - c1.z * b.y));
-    a = oa;
-    b = ob;
-}
 // generic (shared-memory) form for leader entry idx in [0, M/2]
 template <int LOG2M>
 __device__ __forceinline__ void pointwise_smem(float2 *s, int idx, const float4 c, const float4 c1) {
@@ -273,6 +178,7 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
         }
         for (int j = tid; j < Cfg::NTW; j += NT) stw[j] = tw[2 * j];
         __syncthreads();
+#pragma unroll 1
         for (; bi < sub0; bi += NT) {
             float2 xx[16];
 #pragma unroll
@@ -310,6 +216,7 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
         };
         float4 ca[R], cb[R];
         if (tid < NITEM) load_coef(tid, ca, cb);
+#pragma unroll 1
         for (int item = tid; item < NITEM; item += NT) {
             const int ga = 2 * item, gb = partner(ga);
             float2 xa[R], xb[R];
@@ -375,6 +282,7 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
             c0 = __ldg(kcr + 2 * tid);
             c1 = __ldg(kcr + 2 * tid + 1);
         }
+#pragma unroll 1
         for (int idx = tid; idx <= M / 2; idx += NT) {
             float4 n0 = c0, n1 = c1;
             if (idx + NT <= M / 2) {
@@ -392,6 +300,7 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
     fft_mid_passes<LOG2M, NT, true, 1, Cfg::FUSED ? NP - 2 : NP - 1>(s, stw, tid);
 
     // ---- last inverse pass (pass 0), fused with the epilogue: only outputs p < 8 can fall inside the row
+#pragma unroll 1
     for (int bi = tid; bi < sub0; bi += NT) {
         float2 xx[16];
 #pragma unroll
@@ -411,6 +320,255 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
                 if (2 * i + 1 < l) gr[2 * i + 1] = gelu_fast(xx[p].y);
             }
         }
+    }
+}
+
+// =====================================================================================================
+// v2: split transform.  The packed row z[i] (i < M) is zero for i >= M/2, so its M-point spectrum is two
+// independent Mh = M/2 point transforms:  Z[2k'] = FFT_Mh(z)[k']  and  Z[2k'+1] = FFT_Mh(z[i] W_M^i)[k'].
+// The conjugate pairs (k, M-k) of the real-FFT untangle never mix the two (k and M-k have the same
+// parity), and the wanted outputs are z'[i] = a[i] + W_M^{-i} b[i], i < Mh, with a, b the inverse
+// transforms of the two halves.  One CTA runs the two halves one after the other in Mh complex of shared
+// memory (half of v1's footprint, so two rows are resident per SM and one row's shared-memory phases
+// overlap the other's arithmetic); `a` is parked in the output row (written and read back by the same
+// thread) and the W_M^{+-i} rotations are folded into the outer radix-16 passes (a constant rotation
+// W_32^p of the butterfly inputs/outputs and odd instead of even twiddle powers).
+// =====================================================================================================
+
+template <int LOG2M>
+struct Fft2Cfg {
+    static constexpr int LH = LOG2M - 1, Mh = 1 << LH;
+    static constexpr int NT = (Mh / 32 > 256) ? 256 : ((Mh / 32 < 64) ? 64 : Mh / 32);
+    static constexpr int NTW = Mh / 16;                        // W_Mh^j and W_M^j, j < Mh/16
+    static constexpr int SDATA = Mh + Mh / 16 + 1;
+    static constexpr int SMEM = (SDATA + 2 * NTW) * (int)sizeof(float2);
+    static constexpr int NP = fft_num_passes(LH);
+    static constexpr int RL = fft_radix_log2(LH, NP - 1);      // centre radix: 2, 4 or 8 (fft_use_v2)
+    static_assert(LH >= 8 && RL >= 1 && RL <= 3, "v2 needs a radix-2/4/8 tail");
+};
+
+template <int LOG2M>
+__global__ void __launch_bounds__(Fft2Cfg<LOG2M>::NT, 512 / Fft2Cfg<LOG2M>::NT)
+fftconv2_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
+                long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
+                const float2 *__restrict__ tw /* W_n^i, i < M */, float *g, int B, int H, int l) {
+    using Cfg = Fft2Cfg<LOG2M>;
+    constexpr int LH = Cfg::LH, Mh = Cfg::Mh, NT = Cfg::NT, NP = Cfg::NP, RL = Cfg::RL;
+    constexpr int log2sub0 = LH - 4, sub0 = 1 << log2sub0;         // outer pass: radix 16, span Mh
+    extern __shared__ float2 s[];
+    float2 *stwA = s + Cfg::SDATA;                                 // W_Mh^j
+    float2 *stwB = stwA + Cfg::NTW;                                // W_M^j
+    const int tid = threadIdx.x;
+    const int row = blockIdx.x;
+    const int h = row / B, b = row - h * B;
+    const size_t off = ((size_t)b * H + h) * (size_t)l;
+    const float *xr = x + off;
+    float *gr = g + off;
+    const float pt = part_t ? part_t[(size_t)b * part_stride_b + h] : 0.f;
+    const float *st = stats ? stats + (size_t)b * l * 2 : nullptr;
+    const float4 *kcr = kc + (size_t)h * (2 * Mh + 2);             // (Mh + 1) entries of two float4
+    const float lns = st ? ln_s : 1.f, lnm = st ? ln_m : 0.f;
+    const bool vec = ((l & 1) == 0);
+    const int half = l >> 1;
+
+    auto load_in = [&](int i, float2 &xv, float4 &sv) {
+        xv = make_float2(0.f, 0.f);
+        sv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec) {
+            if (i < half) {
+                xv = reinterpret_cast<const float2 *>(xr)[i];
+                sv = st ? reinterpret_cast<const float4 *>(st)[i] : make_float4(0.f, 1.f, 0.f, 1.f);
+            }
+        } else {
+            const int t0 = 2 * i;
+            if (t0 < l) {
+                xv.x = xr[t0];
+                sv.x = st ? st[2 * t0] : 0.f;
+                sv.y = st ? st[2 * t0 + 1] : 1.f;
+            }
+            if (t0 + 1 < l) {
+                xv.y = xr[t0 + 1];
+                sv.z = st ? st[2 * t0 + 2] : 0.f;
+                sv.w = st ? st[2 * t0 + 3] : 1.f;
+            }
+        }
+    };
+    auto apply_in = [&](int i, float2 xv, float4 sv) {
+        const int t0 = 2 * i;
+        return make_float2((lns * sv.y) * (xv.x - sv.x + lnm) + (t0 < l ? pt : 0.f),
+                           (lns * sv.w) * (xv.y - sv.z + lnm) + (t0 + 1 < l ? pt : 0.f));
+    };
+
+    // L1 prefetches (no destination registers): inputs of the next outer butterfly / the parked a[i]
+    auto prefetch_in = [&](int bi) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const int i = bi + (p << log2sub0);
+            if (2 * i < l) {
+                prefetch_l1(xr + 2 * i);
+                if (st) prefetch_l1(st + 4 * i);
+            }
+        }
+    };
+    auto prefetch_out = [&](int bi) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const int i = bi + (p << log2sub0);
+            if (2 * i < l) prefetch_l1(gr + 2 * i);
+        }
+    };
+
+    for (int j = tid; j < Cfg::NTW; j += NT) {
+        stwA[j] = tw[4 * j];
+        stwB[j] = tw[2 * j];
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int odd = 0; odd < 2; ++odd) {       // one copy of the code for both halves: instruction-cache footprint
+        // ---- outer forward pass, fused with the prologue: inputs i = j + p sub0, p < 16
+#pragma unroll 1
+        for (int bi = tid; bi < sub0; bi += NT) {
+            float2 xx[16];
+            if (bi + NT < sub0) prefetch_in(bi + NT);
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {          // two batches of 8 loads bound the registers in flight
+                float2 xv[8];
+                float4 sv[8];
+#pragma unroll
+                for (int p = 0; p < 8; ++p) load_in(bi + ((8 * hb + p) << log2sub0), xv[p], sv[p]);
+#pragma unroll
+                for (int p = 0; p < 8; ++p) xx[8 * hb + p] = apply_in(bi + ((8 * hb + p) << log2sub0), xv[p], sv[p]);
+            }
+            if (odd) rotate_w32<false>(xx);
+            Radix<16, false>::run(xx);
+            apply_twiddles16<true>(xx, odd ? stwB[bi] : make_float2(1.f, 0.f), stwA[bi]);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) s[fft_pad(bi + (fft_brev(q, 4) << log2sub0))] = xx[q];
+        }
+        __syncthreads();
+
+        fft_mid_passes<LH, NT, false, 1, NP - 2>(s, stwA, tid);
+
+        // ---- centre: last forward pass + untangle/product/re-tangle + first inverse pass, in registers
+        {
+            constexpr int R = 1 << RL, G = Mh / R, NITEM = Mh / (2 * R);
+            const float4 *kh = odd ? kcr + (Mh + 2) : kcr;          // odd half: entries Mh/2 + 1 ...
+            auto partner = [&](int ga) {
+                return odd ? (ga ^ (G - 1)) : (ga == 0 ? 1 : ga ^ ((1 << (31 - __clz(ga))) - 1));
+            };
+            auto load_coef = [&](int item, float4 (&ca)[R], float4 (&cb)[R]) {
+                const float4 *ka = kh + (size_t)R * (2 * item), *kb = kh + (size_t)R * partner(2 * item);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    ca[i] = __ldg(ka + i);
+                    cb[i] = __ldg(kb + i);
+                }
+            };
+            float4 ca[R], cb[R];
+            if (tid < NITEM) load_coef(tid, ca, cb);
+#pragma unroll 1
+            for (int item = tid; item < NITEM; item += NT) {
+                const int ga = 2 * item, gb = partner(ga);
+                float2 xa[R], xb[R];
+#pragma unroll
+                for (int c = 0; c < R; ++c) {
+                    xa[c] = s[fft_pad(R * ga + c)];
+                    xb[c] = s[fft_pad(R * gb + c)];
+                }
+                float4 na[R], nb[R];
+                if (item + NT < NITEM) load_coef(item + NT, na, nb);
+                Radix<R, false>::run(xa);
+                Radix<R, false>::run(xb);
+                if (!odd && item == 0) {
+                    const float4 s0 = __ldg(kcr + Mh), s1 = __ldg(kcr + Mh + 1);
+                    {
+                        const float2 a = xa[0];
+                        const float p0 = 2.f * (a.x + a.y) * ca[0].x, pM = 2.f * (a.x - a.y) * ca[0].y;
+                        xa[0] = make_float2(p0 + pM, p0 - pM);
+                        float2 d = xa[R / 2];
+                        pair_map(xa[R / 2], d, s0, s1);
+                    }
+#pragma unroll
+                    for (int c = 2; c < R; c += 2) {
+                        int msb = 0;
+                        while ((2 << msb) <= c) ++msb;
+                        const int c2 = c ^ ((1 << msb) - 1);
+                        pair_map(xa[fft_brev(c, RL)], xa[fft_brev(c2, RL)], ca[c], ca[c + 1]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < R / 2; ++q) {
+                        const int e = fft_brev(q, RL) >> 1;
+                        pair_map(xb[q], xb[q ^ (R - 1)], cb[2 * e], cb[2 * e + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < R / 2; ++q) {
+                        const int e = fft_brev(q, RL) >> 1;
+                        pair_map(xa[q], xb[q ^ (R - 1)], ca[2 * e], ca[2 * e + 1]);
+                        pair_map(xb[q], xa[q ^ (R - 1)], cb[2 * e], cb[2 * e + 1]);
+                    }
+                }
+                Radix<R, true>::run(xa);
+                Radix<R, true>::run(xb);
+#pragma unroll
+                for (int p = 0; p < R; ++p) {
+                    s[fft_pad(R * ga + p)] = xa[p];
+                    s[fft_pad(R * gb + p)] = xb[p];
+                }
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    ca[i] = na[i];
+                    cb[i] = nb[i];
+                }
+            }
+            __syncthreads();
+        }
+
+        if (odd && tid < sub0) prefetch_out(tid);
+        fft_mid_passes<LH, NT, true, 1, NP - 2>(s, stwA, tid);
+
+        // ---- outer inverse pass: even half parks a[i] in the output row; odd half reads it back (same
+        //      thread, same addresses), adds W_M^{-i} b[i] and writes GELU
+#pragma unroll 1
+        for (int bi = tid; bi < sub0; bi += NT) {
+            if (bi + NT < sub0) {
+                if (odd) prefetch_out(bi + NT);
+            } else if (!odd) {
+                prefetch_in(tid);               // first outer butterfly of the odd half
+            }
+            float2 xx[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) xx[q] = s[fft_pad(bi + (fft_brev(q, 4) << log2sub0))];
+            apply_twiddles16<true>(xx, odd ? cconj(stwB[bi]) : make_float2(1.f, 0.f), cconj(stwA[bi]));
+            Radix<16, true>::run(xx);
+            if (odd) {
+                rotate_w32<true>(xx);
+#pragma unroll
+                for (int p = 0; p < 16; ++p) {
+                    const int i = bi + (p << log2sub0);
+                    float2 av = make_float2(0.f, 0.f);          // a[i]: parked by this thread, prefetched to L1
+                    if (vec) {
+                        if (i < half) av = reinterpret_cast<const float2 *>(gr)[i];
+                    } else {
+                        if (2 * i < l) av.x = gr[2 * i];
+                        if (2 * i + 1 < l) av.y = gr[2 * i + 1];
+                    }
+                    xx[p] = make_float2(gelu_fast(av.x + xx[p].x), gelu_fast(av.y + xx[p].y));
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int i = bi + (p << log2sub0);
+                if (vec) {
+                    if (i < half) reinterpret_cast<float2 *>(gr)[i] = xx[p];
+                } else {
+                    if (2 * i < l) gr[2 * i] = xx[p].x;
+                    if (2 * i + 1 < l) gr[2 * i + 1] = xx[p].y;
+                }
+            }
+        }
+        __syncthreads();          // the next half overwrites the shared array
     }
 }
 
@@ -468,6 +626,22 @@ static int launch_fftconv(const float *x, const float *stats, const float *part_
     return DWB_OK;
 }
 
+template <int LOG2M>
+static int launch_fftconv2(const float *x, const float *stats, const float *part_t, long long psb, float ln_m,
+                           float ln_s, const float *kc, const float2 *tw, float *g, int B, int H, int l, cudaStream_t st) {
+    using Cfg = Fft2Cfg<LOG2M>;
+    static bool attr_set[16] = {};
+    int dev = 0;
+    DWB_CUDA(cudaGetDevice(&dev));
+    if (Cfg::SMEM > 48 * 1024 && !attr_set[dev & 15]) {
+        DWB_CUDA(cudaFuncSetAttribute(fftconv2_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_set[dev & 15] = true;
+    }
+    fftconv2_kernel<LOG2M><<<B * H, Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw, g, B, H, l);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
 int fftconv_launch(const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
                    const float *kc, float *g, int B, int H, int l, cudaStream_t st) {
     const int lg = fft_log2m_for(l);
@@ -475,6 +649,16 @@ int fftconv_launch(const float *x, const float *stats, const float *part_t, long
     const float2 *tw;
     int rc = fft_twiddles(lg, st, &tw);
     if (rc != DWB_OK) return rc;
+    if (fft_use_v2(lg)) {
+        if (fft_forced_variant() != 2 && fftconv3_supported(lg, x, stats, g, l))
+            return fftconv3_launch(lg, x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+        switch (lg) {
+            case 10: return launch_fftconv2<10>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+            case 11: return launch_fftconv2<11>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+            case 12: return launch_fftconv2<12>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+            case 14: return launch_fftconv2<14>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+        }
+    }
 #define DWB_FFT_CASE(LG) \
     case LG:             \
         return launch_fftconv<LG>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);

@@ -1,0 +1,405 @@
+// fftconv v3: the split transform of fftconv2_kernel (fftconv.cu) on packed fp32 arithmetic.
+//
+// Same algorithm as v2 — the half-empty M-point packed row is two independent Mh = M/2 point
+// transforms (even / odd output frequencies) run one after the other in Mh complex of shared memory,
+// `a` parked in the output row — but every radix-16 pass processes TWO butterflies per thread in the two
+// lanes of FADD2/FMUL2/FFMA2 (fft_simd2.cuh).  For that the shared array is kept as separate re / im
+// planes: the butterflies j and j+1 of a pass touch adjacent plane entries, so one 64-bit LDS/STS moves
+// the same element of both butterflies and lands directly in a register pair.  The radix-2/4/8 centre
+// (last forward pass + untangle/product/re-tangle + first inverse pass) stays scalar: its conjugate-pair
+// partner map reverses index order, which would need lane swaps.
+//
+// Reference: models/s4.py:1403-1411 (rfft/irfft product at n = 2l, D skip), :1430 (GELU),
+// models/sashimi.py:148-152 (norm1 + fc_t).  Requires l % 4 == 0 and 16-byte aligned rows.
+#include <stdint.h>
+
+#include "common.cuh"
+#include "fft_plan.cuh"
+#include "fft_radix.cuh"
+#include "fft_simd2.cuh"
+#include "kernels.h"
+
+namespace dwb {
+using s2::C2;
+using s2::V2;
+
+// plane padding: two floats per 32 keep 64-bit alignment and make the stride-32 accesses of the last
+// radix-16 pass (one 32-float block per thread) conflict free
+__host__ __device__ constexpr int padf(int i) { return i + 2 * (i >> 5); }
+
+template <int LOG2M>
+struct Fft3Cfg {
+    static constexpr int LH = LOG2M - 1, Mh = 1 << LH;
+    static constexpr int NT = Mh / 32;                       // one butterfly PAIR per thread in every radix-16 pass
+    static constexpr int NP = fft_num_passes(LH);            // radix-16 passes + the radix-2/4/8 tail
+    static constexpr int RL = fft_radix_log2(LH, NP - 1);
+    static constexpr int PLANE = Mh + Mh / 16 + 2;           // floats per plane
+    static constexpr int NTW0 = Mh / 16;                     // W_Mh^j and W_M^j, j < Mh/16
+    static constexpr int mid_off(int P) {                    // twiddles of pass P (1..NP-2): W_{S_P}^j, j < S_P/16
+        int o = 0;
+        for (int q = 1; q < P; ++q) o += Mh >> (4 * q + 4);
+        return o;
+    }
+    static constexpr int NMID = mid_off(NP - 1);
+    static constexpr int SMEM = (2 * PLANE + 4 * NTW0 + 2 * NMID) * (int)sizeof(float);
+    static constexpr int MINB = (512 / NT > 8) ? 8 : 512 / NT;
+    static_assert(RL >= 1 && RL <= 3 && NP >= 3 && NT >= 32, "v3 plan");
+};
+
+__device__ __forceinline__ V2 ld2(const float *p) { return V2(*reinterpret_cast<const float2 *>(p)); }
+__device__ __forceinline__ void st2(float *p, const V2 &a) { *reinterpret_cast<float2 *>(p) = a.v; }
+
+// GELU (erf form), two lanes: same formula as gelu_fast (common.cuh); MUFU and the select stay scalar
+__device__ __forceinline__ V2 gelu_fast2(const V2 &x) {
+    float t0, t1, e0, e1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.v.x), 1.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.v.y), 1.0f)));
+    const V2 t(t0, t1);
+    V2 p = fma(t, V2(1.061405429f), V2(-1.453152027f));
+    p = fma(t, p, V2(1.421413741f));
+    p = fma(t, p, V2(-0.284496736f));
+    p = fma(t, p, V2(0.254829592f));
+    const V2 ea = (x * x) * (-0.5f * 1.4426950408889634f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(ea.v.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(ea.v.y));
+    const V2 hh = (x * 0.5f) * (V2(e0, e1) * (p * t));
+    const V2 d = x - hh;
+    return V2(x.v.x >= 0.f ? d.v.x : hh.v.x, x.v.y >= 0.f ? d.v.y : hh.v.y);
+}
+
+// one in-place radix-16 pass P (span S = Mh / 16^P) over the planes, butterflies 2 tid and 2 tid + 1
+template <int LH, int P, bool INV>
+__device__ __forceinline__ void mid_pass(float *re, float *im, const float *twr, const float *twi, int tid) {
+    constexpr int LOG2S = LH - 4 * P, log2sub = LOG2S - 4, sub = 1 << log2sub;
+    static_assert(log2sub >= 1, "pairs of adjacent butterflies need sub >= 2");
+    const int bi = 2 * tid;
+    const int j = bi & (sub - 1);
+    const int base = ((bi >> log2sub) << LOG2S) + j;
+    const int pb = padf(base);
+    C2 w1;
+    w1.x = ld2(twr + j);
+    w1.y = ld2(twi + j);
+    if (INV) w1.y = -w1.y;
+    C2 one;
+    one.x = V2(1.f);
+    one.y = V2(0.f);
+    C2 x[16];
+    if (!INV) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const int o = p * sub + 2 * ((p * sub) >> 5);
+            x[p].x = ld2(re + pb + o);
+            x[p].y = ld2(im + pb + o);
+        }
+        s2::RadixS<16, false>::run(x);
+        s2::apply_twiddles16<false>(x, one, w1);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int c = fft_brev(q, 4), o = c * sub + 2 * ((c * sub) >> 5);
+            st2(re + pb + o, x[q].x);
+            st2(im + pb + o, x[q].y);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int c = fft_brev(q, 4), o = c * sub + 2 * ((c * sub) >> 5);
+            x[q].x = ld2(re + pb + o);
+            x[q].y = ld2(im + pb + o);
+        }
+        s2::apply_twiddles16<false>(x, one, w1);
+        s2::RadixS<16, true>::run(x);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const int o = p * sub + 2 * ((p * sub) >> 5);
+            st2(re + pb + o, x[p].x);
+            st2(im + pb + o, x[p].y);
+        }
+    }
+    __syncthreads();
+}
+
+template <int LH, bool INV, int P, int LAST, int NMIDOFF>
+__device__ __forceinline__ void mid_passes(float *re, float *im, const float *mr, const float *mi, int tid) {
+    if constexpr (P <= LAST) {
+        constexpr int sub = 1 << (LH - 4 * P - 4);
+        if constexpr (!INV) {
+            mid_pass<LH, P, false>(re, im, mr + NMIDOFF, mi + NMIDOFF, tid);
+            mid_passes<LH, false, P + 1, LAST, NMIDOFF + sub>(re, im, mr, mi, tid);
+        } else {
+            mid_passes<LH, true, P + 1, LAST, NMIDOFF + sub>(re, im, mr, mi, tid);
+            mid_pass<LH, P, true>(re, im, mr + NMIDOFF, mi + NMIDOFF, tid);
+        }
+    }
+}
+
+template <int LOG2M>
+__global__ void __launch_bounds__(Fft3Cfg<LOG2M>::NT, Fft3Cfg<LOG2M>::MINB)
+fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
+                long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
+                const float2 *__restrict__ tw /* W_n^i, i < M */, float *g, int B, int H, int l) {
+    using Cfg = Fft3Cfg<LOG2M>;
+    constexpr int LH = Cfg::LH, Mh = Cfg::Mh, NT = Cfg::NT, NP = Cfg::NP, RL = Cfg::RL;
+    constexpr int log2sub0 = LH - 4, sub0 = 1 << log2sub0;         // outer pass: radix 16, span Mh
+    extern __shared__ float sm[];
+    float *re = sm, *im = sm + Cfg::PLANE;
+    float *twAr = im + Cfg::PLANE, *twAi = twAr + Cfg::NTW0;       // W_Mh^j
+    float *twBr = twAi + Cfg::NTW0, *twBi = twBr + Cfg::NTW0;      // W_M^j
+    float *midr = twBi + Cfg::NTW0, *midi = midr + Cfg::NMID;
+    const int tid = threadIdx.x;
+    const int row = blockIdx.x;
+    const int h = row / B, b = row - h * B;
+    const size_t off = ((size_t)b * H + h) * (size_t)l;
+    const float4 *xr4 = reinterpret_cast<const float4 *>(x + off);
+    float *gr = g + off;
+    const float pt = part_t ? part_t[(size_t)b * part_stride_b + h] : 0.f;
+    const float4 *st4 = stats ? reinterpret_cast<const float4 *>(stats + (size_t)b * l * 2) : nullptr;
+    const float4 *kcr = kc + (size_t)h * (2 * Mh + 2);             // (Mh + 1) entries of two float4
+    const float lns = st4 ? ln_s : 1.f, lnm = st4 ? ln_m : 0.f;
+    const int half = l >> 1;                                       // complex entries of the packed row (even)
+
+    for (int j = tid; j < Cfg::NTW0; j += NT) {
+        const float2 a = tw[4 * j], bb = tw[2 * j];
+        twAr[j] = a.x;
+        twAi[j] = a.y;
+        twBr[j] = bb.x;
+        twBi[j] = bb.y;
+    }
+    {
+        int o = 0;
+#pragma unroll
+        for (int P = 1; P <= NP - 2; ++P) {                        // W_{S_P}^j = W_n^{j 2^(2 + 4P)}
+            const int subP = Mh >> (4 * P + 4);
+            for (int j = tid; j < subP; j += NT) {
+                const float2 a = tw[j << (2 + 4 * P)];
+                midr[o + j] = a.x;
+                midi[o + j] = a.y;
+            }
+            o += subP;
+        }
+    }
+    __syncthreads();
+
+    const int j0 = 2 * tid;                                         // outer-pass butterflies j0, j0 + 1
+    const int pb0 = padf(j0);
+
+#pragma unroll 1
+    for (int odd = 0; odd < 2; ++odd) {
+        // ---- outer forward pass, fused with the prologue: packed inputs i = j + p sub0 (+1 in lane 1), p < 16
+        {
+            C2 xx[16];
+#pragma unroll
+            for (int hb = 0; hb < 4; ++hb) {                        // batches of 4 bound the registers in flight
+                float4 xv[4], sa[4], sb[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int i = j0 + ((4 * hb + p) << log2sub0);
+                    xv[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    sa[p] = make_float4(0.f, 1.f, 0.f, 1.f);
+                    sb[p] = sa[p];
+                    if (i < half) {
+                        xv[p] = __ldg(xr4 + (i >> 1));
+                        if (st4) {
+                            sa[p] = __ldg(st4 + i);
+                            sb[p] = __ldg(st4 + i + 1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int i = j0 + ((4 * hb + p) << log2sub0);
+                    const float add = (i < half) ? pt : 0.f;
+                    const float y0 = (lns * sa[p].y) * (xv[p].x - sa[p].x + lnm) + add;
+                    const float y1 = (lns * sa[p].w) * (xv[p].y - sa[p].z + lnm) + add;
+                    const float y2 = (lns * sb[p].y) * (xv[p].z - sb[p].x + lnm) + add;
+                    const float y3 = (lns * sb[p].w) * (xv[p].w - sb[p].z + lnm) + add;
+                    const bool in = i < half;
+                    xx[4 * hb + p].x = V2(in ? y0 : 0.f, in ? y2 : 0.f);
+                    xx[4 * hb + p].y = V2(in ? y1 : 0.f, in ? y3 : 0.f);
+                }
+            }
+            if (odd) s2::rotate_w32<false>(xx);
+            s2::RadixS<16, false>::run(xx);
+            C2 v, u0;
+            v.x = ld2(twAr + j0);
+            v.y = ld2(twAi + j0);
+            u0.x = odd ? ld2(twBr + j0) : V2(1.f);
+            u0.y = odd ? ld2(twBi + j0) : V2(0.f);
+            s2::apply_twiddles16<true>(xx, u0, v);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int c = fft_brev(q, 4), o = c * sub0 + 2 * ((c * sub0) >> 5);
+                st2(re + pb0 + o, xx[q].x);
+                st2(im + pb0 + o, xx[q].y);
+            }
+        }
+        __syncthreads();
+
+        mid_passes<LH, false, 1, NP - 2, 0>(re, im, midr, midi, tid);
+
+        // ---- centre (scalar): last forward pass + untangle/product/re-tangle + first inverse pass
+        {
+            constexpr int R = 1 << RL, G = Mh / R, NITEM = Mh / (2 * R);
+            const float4 *kh = odd ? kcr + (Mh + 2) : kcr;          // odd half: entries Mh/2 + 1 ...
+            auto partner = [&](int ga) {
+                return odd ? (ga ^ (G - 1)) : (ga == 0 ? 1 : ga ^ ((1 << (31 - __clz(ga))) - 1));
+            };
+            auto load_coef = [&](int item, float4 (&ca)[R], float4 (&cb)[R]) {
+                const float4 *ka = kh + (size_t)R * (2 * item), *kb = kh + (size_t)R * partner(2 * item);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    ca[i] = __ldg(ka + i);
+                    cb[i] = __ldg(kb + i);
+                }
+            };
+            constexpr bool PF = R <= 4;                            // next item's coefficients in flight (register budget)
+            float4 ca[R], cb[R];
+            if (PF) load_coef(tid, ca, cb);
+#pragma unroll 1
+            for (int item = tid; item < NITEM; item += NT) {
+                if (!PF) load_coef(item, ca, cb);
+                const int ga = 2 * item, gb = partner(ga);
+                const int pa = padf(R * ga), pg = padf(R * gb);
+                float2 xa[R], xb[R];
+#pragma unroll
+                for (int k = 0; k < R / 2; ++k) {
+                    const float2 ar = *reinterpret_cast<const float2 *>(re + pa + 2 * k);
+                    const float2 ai = *reinterpret_cast<const float2 *>(im + pa + 2 * k);
+                    const float2 br = *reinterpret_cast<const float2 *>(re + pg + 2 * k);
+                    const float2 bi = *reinterpret_cast<const float2 *>(im + pg + 2 * k);
+                    xa[2 * k] = make_float2(ar.x, ai.x);
+                    xa[2 * k + 1] = make_float2(ar.y, ai.y);
+                    xb[2 * k] = make_float2(br.x, bi.x);
+                    xb[2 * k + 1] = make_float2(br.y, bi.y);
+                }
+                float4 na[PF ? R : 1], nb[PF ? R : 1];
+                if constexpr (PF) {
+                    if (item + NT < NITEM) load_coef(item + NT, na, nb);
+                }
+                Radix<R, false>::run(xa);
+                Radix<R, false>::run(xb);
+                if (!odd && item == 0) {
+                    const float4 s0 = __ldg(kcr + Mh), s1 = __ldg(kcr + Mh + 1);
+                    {
+                        const float2 a = xa[0];
+                        const float p0 = 2.f * (a.x + a.y) * ca[0].x, pM = 2.f * (a.x - a.y) * ca[0].y;
+                        xa[0] = make_float2(p0 + pM, p0 - pM);
+                        float2 d = xa[R / 2];
+                        pair_map(xa[R / 2], d, s0, s1);
+                    }
+#pragma unroll
+                    for (int c = 2; c < R; c += 2) {
+                        int msb = 0;
+                        while ((2 << msb) <= c) ++msb;
+                        const int c2 = c ^ ((1 << msb) - 1);
+                        pair_map(xa[fft_brev(c, RL)], xa[fft_brev(c2, RL)], ca[c], ca[c + 1]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < R / 2; ++q) {
+                        const int e = fft_brev(q, RL) >> 1;
+                        pair_map(xb[q], xb[q ^ (R - 1)], cb[2 * e], cb[2 * e + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < R / 2; ++q) {
+                        const int e = fft_brev(q, RL) >> 1;
+                        pair_map(xa[q], xb[q ^ (R - 1)], ca[2 * e], ca[2 * e + 1]);
+                        pair_map(xb[q], xa[q ^ (R - 1)], cb[2 * e], cb[2 * e + 1]);
+                    }
+                }
+                Radix<R, true>::run(xa);
+                Radix<R, true>::run(xb);
+#pragma unroll
+                for (int k = 0; k < R / 2; ++k) {
+                    *reinterpret_cast<float2 *>(re + pa + 2 * k) = make_float2(xa[2 * k].x, xa[2 * k + 1].x);
+                    *reinterpret_cast<float2 *>(im + pa + 2 * k) = make_float2(xa[2 * k].y, xa[2 * k + 1].y);
+                    *reinterpret_cast<float2 *>(re + pg + 2 * k) = make_float2(xb[2 * k].x, xb[2 * k + 1].x);
+                    *reinterpret_cast<float2 *>(im + pg + 2 * k) = make_float2(xb[2 * k].y, xb[2 * k + 1].y);
+                }
+                if constexpr (PF) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        ca[i] = na[i];
+                        cb[i] = nb[i];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        mid_passes<LH, true, 1, NP - 2, 0>(re, im, midr, midi, tid);
+
+        // ---- outer inverse pass + epilogue.  even half: park a[i] in the output row as (re_i, re_i+1, im_i, im_i+1);
+        //      odd half: read it back (same thread, same addresses), add W_M^{-i} b[i], GELU, store y[2i .. 2i+3]
+        {
+            C2 xx[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int c = fft_brev(q, 4), o = c * sub0 + 2 * ((c * sub0) >> 5);
+                xx[q].x = ld2(re + pb0 + o);
+                xx[q].y = ld2(im + pb0 + o);
+            }
+            C2 v, u0;
+            v.x = ld2(twAr + j0);
+            v.y = -ld2(twAi + j0);
+            u0.x = odd ? ld2(twBr + j0) : V2(1.f);
+            u0.y = odd ? -ld2(twBi + j0) : V2(0.f);
+            s2::apply_twiddles16<true>(xx, u0, v);
+            s2::RadixS<16, true>::run(xx);
+            if (odd) {
+                s2::rotate_w32<true>(xx);
+#pragma unroll
+                for (int p = 0; p < 16; ++p) {
+                    const int i = j0 + (p << log2sub0);
+                    if (i < half) {
+                        float4 *dst = reinterpret_cast<float4 *>(gr + 2 * i);
+                        const float4 a = *dst;
+                        const V2 r = gelu_fast2(xx[p].x + V2(a.x, a.y)), q = gelu_fast2(xx[p].y + V2(a.z, a.w));
+                        *dst = make_float4(r.v.x, q.v.x, r.v.y, q.v.y);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < 16; ++p) {
+                    const int i = j0 + (p << log2sub0);
+                    if (i < half)
+                        *reinterpret_cast<float4 *>(gr + 2 * i) =
+                            make_float4(xx[p].x.v.x, xx[p].x.v.y, xx[p].y.v.x, xx[p].y.v.y);
+                }
+            }
+        }
+        __syncthreads();          // the next half overwrites the planes
+    }
+}
+
+template <int LOG2M>
+static int launch_fftconv3(const float *x, const float *stats, const float *part_t, long long psb, float ln_m,
+                           float ln_s, const float *kc, const float2 *tw, float *g, int B, int H, int l, cudaStream_t st) {
+    using Cfg = Fft3Cfg<LOG2M>;
+    static bool attr_set[16] = {};
+    int dev = 0;
+    DWB_CUDA(cudaGetDevice(&dev));
+    if (Cfg::SMEM > 48 * 1024 && !attr_set[dev & 15]) {
+        DWB_CUDA(cudaFuncSetAttribute(fftconv3_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_set[dev & 15] = true;
+    }
+    fftconv3_kernel<LOG2M><<<B * H, Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw, g, B, H, l);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+bool fftconv3_supported(int lg, const float *x, const float *stats, const float *g, int l) {
+    const uintptr_t a = (uintptr_t)x | (uintptr_t)stats | (uintptr_t)g;
+    return (lg == 12 || lg == 14) && (l % 4) == 0 && (a & 15) == 0;
+}
+
+int fftconv3_launch(int lg, const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
+                    const float *kc, const float2 *tw, float *g, int B, int H, int l, cudaStream_t st) {
+    switch (lg) {
+        case 12: return launch_fftconv3<12>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+        case 14: return launch_fftconv3<14>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+    }
+    set_error("fftconv3: no kernel for log2M=%d", lg);
+    return DWB_ERR_UNSUPPORTED;
+}
+
+}  // namespace dwb

@@ -225,7 +225,11 @@ kf_kernel(const T *__restrict__ k /* (2,H,l) */, const float *__restrict__ D /* 
 //   Z'[k]   = alpha a + beta conj(b),   Z'[M-k] = conj(gamma a + delta conj(b))
 //   alpha = K1 |u|^2 + conj(K2) |v|^2      beta  = K1 v conj(u) + conj(K2) u conj(v)
 //   gamma = K1 u conj(v) + conj(K2) v conj(u)   delta = K1 |v|^2 + conj(K2) |u|^2,   K1 = K'[k], K2 = K'[M-k]
-__global__ void kcoef_kernel(const double2 *__restrict__ Kd, int log2M, float *__restrict__ kc) {
+// v2 (split transform, fft_use_v2): the same maps regrouped per half transform of size Mh = M/2, slots p' =
+// bit reversal of k' over log2M - 1 bits: entries [0, Mh/2] pair the even frequencies k = 2k' (e = 0: DC/Nyquist,
+// e = Mh/2: slot 1 = the self-paired k = M/2, else leader slot 2e); entries Mh/2 + 1 + e pair the odd
+// frequencies k = 2k' + 1 (leader slot 2e, partner slot = complement).  Same size, M/2 + 1 entries.
+__global__ void kcoef_kernel(const double2 *__restrict__ Kd, int log2M, int split, float *__restrict__ kc) {
     const int M = 1 << log2M, n = 2 * M;
     const int e = blockIdx.x * blockDim.x + threadIdx.x, h = blockIdx.y;
     if (e > M / 2) return;
@@ -237,8 +241,19 @@ __global__ void kcoef_kernel(const double2 *__restrict__ Kd, int log2M, float *_
         for (int i = 2; i < 8; ++i) o[i] = 0.f;
         return;
     }
-    const int p = (e == M / 2) ? 1 : 2 * e;
-    const int k = fft_freq(p, log2M);
+    int k;
+    if (!split) {
+        const int p = (e == M / 2) ? 1 : 2 * e;
+        k = fft_freq(p, log2M);
+    } else {
+        const int Mh = M / 2;
+        if (e <= Mh / 2) {
+            const int p = (e == Mh / 2) ? 1 : 2 * e;
+            k = 2 * fft_freq(p, log2M - 1);
+        } else {
+            k = 2 * fft_freq(2 * (e - Mh / 2 - 1), log2M - 1) + 1;
+        }
+    }
     const double2 K1 = K[k], K2 = make_double2(K[M - k].x, -K[M - k].y);      // K2 = conj(K'[M-k])
     double ws, wc;
     sincospi(-2.0 * (double)k / (double)n, &ws, &wc);
@@ -268,7 +283,7 @@ static int fftconv_prepare_any(const T *k, const float *D, int H, int l, float *
     kf_kernel<T><<<dim3(ceil_div(M + 1, DFT_THREADS), H), DFT_THREADS, 0, st>>>(k, D, H, l, log2M, Kd);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
-        kcoef_kernel<<<dim3(ceil_div(M / 2 + 1, 256), H), 256, 0, st>>>(Kd, log2M, kc);
+        kcoef_kernel<<<dim3(ceil_div(M / 2 + 1, 256), H), 256, 0, st>>>(Kd, log2M, fft_use_v2(log2M) ? 1 : 0, kc);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
