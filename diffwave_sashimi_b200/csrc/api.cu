@@ -575,7 +575,7 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
         for (auto &o : p->ops) {
             if (o.kind == OP_BLOCK) {
                 TRY(fftconv_launch(p->bufs[o.in_buf], p->stat_bufs[o.in_buf], part + o.part_off, psb, o.ln1_m, o.ln1_s,
-                                   o.kf, p->g_buf, B, o.H, o.l, st));
+                                   o.kf, p->g_buf, B, o.H, o.l, st, p->bufs[o.out_buf]));   // the block's output buffer is free scratch here
                 PROF(DWB_PROF_FFTCONV0 + std::min(stage_of(p, o.l), 3));
                 MixArgs a{};
                 a.g = p->g_buf; a.x = p->bufs[o.in_buf];

@@ -643,7 +643,7 @@ static int launch_fftconv2(const float *x, const float *stats, const float *part
 }
 
 int fftconv_launch(const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
-                   const float *kc, float *g, int B, int H, int l, cudaStream_t st) {
+                   const float *kc, float *g, int B, int H, int l, cudaStream_t st, float *scratch) {
     const int lg = fft_log2m_for(l);
     DWB_REQUIRE(lg > 0, DWB_ERR_UNSUPPORTED, "fftconv: stage length %d unsupported (max %d)", l, 1 << FFT_MAX_LOG2M);
     const float2 *tw;
@@ -651,7 +651,7 @@ int fftconv_launch(const float *x, const float *stats, const float *part_t, long
     if (rc != DWB_OK) return rc;
     if (fft_use_v2(lg)) {
         if (fft_forced_variant() != 2 && fftconv3_supported(lg, x, stats, g, l))
-            return fftconv3_launch(lg, x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+            return fftconv3_launch(lg, x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, scratch, B, H, l, st);
         switch (lg) {
             case 10: return launch_fftconv2<10>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
             case 11: return launch_fftconv2<11>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
@@ -673,10 +673,39 @@ int fftconv_launch(const float *x, const float *stats, const float *part_t, long
 
 }  // namespace dwb
 
+// scratch row store for the standalone op (the plan passes the block's still-unused output buffer instead):
+// grown on demand per device, never during stream capture (then the kernel simply re-reads its input)
+static float *op_scratch(size_t floats, cudaStream_t st) {
+    static std::mutex mu;
+    static float *buf[16] = {};
+    static size_t cap[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cap[dev] < floats) {
+        if (buf[dev]) {
+            cudaDeviceSynchronize();
+            cudaFree(buf[dev]);
+        }
+        buf[dev] = nullptr;
+        cap[dev] = 0;
+        if (cudaMalloc(&buf[dev], floats * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        cap[dev] = floats;
+    }
+    return buf[dev];
+}
+
 extern "C" int dwb_fftconv(const float *x, const float *stats, const float *part_t, int64_t part_stride_b, float ln_m,
                            float ln_s, const float *kf, float *g, int B, int H, int l, void *stream) {
     DWB_REQUIRE(x && kf && g, DWB_ERR_INVALID, "dwb_fftconv: null pointer");
     DWB_REQUIRE(B >= 1 && H >= 1 && l >= 1, DWB_ERR_INVALID, "dwb_fftconv: bad sizes B=%d H=%d l=%d", B, H, l);
+    float *scratch = nullptr;
+    if (dwb::fft_use_v2(dwb::fft_log2m_for(l))) scratch = op_scratch((size_t)B * H * l, (cudaStream_t)stream);
     return dwb::fftconv_launch(x, stats, part_t, (long long)part_stride_b, ln_m, ln_s, kf, g, B, H, l,
-                               (cudaStream_t)stream);
+                               (cudaStream_t)stream, scratch);
 }

@@ -46,6 +46,7 @@ struct Fft3Cfg {
     static_assert(RL >= 1 && RL <= 3 && NP >= 3 && NT >= 32, "v3 plan");
 };
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ V2 ld2(const float *p) { return V2(*reinterpret_cast<const float2 *>(p)); }
 __device__ __forceinline__ void st2(float *p, const V2 &a) { *reinterpret_cast<float2 *>(p) = a.v; }
 
@@ -136,7 +137,7 @@ template <int LOG2M>
 __global__ void __launch_bounds__(Fft3Cfg<LOG2M>::NT, Fft3Cfg<LOG2M>::MINB)
 fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
                 long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
-                const float2 *__restrict__ tw /* W_n^i, i < M */, float *g, int B, int H, int l) {
+                const float2 *__restrict__ tw /* W_n^i, i < M */, float *g, float *scratch, int B, int H, int l, int resident) {
     using Cfg = Fft3Cfg<LOG2M>;
     constexpr int LH = Cfg::LH, Mh = Cfg::Mh, NT = Cfg::NT, NP = Cfg::NP, RL = Cfg::RL;
     constexpr int log2sub0 = LH - 4, sub0 = 1 << log2sub0;         // outer pass: radix 16, span Mh
@@ -151,6 +152,7 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
     const size_t off = ((size_t)b * H + h) * (size_t)l;
     const float4 *xr4 = reinterpret_cast<const float4 *>(x + off);
     float *gr = g + off;
+    float *ys = scratch ? scratch + off : nullptr;               // parks the LN-applied input for the odd half
     const float pt = part_t ? part_t[(size_t)b * part_stride_b + h] : 0.f;
     const float4 *st4 = stats ? reinterpret_cast<const float4 *>(stats + (size_t)b * l * 2) : nullptr;
     const float4 *kcr = kc + (size_t)h * (2 * Mh + 2);             // (Mh + 1) entries of two float4
@@ -184,37 +186,60 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
 
 #pragma unroll 1
     for (int odd = 0; odd < 2; ++odd) {
+        if (odd) {
+            // warm L2 with the input row of the CTA that will run two waves from now (rows are dispatched in
+            // order, two per SM): its outer pass then waits for L2 instead of HBM
+            const int nrow = row + resident;
+            if (nrow < B * H) {
+                const int nh = nrow / B, nb = nrow - nh * B;
+                const char *nx = reinterpret_cast<const char *>(x + ((size_t)nb * H + nh) * (size_t)l);
+                for (int o = tid * 128; o < l * 4; o += NT * 128) prefetch_l2(nx + o);
+            }
+        }
         // ---- outer forward pass, fused with the prologue: packed inputs i = j + p sub0 (+1 in lane 1), p < 16
         {
             C2 xx[16];
+            if (odd && ys) {
+                // the even half parked y as (re_i, re_i+1, im_i, im_i+1): one round trip, no statistics, no LN
 #pragma unroll
-            for (int hb = 0; hb < 4; ++hb) {                        // batches of 4 bound the registers in flight
-                float4 xv[4], sa[4], sb[4];
+                for (int p = 0; p < 16; ++p) {
+                    const int i = j0 + (p << log2sub0);
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < half) a = *reinterpret_cast<const float4 *>(ys + 2 * i);
+                    xx[p].x = V2(a.x, a.y);
+                    xx[p].y = V2(a.z, a.w);
+                }
+            } else {
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const int i = j0 + ((4 * hb + p) << log2sub0);
-                    xv[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    sa[p] = make_float4(0.f, 1.f, 0.f, 1.f);
-                    sb[p] = sa[p];
-                    if (i < half) {
-                        xv[p] = __ldg(xr4 + (i >> 1));
-                        if (st4) {
-                            sa[p] = __ldg(st4 + i);
-                            sb[p] = __ldg(st4 + i + 1);
+                for (int hb = 0; hb < 4; ++hb) {                    // batches of 4 bound the registers in flight
+                    float4 xv[4], sa[4], sb[4];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const int i = j0 + ((4 * hb + p) << log2sub0);
+                        xv[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        sa[p] = make_float4(0.f, 1.f, 0.f, 1.f);
+                        sb[p] = sa[p];
+                        if (i < half) {
+                            xv[p] = __ldg(xr4 + (i >> 1));
+                            if (st4) {
+                                sa[p] = __ldg(st4 + i);
+                                sb[p] = __ldg(st4 + i + 1);
+                            }
                         }
                     }
-                }
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const int i = j0 + ((4 * hb + p) << log2sub0);
-                    const float add = (i < half) ? pt : 0.f;
-                    const float y0 = (lns * sa[p].y) * (xv[p].x - sa[p].x + lnm) + add;
-                    const float y1 = (lns * sa[p].w) * (xv[p].y - sa[p].z + lnm) + add;
-                    const float y2 = (lns * sb[p].y) * (xv[p].z - sb[p].x + lnm) + add;
-                    const float y3 = (lns * sb[p].w) * (xv[p].w - sb[p].z + lnm) + add;
-                    const bool in = i < half;
-                    xx[4 * hb + p].x = V2(in ? y0 : 0.f, in ? y2 : 0.f);
-                    xx[4 * hb + p].y = V2(in ? y1 : 0.f, in ? y3 : 0.f);
+                    for (int p = 0; p < 4; ++p) {
+                        const int i = j0 + ((4 * hb + p) << log2sub0);
+                        const bool in = i < half;
+                        const float add = in ? pt : 0.f;
+                        const float y0 = (lns * sa[p].y) * (xv[p].x - sa[p].x + lnm) + add;
+                        const float y1 = (lns * sa[p].w) * (xv[p].y - sa[p].z + lnm) + add;
+                        const float y2 = (lns * sb[p].y) * (xv[p].z - sb[p].x + lnm) + add;
+                        const float y3 = (lns * sb[p].w) * (xv[p].w - sb[p].z + lnm) + add;
+                        xx[4 * hb + p].x = V2(in ? y0 : 0.f, in ? y2 : 0.f);
+                        xx[4 * hb + p].y = V2(in ? y1 : 0.f, in ? y3 : 0.f);
+                        if (!odd && ys && in) *reinterpret_cast<float4 *>(ys + 2 * i) = make_float4(y0, y2, y1, y3);
+                    }
                 }
             }
             if (odd) s2::rotate_w32<false>(xx);
@@ -251,75 +276,71 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
                     cb[i] = __ldg(kb + i);
                 }
             };
-            constexpr bool PF = R <= 4;                            // next item's coefficients in flight (register budget)
-            float4 ca[R], cb[R];
-            if (PF) load_coef(tid, ca, cb);
+            // coefficients come from L2 (16 B per point, shared by the rows of a channel): GRP items' worth (64
+            // registers) are requested at once, so a thread exposes IPT / GRP round trips instead of IPT
+            constexpr int IPT = NITEM / NT, GRP = 8 / R;
+            static_assert(IPT % GRP == 0, "centre grouping");
 #pragma unroll 1
-            for (int item = tid; item < NITEM; item += NT) {
-                if (!PF) load_coef(item, ca, cb);
-                const int ga = 2 * item, gb = partner(ga);
-                const int pa = padf(R * ga), pg = padf(R * gb);
-                float2 xa[R], xb[R];
+            for (int k0 = 0; k0 < IPT; k0 += GRP) {
+                float4 ca[GRP][R], cb[GRP][R];
 #pragma unroll
-                for (int k = 0; k < R / 2; ++k) {
-                    const float2 ar = *reinterpret_cast<const float2 *>(re + pa + 2 * k);
-                    const float2 ai = *reinterpret_cast<const float2 *>(im + pa + 2 * k);
-                    const float2 br = *reinterpret_cast<const float2 *>(re + pg + 2 * k);
-                    const float2 bi = *reinterpret_cast<const float2 *>(im + pg + 2 * k);
-                    xa[2 * k] = make_float2(ar.x, ai.x);
-                    xa[2 * k + 1] = make_float2(ar.y, ai.y);
-                    xb[2 * k] = make_float2(br.x, bi.x);
-                    xb[2 * k + 1] = make_float2(br.y, bi.y);
-                }
-                float4 na[PF ? R : 1], nb[PF ? R : 1];
-                if constexpr (PF) {
-                    if (item + NT < NITEM) load_coef(item + NT, na, nb);
-                }
-                Radix<R, false>::run(xa);
-                Radix<R, false>::run(xb);
-                if (!odd && item == 0) {
-                    const float4 s0 = __ldg(kcr + Mh), s1 = __ldg(kcr + Mh + 1);
-                    {
-                        const float2 a = xa[0];
-                        const float p0 = 2.f * (a.x + a.y) * ca[0].x, pM = 2.f * (a.x - a.y) * ca[0].y;
-                        xa[0] = make_float2(p0 + pM, p0 - pM);
-                        float2 d = xa[R / 2];
-                        pair_map(xa[R / 2], d, s0, s1);
+                for (int u = 0; u < GRP; ++u) load_coef(tid + (k0 + u) * NT, ca[u], cb[u]);
+#pragma unroll
+                for (int u = 0; u < GRP; ++u) {
+                    const int item = tid + (k0 + u) * NT;
+                    const int ga = 2 * item, gb = partner(ga);
+                    const int pa = padf(R * ga), pg = padf(R * gb);
+                    float2 xa[R], xb[R];
+#pragma unroll
+                    for (int k = 0; k < R / 2; ++k) {
+                        const float2 ar = *reinterpret_cast<const float2 *>(re + pa + 2 * k);
+                        const float2 ai = *reinterpret_cast<const float2 *>(im + pa + 2 * k);
+                        const float2 br = *reinterpret_cast<const float2 *>(re + pg + 2 * k);
+                        const float2 bi = *reinterpret_cast<const float2 *>(im + pg + 2 * k);
+                        xa[2 * k] = make_float2(ar.x, ai.x);
+                        xa[2 * k + 1] = make_float2(ar.y, ai.y);
+                        xb[2 * k] = make_float2(br.x, bi.x);
+                        xb[2 * k + 1] = make_float2(br.y, bi.y);
                     }
+                    Radix<R, false>::run(xa);
+                    Radix<R, false>::run(xb);
+                    if (!odd && item == 0) {
+                        const float4 s0 = __ldg(kcr + Mh), s1 = __ldg(kcr + Mh + 1);
+                        {
+                            const float2 a = xa[0];
+                            const float p0 = 2.f * (a.x + a.y) * ca[u][0].x, pM = 2.f * (a.x - a.y) * ca[u][0].y;
+                            xa[0] = make_float2(p0 + pM, p0 - pM);
+                            float2 d = xa[R / 2];
+                            pair_map(xa[R / 2], d, s0, s1);
+                        }
 #pragma unroll
-                    for (int c = 2; c < R; c += 2) {
-                        int msb = 0;
-                        while ((2 << msb) <= c) ++msb;
-                        const int c2 = c ^ ((1 << msb) - 1);
-                        pair_map(xa[fft_brev(c, RL)], xa[fft_brev(c2, RL)], ca[c], ca[c + 1]);
+                        for (int c = 2; c < R; c += 2) {
+                            int msb = 0;
+                            while ((2 << msb) <= c) ++msb;
+                            const int c2 = c ^ ((1 << msb) - 1);
+                            pair_map(xa[fft_brev(c, RL)], xa[fft_brev(c2, RL)], ca[u][c], ca[u][c + 1]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < R / 2; ++q) {
+                            const int e = fft_brev(q, RL) >> 1;
+                            pair_map(xb[q], xb[q ^ (R - 1)], cb[u][2 * e], cb[u][2 * e + 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < R / 2; ++q) {
+                            const int e = fft_brev(q, RL) >> 1;
+                            pair_map(xa[q], xb[q ^ (R - 1)], ca[u][2 * e], ca[u][2 * e + 1]);
+                            pair_map(xb[q], xa[q ^ (R - 1)], cb[u][2 * e], cb[u][2 * e + 1]);
+                        }
                     }
+                    Radix<R, true>::run(xa);
+                    Radix<R, true>::run(xb);
 #pragma unroll
-                    for (int q = 0; q < R / 2; ++q) {
-                        const int e = fft_brev(q, RL) >> 1;
-                        pair_map(xb[q], xb[q ^ (R - 1)], cb[2 * e], cb[2 * e + 1]);
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < R / 2; ++q) {
-                        const int e = fft_brev(q, RL) >> 1;
-                        pair_map(xa[q], xb[q ^ (R - 1)], ca[2 * e], ca[2 * e + 1]);
-                        pair_map(xb[q], xa[q ^ (R - 1)], cb[2 * e], cb[2 * e + 1]);
-                    }
-                }
-                Radix<R, true>::run(xa);
-                Radix<R, true>::run(xb);
-#pragma unroll
-                for (int k = 0; k < R / 2; ++k) {
-                    *reinterpret_cast<float2 *>(re + pa + 2 * k) = make_float2(xa[2 * k].x, xa[2 * k + 1].x);
-                    *reinterpret_cast<float2 *>(im + pa + 2 * k) = make_float2(xa[2 * k].y, xa[2 * k + 1].y);
-                    *reinterpret_cast<float2 *>(re + pg + 2 * k) = make_float2(xb[2 * k].x, xb[2 * k + 1].x);
-                    *reinterpret_cast<float2 *>(im + pg + 2 * k) = make_float2(xb[2 * k].y, xb[2 * k + 1].y);
-                }
-                if constexpr (PF) {
-#pragma unroll
-                    for (int i = 0; i < R; ++i) {
-                        ca[i] = na[i];
-                        cb[i] = nb[i];
+                    for (int k = 0; k < R / 2; ++k) {
+                        *reinterpret_cast<float2 *>(re + pa + 2 * k) = make_float2(xa[2 * k].x, xa[2 * k + 1].x);
+                        *reinterpret_cast<float2 *>(im + pa + 2 * k) = make_float2(xa[2 * k].y, xa[2 * k + 1].y);
+                        *reinterpret_cast<float2 *>(re + pg + 2 * k) = make_float2(xb[2 * k].x, xb[2 * k + 1].x);
+                        *reinterpret_cast<float2 *>(im + pg + 2 * k) = make_float2(xb[2 * k].y, xb[2 * k + 1].y);
                     }
                 }
             }
@@ -373,7 +394,8 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
 
 template <int LOG2M>
 static int launch_fftconv3(const float *x, const float *stats, const float *part_t, long long psb, float ln_m,
-                           float ln_s, const float *kc, const float2 *tw, float *g, int B, int H, int l, cudaStream_t st) {
+                           float ln_s, const float *kc, const float2 *tw, float *g, float *scratch, int B, int H, int l,
+                           cudaStream_t st) {
     using Cfg = Fft3Cfg<LOG2M>;
     static bool attr_set[16] = {};
     int dev = 0;
@@ -382,7 +404,10 @@ static int launch_fftconv3(const float *x, const float *stats, const float *part
         DWB_CUDA(cudaFuncSetAttribute(fftconv3_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_set[dev & 15] = true;
     }
-    fftconv3_kernel<LOG2M><<<B * H, Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw, g, B, H, l);
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    fftconv3_kernel<LOG2M><<<dim3(B * H, 1, 1), Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw, g,
+                                                                        scratch, B, H, l, nsm * Cfg::MINB);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
 }
@@ -393,10 +418,11 @@ bool fftconv3_supported(int lg, const float *x, const float *stats, const float 
 }
 
 int fftconv3_launch(int lg, const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
-                    const float *kc, const float2 *tw, float *g, int B, int H, int l, cudaStream_t st) {
+                    const float *kc, const float2 *tw, float *g, float *scratch, int B, int H, int l, cudaStream_t st) {
+    if (((uintptr_t)scratch & 15) != 0) scratch = nullptr;
     switch (lg) {
-        case 12: return launch_fftconv3<12>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
-        case 14: return launch_fftconv3<14>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+        case 12: return launch_fftconv3<12>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, scratch, B, H, l, st);
+        case 14: return launch_fftconv3<14>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, scratch, B, H, l, st);
     }
     set_error("fftconv3: no kernel for log2M=%d", lg);
     return DWB_ERR_UNSUPPORTED;
