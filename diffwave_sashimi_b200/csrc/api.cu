@@ -110,6 +110,7 @@ struct dwb_plan {
     // input conv / head
     float *init_w = nullptr, *init_b = nullptr;
     float *Wf_t = nullptr, *bf = nullptr, *wz = nullptr;
+    uint4 *Wf_f[2] = {nullptr, nullptr};      // split-bf16 A fragments of the head's C -> C weight
     float bz = 0.f, norm_m = 0.f, norm_s = 1.f;
     int headC = 0;
 
@@ -295,6 +296,15 @@ static int finalize_head(dwb_plan *p, int C, cudaStream_t st) {
     TRY(need(p, "final_conv.2.conv.weight", C, &t)); p->wz = (float *)t->dev;
     TRY(scalar_of(p, "final_conv.2.conv.bias", &p->bz, st));
     p->headC = C;
+    if (p->use_mma && C % 16 == 0) {
+        for (int q = 0; q < 2; ++q) {
+            void *d;
+            TRY(dev_alloc(p, (size_t)C * C * 2, &d));
+            p->Wf_f[q] = (uint4 *)d;
+        }
+        TRY(frag_pack(p->Wf_t, C, C, (uint32_t *)p->Wf_f[0], (uint32_t *)p->Wf_f[1], st));
+        p->launches += 1;
+    }
     return DWB_OK;
 }
 
@@ -643,7 +653,9 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
     h.Wf_t = p->Wf_t; h.bf = p->bf; h.wz = p->wz; h.bz = p->bz;
     h.out = out; h.l = L;
     if (upd) { h.upd_x = upd->x; h.noise = upd->noise; h.c1 = upd->c1; h.sqrt_alpha = upd->sqrt_alpha; h.sigma = upd->sigma; }
-    TRY(head_launch(h, B, st));
+    h.Wf_fh = p->Wf_f[0]; h.Wf_fl = p->Wf_f[1];
+    if (h.Wf_fh) TRY(head_mma_launch(h, B, st));
+    else TRY(head_launch(h, B, st));
     p->launches += 1;
     PROF(DWB_PROF_HEAD);
     return DWB_OK;

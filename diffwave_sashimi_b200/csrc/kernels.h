@@ -38,6 +38,7 @@ struct HeadArgs {
     const float *stats;            // (B,l,2) or null (no LN)
     float ln_m, ln_s, prescale;
     const float *Wf_t, *bf;        // [C][C], (C)
+    const uint4 *Wf_fh, *Wf_fl;    // split-bf16 A fragments of Wf (frag_pack) or null -> fp32 SIMT kernel
     const float *wz;               // (C)
     float bz;
     // optional fused DDPM update: out = (upd_x - c1 eps)/sqrt_alpha (+ sigma noise)
@@ -84,6 +85,7 @@ int frag_pack(const float *Wt, int M, int K, uint32_t *fhi, uint32_t *flo, cudaS
 int down_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
 int up_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
 int head_launch(const HeadArgs &a, int B, cudaStream_t st);
+int head_mma_launch(const HeadArgs &a, int B, cudaStream_t st);
 int wave_block_launch(const WaveBlockArgs &a, int B, cudaStream_t st);
 bool wave_mma_supported(int C, int S);
 int wave_block_mma_launch(const WaveBlockArgs &a, int B, cudaStream_t st);

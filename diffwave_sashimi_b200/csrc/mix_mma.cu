@@ -373,13 +373,99 @@ bool pool_mma_supported(int Hi, int Ho, int s, bool up) {
     return (Hi * s) % 16 == 0 && Ho % 16 == 0;
 }
 
-template <typename KernelT>
-static int launch_pool(KernelT k, const PoolArgs &a, dim3 grid, size_t sm, cudaStream_t st) {
+template <typename KernelT, typename ArgsT>
+static int launch_pool(KernelT k, const ArgsT &a, dim3 grid, size_t sm, cudaStream_t st) {
     DWB_REQUIRE(sm <= 227 * 1024, DWB_ERR_UNSUPPORTED, "pool tile needs %zu B of shared memory", sm);
     if (sm > 48 * 1024) DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k<<<grid, MIX_THREADS, sm, st>>>(a);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// output head on the same path: final LN, C -> C + ReLU, C -> 1, optional DDPM update
+// (models/sashimi.py:310-311, models/wavenet.py:198-208, generate.py:52-54)
+// 8 warps = 4 m-tile groups x 2 column halves; eps[t] = bz + sum_m wz[m] relu((Wf y)[m][t] + bf[m])
+// ---------------------------------------------------------------------------------------
+template <int TT>
+__global__ void __launch_bounds__(MIX_THREADS)
+head_mma_kernel(HeadArgs a) {
+    constexpr int TTP = TT + 8, NT = TT / 16;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int C = a.C, l = a.l;
+    __nv_bfloat16 *Bhi = reinterpret_cast<__nv_bfloat16 *>(smraw);                 // [C][TTP]
+    __nv_bfloat16 *Blo = Bhi + (size_t)C * TTP;
+    float *red = reinterpret_cast<float *>(Blo + (size_t)C * TTP);                  // [4][TT]
+    float *sc = red + 4 * TT, *sh = sc + TT;                                        // LN scale / shift per column
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    if (tid < TT) {
+        float s = a.prescale, h = 0.f;
+        if (a.stats && t0 + tid < l) {
+            const float2 ms = *reinterpret_cast<const float2 *>(a.stats + ((size_t)b * l + t0 + tid) * 2);
+            s = a.ln_s * ms.y * a.prescale;          // v = (ln_s rstd)(x - mean + ln_m) prescale
+            h = (a.ln_m - ms.x) * s;
+        }
+        sc[tid] = s;
+        sh[tid] = h;
+    }
+    __syncthreads();
+    for (int i = tid; i < C * TT; i += MIX_THREADS) {
+        const int r = i / TT, c = i - r * TT;
+        float v = 0.f;
+        if (t0 + c < l) v = fmaf(a.x[((size_t)b * C + r) * l + t0 + c], sc[c], sh[c]);
+        split_store(Bhi, Blo, (size_t)r * TTP + c, v);
+    }
+    __syncthreads();
+    const int wm = warp >> 1, col0 = (warp & 1) * (TT / 2);
+    float part[NT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) part[n][0] = part[n][1] = 0.f;
+    for (int mt = wm; mt < C / 16; mt += 4) {
+        int tiles[1] = {mt};
+        float acc[1][NT][4];
+        zero3(acc);
+        gemm_split_bf16<1, NT, TTP>(a.Wf_fh, a.Wf_fl, C / 16, tiles, Bhi, Blo, col0, acc, lane);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int m = mt * 16 + g + half * 8;
+            const float bv = a.bf[m], wz = a.wz[m];
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) part[n][j] = fmaf(wz, fmaxf(acc[0][n][half * 2 + j] + bv, 0.f), part[n][j]);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float v = part[n][j];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g == 0) red[wm * TT + col0 + n * 8 + 2 * tq + j] = v;
+        }
+    __syncthreads();
+    if (tid < TT && t0 + tid < l) {
+        const float e = a.bz + ((red[tid] + red[TT + tid]) + (red[2 * TT + tid] + red[3 * TT + tid]));
+        const size_t o = (size_t)b * l + t0 + tid;
+        if (a.upd_x) {
+            // x <- (x - c1 eps) / sqrt(alpha) (+ sigma z)           generate.py:52-54
+            float xn = (a.upd_x[o] - a.c1 * e) / a.sqrt_alpha;
+            if (a.noise) xn += a.sigma * a.noise[o];
+            a.out[o] = xn;
+        } else {
+            a.out[o] = e;
+        }
+    }
+}
+
+int head_mma_launch(const HeadArgs &a, int B, cudaStream_t st) {
+    constexpr int TT = 64;
+    DWB_REQUIRE(a.Wf_fh && a.Wf_fl && a.C % 16 == 0, DWB_ERR_INVALID, "head_mma: C=%d needs packed weights", a.C);
+    const size_t sm = (size_t)2 * a.C * (TT + 8) * 2 + (size_t)6 * TT * 4;
+    return launch_pool(head_mma_kernel<TT>, a, dim3(ceil_div(a.l, TT), B), sm, st);
 }
 
 static size_t down_pool_smem(const PoolArgs &a, int TT) {

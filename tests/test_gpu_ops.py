@@ -98,7 +98,9 @@ def _fftconv_ref(x, stats, part, m, s, k, D):
 
 
 @pytest.mark.parametrize("B,H,l", [(1, 1, 16), (2, 3, 40), (1, 2, 33), (3, 2, 64), (2, 2, 100), (1, 3, 250), (2, 2, 1000),
-                                   (1, 2, 1001), (2, 3, 4000), (2, 2, 16000), (1, 1, 16384)])
+                                   (1, 2, 1001), (2, 3, 4000), (2, 2, 16000), (1, 1, 16384),
+                                   # n = 32768 variants: packed split kernel (l % 4 == 0), scalar split kernel (even / odd l)
+                                   (2, 2, 8200), (1, 2, 15998), (1, 2, 15999), (1, 1, 8193)])
 def test_fftconv_vs_oracle(dwb, B, H, l):
     g = torch.Generator().manual_seed(B * 7 + H * 13 + l)
     x = torch.randn(B, H, l, generator=g) * 2 + 0.3
