@@ -39,7 +39,7 @@ CFG = dict(_name_="sashimi", unconditional=True, in_channels=1, out_channels=1,
            unet=True, d_model=64, n_layers=6, pool=[4, 4], expand=2, ff=2, L=16000)
 T_STEPS, BETA_0, BETA_T, L = 200, 1e-4, 0.02, 16000
 METRIC = "audio clips/sec (16k-sample, T=200)"
-KERNEL_NAMES = {"fftconv_s0": "fftconv_kernel<14> (H=64, l=16000)", "fftconv_s1": "fftconv_kernel<12> (H=128, l=4000)",
+KERNEL_NAMES = {"fftconv_s0": "fftconv3_kernel<14> (H=64, l=16000)", "fftconv_s1": "fftconv_kernel<12> (H=128, l=4000)",
                 "fftconv_s2": "fftconv_kernel<10> (H=256, l=1000)", "mix_s0": "sashimi_mix_umma_kernel<64> (l=16000)",
                 "mix_s1": "sashimi_mix_umma_pers_kernel<128> (l=4000)", "mix_s2": "sashimi_mix_umma256_kernel (l=1000)"}
 

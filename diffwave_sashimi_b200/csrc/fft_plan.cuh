@@ -56,7 +56,10 @@ inline int fft_forced_variant() {
     }();
     return forced;
 }
-inline bool fft_use_v2(int log2M) { return fft_forced_variant() != 1 && log2M == 14; }
+inline bool fft_use_v2(int log2M) {
+    static const bool s12 = getenv("DWB_FFT12") != nullptr;       // experiment: split kernels at n = 8192 too
+    return fft_forced_variant() != 1 && (log2M == 14 || (s12 && log2M == 12));
+}
 
 // shared-memory padding: one float2 of slack per 16 so that the stride-16 and stride-1
 // passes (16 consecutive elements per thread) are bank-conflict free

@@ -169,6 +169,8 @@ FULL = {
     "full_wnet_h128_d30": ("wnet_h128_d30", 1, 100.0, None),
     "full_unet_d64": ("unet_d64", 1, 100.0, None),
     "full_unet_d32_cond": ("unet_d32_cond", 1, 25.0, (1, 80, 63)),
+    "full_unet_d128": ("unet_d128", 1, 100.0, None),            # BASELINE.json configs[2] (widths 128/256/512)
+    "full_wnet_h256_d36": ("wnet_h256_d36", 1, 100.0, None),    # BASELINE.json configs[4]
 }
 
 
@@ -178,6 +180,8 @@ def make_full(ns):
     engine with these stored reference outputs (64 KB each)."""
     import diffwave_sashimi_b200 as dwb
     for name, (base, B, tval, melshape) in FULL.items():
+        if os.path.exists(os.path.join(HERE, name + ".npz")) and os.environ.get("GOLDEN_ONLY_MISSING"):
+            continue
         cfg = refshim.Cfg(refshim.MODEL_CFGS[base])
         sd = dwb.init.seeded_state_dict(dict(cfg), seed=0)
         net = ns.models.construct_model(cfg).eval()

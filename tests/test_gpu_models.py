@@ -91,6 +91,8 @@ FULL = {
     "wnet_h128_d30": ("full_wnet_h128_d30", None),
     "unet_d64": ("full_unet_d64", None),
     "unet_d32_cond": ("full_unet_d32_cond", (1, 80, 63)),
+    "unet_d128": ("full_unet_d128", None),
+    "wnet_h256_d36": ("full_wnet_h256_d36", None),
 }
 
 
