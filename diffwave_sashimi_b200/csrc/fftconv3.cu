@@ -50,24 +50,6 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 __device__ __forceinline__ V2 ld2(const float *p) { return V2(*reinterpret_cast<const float2 *>(p)); }
 __device__ __forceinline__ void st2(float *p, const V2 &a) { *reinterpret_cast<float2 *>(p) = a.v; }
 
-// GELU (erf form), two lanes: same formula as gelu_fast (common.cuh); MUFU and the select stay scalar
-__device__ __forceinline__ V2 gelu_fast2(const V2 &x) {
-    float t0, t1, e0, e1;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.v.x), 1.0f)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.v.y), 1.0f)));
-    const V2 t(t0, t1);
-    V2 p = fma(t, V2(1.061405429f), V2(-1.453152027f));
-    p = fma(t, p, V2(1.421413741f));
-    p = fma(t, p, V2(-0.284496736f));
-    p = fma(t, p, V2(0.254829592f));
-    const V2 ea = (x * x) * (-0.5f * 1.4426950408889634f);
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(ea.v.x));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(ea.v.y));
-    const V2 hh = (x * 0.5f) * (V2(e0, e1) * (p * t));
-    const V2 d = x - hh;
-    return V2(x.v.x >= 0.f ? d.v.x : hh.v.x, x.v.y >= 0.f ? d.v.y : hh.v.y);
-}
-
 // one in-place radix-16 pass P (span S = Mh / 16^P) over the planes, butterflies 2 tid and 2 tid + 1
 template <int LH, int P, bool INV>
 __device__ __forceinline__ void mid_pass(float *re, float *im, const float *twr, const float *twi, int tid) {
@@ -374,7 +356,7 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
                     if (i < half) {
                         float4 *dst = reinterpret_cast<float4 *>(gr + 2 * i);
                         const float4 a = *dst;
-                        const V2 r = gelu_fast2(xx[p].x + V2(a.x, a.y)), q = gelu_fast2(xx[p].y + V2(a.z, a.w));
+                        const V2 r = s2::gelu_fast2(xx[p].x + V2(a.x, a.y)), q = s2::gelu_fast2(xx[p].y + V2(a.z, a.w));
                         *dst = make_float4(r.v.x, q.v.x, r.v.y, q.v.y);
                     }
                 }

@@ -266,17 +266,23 @@ int mix_mma_launch(const MixArgs &a, int B, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------
 // pools on the same split-bf16 path                               (models/sashimi.py:23-58)
 // ---------------------------------------------------------------------------------------
+// Both kernels: the fp32 output staging tile aliases the split-bf16 operand tile (a barrier separates the
+// last MMA from the first staging store), so the tile can be twice as wide in the same shared memory and
+// the weight fragments (read from L2 by every CTA) are fetched half as often; a warp owns MTW m-tiles
+// that share every B fragment it loads.
+//
 // down(s): x'[h*s+j][c] = x[b, h, (t0+c)*s + j];  out = W x' + bias  (K = Hi*s -> Ho), + stats
-template <int TT>
+template <int TT, int MTW>
 __global__ void __launch_bounds__(MIX_THREADS)
 down_pool_mma_kernel(PoolArgs a) {
     constexpr int TTP = TT + 8, XS = TT + 4, NT = TT / 8;
     extern __shared__ __align__(16) unsigned char smraw[];
     const int Hi = a.Hi, Ho = a.Ho, s = a.s, li = a.li, lo = li / s, K = Hi * s;
-    float *Os = reinterpret_cast<float *>(smraw);                                  // [Ho][XS]
-    __nv_bfloat16 *Bhi = reinterpret_cast<__nv_bfloat16 *>(Os + (size_t)Ho * XS);  // [K][TTP]
+    const size_t ubytes = max((size_t)Ho * XS * 4, (size_t)2 * K * TTP * 2);
+    float *Os = reinterpret_cast<float *>(smraw);                                  // [Ho][XS]   (after the GEMM)
+    __nv_bfloat16 *Bhi = reinterpret_cast<__nv_bfloat16 *>(smraw);                 // [K][TTP]   (before)
     __nv_bfloat16 *Blo = Bhi + (size_t)K * TTP;
-    float *scratch = reinterpret_cast<float *>(Blo + (size_t)K * TTP);
+    float *scratch = reinterpret_cast<float *>(smraw + ((ubytes + 15) & ~(size_t)15));
     float *stat_s = scratch + 2 * MIX_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
     const int b = blockIdx.y, t0 = blockIdx.x * TT;
@@ -287,19 +293,24 @@ down_pool_mma_kernel(PoolArgs a) {
         split_store(Bhi, Blo, (size_t)(h * s + j) * TTP + c, v);
     }
     __syncthreads();
-    for (int mt = warp; mt < Ho / 16; mt += MIX_THREADS / 32) {
-        int tiles[1] = {mt};
-        float acc[1][NT][4];
-        zero3(acc);
-        gemm_split_bf16<1, NT, TTP>(a.W_fh, a.W_fl, K / 16, tiles, Bhi, Blo, 0, acc, lane);
+    int tiles[MTW];
+#pragma unroll
+    for (int i = 0; i < MTW; ++i) tiles[i] = min(warp + 8 * i, Ho / 16 - 1);     // clamped duplicates are not stored
+    float acc[MTW][NT][4];
+    zero3(acc);
+    gemm_split_bf16<MTW, NT, TTP>(a.W_fh, a.W_fl, K / 16, tiles, Bhi, Blo, 0, acc, lane);
+    __syncthreads();                                                               // operands dead: Os may overwrite them
+#pragma unroll
+    for (int i = 0; i < MTW; ++i) {
+        if (warp + 8 * i >= Ho / 16) continue;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int m = mt * 16 + g + half * 8;
+            const int m = tiles[i] * 16 + g + half * 8;
             const float bv = a.bias[m];
 #pragma unroll
             for (int n = 0; n < NT; ++n)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) Os[(size_t)m * XS + n * 8 + 2 * tq + j] = acc[0][n][half * 2 + j] + bv;
+                for (int j = 0; j < 2; ++j) Os[(size_t)m * XS + n * 8 + 2 * tq + j] = acc[i][n][half * 2 + j] + bv;
         }
     }
     __syncthreads();
@@ -315,16 +326,17 @@ down_pool_mma_kernel(PoolArgs a) {
 }
 
 // up(s): y = W x + bias (Hi -> Ho*s);  out[b, h, (t0+c)*s + j] = y[h*s+j][c] (+ skip), + stats
-template <int S>
+template <int S, int TT, int MTW>
 __global__ void __launch_bounds__(MIX_THREADS)
 up_pool_mma_kernel(PoolArgs a) {
-    constexpr int TT = 16, TTP = TT + 8, NT = TT / 8, TTO = TT * S, XSO = TTO + 4;
+    constexpr int TTP = TT + 8, NT = TT / 8, TTO = TT * S, XSO = TTO + 4;
     extern __shared__ __align__(16) unsigned char smraw[];
     const int Hi = a.Hi, Ho = a.Ho, li = a.li, lo = li * S, M = Ho * S;
-    float *Os = reinterpret_cast<float *>(smraw);                                   // [Ho][XSO]
-    __nv_bfloat16 *Bhi = reinterpret_cast<__nv_bfloat16 *>(Os + (size_t)Ho * XSO);  // [Hi][TTP]
+    const size_t ubytes = max((size_t)Ho * XSO * 4, (size_t)2 * Hi * TTP * 2);
+    float *Os = reinterpret_cast<float *>(smraw);                                   // [Ho][XSO]  (after the GEMM)
+    __nv_bfloat16 *Bhi = reinterpret_cast<__nv_bfloat16 *>(smraw);                  // [Hi][TTP]  (before)
     __nv_bfloat16 *Blo = Bhi + (size_t)Hi * TTP;
-    float *scratch = reinterpret_cast<float *>(Blo + (size_t)Hi * TTP);
+    float *scratch = reinterpret_cast<float *>(smraw + ((ubytes + 15) & ~(size_t)15));
     float *stat_s = scratch + 2 * MIX_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
     const int b = blockIdx.y, t0 = blockIdx.x * TT;
@@ -333,20 +345,25 @@ up_pool_mma_kernel(PoolArgs a) {
         split_store(Bhi, Blo, (size_t)r * TTP + c, (t0 + c < li) ? a.x[((size_t)b * Hi + r) * li + t0 + c] : 0.f);
     }
     __syncthreads();
-    for (int mt = warp; mt < M / 16; mt += MIX_THREADS / 32) {
-        int tiles[1] = {mt};
-        float acc[1][NT][4];
-        zero3(acc);
-        gemm_split_bf16<1, NT, TTP>(a.W_fh, a.W_fl, Hi / 16, tiles, Bhi, Blo, 0, acc, lane);
+    int tiles[MTW];
+#pragma unroll
+    for (int i = 0; i < MTW; ++i) tiles[i] = min(warp + 8 * i, M / 16 - 1);
+    float acc[MTW][NT][4];
+    zero3(acc);
+    gemm_split_bf16<MTW, NT, TTP>(a.W_fh, a.W_fl, Hi / 16, tiles, Bhi, Blo, 0, acc, lane);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < MTW; ++i) {
+        if (warp + 8 * i >= M / 16) continue;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int m = mt * 16 + g + half * 8;
+            const int m = tiles[i] * 16 + g + half * 8;
             const int h = m / S, j = m - h * S;
             const float bv = a.bias[m];
 #pragma unroll
             for (int n = 0; n < NT; ++n)
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) Os[(size_t)h * XSO + (n * 8 + 2 * tq + jj) * S + j] = acc[0][n][half * 2 + jj] + bv;
+                for (int jj = 0; jj < 2; ++jj) Os[(size_t)h * XSO + (n * 8 + 2 * tq + jj) * S + j] = acc[i][n][half * 2 + jj] + bv;
         }
     }
     __syncthreads();
@@ -469,20 +486,56 @@ int head_mma_launch(const HeadArgs &a, int B, cudaStream_t st) {
 }
 
 static size_t down_pool_smem(const PoolArgs &a, int TT) {
-    return (size_t)a.Ho * (TT + 4) * 4 + (size_t)2 * a.Hi * a.s * (TT + 8) * 2 + (2 * MIX_THREADS + 2 * TT) * 4;
+    const size_t u = std::max((size_t)a.Ho * (TT + 4) * 4, (size_t)2 * a.Hi * a.s * (TT + 8) * 2);
+    return ((u + 15) & ~(size_t)15) + (size_t)(2 * MIX_THREADS + 2 * TT) * 4;
+}
+static size_t up_pool_smem(const PoolArgs &a, int TT) {
+    const size_t u = std::max((size_t)a.Ho * (TT * a.s + 4) * 4, (size_t)2 * a.Hi * (TT + 8) * 2);
+    return ((u + 15) & ~(size_t)15) + (size_t)(2 * MIX_THREADS + 2 * TT * a.s) * 4;
+}
+
+// widest tile with two CTAs per SM (<= 113 KB each) and <= 16 accumulator tiles per warp (MTW * TT/8)
+template <int TT>
+static int launch_down(const PoolArgs &a, int B, int mtw, cudaStream_t st) {
+    const dim3 grid(ceil_div(a.li / a.s, TT), B);
+    const size_t sm = down_pool_smem(a, TT);
+    if constexpr (TT <= 64) if (mtw == 1) return launch_pool(down_pool_mma_kernel<TT, 1>, a, grid, sm, st);
+    if constexpr (TT <= 64) if (mtw == 2) return launch_pool(down_pool_mma_kernel<TT, 2>, a, grid, sm, st);
+    if constexpr (TT <= 32) if (mtw <= 4) return launch_pool(down_pool_mma_kernel<TT, 4>, a, grid, sm, st);
+    if constexpr (TT <= 16) if (mtw <= 8) return launch_pool(down_pool_mma_kernel<TT, 8>, a, grid, sm, st);
+    set_error("down_pool_mma: Ho=%d needs %d m-tiles per warp at TT=%d", a.Ho, mtw, TT);
+    return DWB_ERR_UNSUPPORTED;
 }
 
 int down_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st) {
-    if (down_pool_smem(a, 32) <= 110 * 1024)      // two CTAs per SM
-        return launch_pool(down_pool_mma_kernel<32>, a, dim3(ceil_div(a.li / a.s, 32), B), down_pool_smem(a, 32), st);
-    return launch_pool(down_pool_mma_kernel<16>, a, dim3(ceil_div(a.li / a.s, 16), B), down_pool_smem(a, 16), st);
+    const int mtw = ceil_div(a.Ho / 16, 8);
+    const size_t cap = 113 * 1024;
+    if (mtw <= 2 && down_pool_smem(a, 64) <= cap) return launch_down<64>(a, B, mtw, st);
+    if (mtw <= 4 && down_pool_smem(a, 32) <= cap) return launch_down<32>(a, B, mtw, st);
+    return launch_down<16>(a, B, mtw, st);
+}
+
+template <int S, int TT>
+static int launch_up(const PoolArgs &a, int B, int mtw, cudaStream_t st) {
+    const dim3 grid(ceil_div(a.li, TT), B);
+    const size_t sm = up_pool_smem(a, TT);
+    if constexpr (TT <= 64 && TT * S <= MIX_THREADS) if (mtw <= 2) return launch_pool(up_pool_mma_kernel<S, TT, 2>, a, grid, sm, st);
+    if constexpr (TT <= 32) if (mtw <= 4) return launch_pool(up_pool_mma_kernel<S, TT, 4>, a, grid, sm, st);
+    if constexpr (TT <= 16) if (mtw <= 8) return launch_pool(up_pool_mma_kernel<S, TT, 8>, a, grid, sm, st);
+    set_error("up_pool_mma: Ho*s=%d needs %d m-tiles per warp at TT=%d", a.Ho * a.s, mtw, TT);
+    return DWB_ERR_UNSUPPORTED;
+}
+
+template <int S>
+static int up_pool_pick(const PoolArgs &a, int B, cudaStream_t st) {
+    const int mtw = ceil_div(a.Ho * S / 16, 8);
+    // measured (B200, unet d64, B = 32): wider tiles LOSE here (174 us at TT = 16 vs 212 / 341 us at 32 / 64): the kernel is
+    // bound by its staging / statistics / scatter phases, not by the weight fragments, and wants many small CTAs
+    return launch_up<S, 16>(a, B, mtw, st);
 }
 
 int up_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st) {
-    constexpr int TT = 16;
-    const size_t sm = (size_t)a.Ho * (TT * a.s + 4) * 4 + (size_t)2 * a.Hi * (TT + 8) * 2 + (2 * MIX_THREADS + 2 * TT * a.s) * 4;
-    const dim3 grid(ceil_div(a.li, TT), B);
-    return a.s == 2 ? launch_pool(up_pool_mma_kernel<2>, a, grid, sm, st) : launch_pool(up_pool_mma_kernel<4>, a, grid, sm, st);
+    return a.s == 2 ? up_pool_pick<2>(a, B, st) : up_pool_pick<4>(a, B, st);
 }
 
 }  // namespace dwb

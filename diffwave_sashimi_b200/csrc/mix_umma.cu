@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "fft_simd2.cuh"
 #include "umma.cuh"
 
 namespace dwb {
@@ -281,10 +282,17 @@ sashimi_mix_umma_kernel(MixArgs a) {
                     tmem_wait_ld();
                     const float *ba = bo_s + nc * 128 + p0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float y = (av[i] + ba[i]) * sigmoid_fast(gv[i] + ba[64 + i]);
-                        if (a.cond && valid) y += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i) * l);
-                        xv[i] += y;
+                    for (int i = 0; i < 16; i += 2) {
+                        // two channels per packed instruction (FADD2 / FMUL2 / FFMA2)
+                        s2::V2 y = (s2::V2(av[i], av[i + 1]) + s2::V2(ba[i], ba[i + 1])) *
+                                   s2::sigmoid_fast2(s2::V2(gv[i], gv[i + 1]) + s2::V2(ba[64 + i], ba[64 + i + 1]));
+                        y = y + s2::V2(xv[i], xv[i + 1]);
+                        xv[i] = y.v.x;
+                        xv[i + 1] = y.v.y;
+                        if (a.cond && valid) {
+                            xv[i] += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i) * l);
+                            xv[i + 1] += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i + 1) * l);
+                        }
                     }
                     stat_merge16(xv, n, mean, M2);
                     n += 16;
@@ -356,7 +364,11 @@ sashimi_mix_umma_kernel(MixArgs a) {
                     tmem_wait_ld();
                     const float *bb = b1_s + f0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i] + bb[i]);
+                    for (int i = 0; i < 16; i += 2) {
+                        const s2::V2 r = s2::gelu_fast2(s2::V2(v[i], v[i + 1]) + s2::V2(bb[i], bb[i + 1]));
+                        v[i] = r.v.x;
+                        v[i + 1] = r.v.y;
+                    }
                     const int kc = f0 >> 6;
                     uint8_t *slot = slots + C::hid_slot(kc) * UM_SLOT;
 #pragma unroll
@@ -717,10 +729,17 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
                         tmem_wait_ld();
                         const float *ba = bo_s + nc * 128 + p0;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float y = (av[i] + ba[i]) * sigmoid_fast(gv[i] + ba[64 + i]);
-                            if (a.cond && valid) y += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i) * l);
-                            xv[i] += y;
+                        for (int i = 0; i < 16; i += 2) {
+                            // two channels per packed instruction (FADD2 / FMUL2 / FFMA2)
+                            s2::V2 y = (s2::V2(av[i], av[i + 1]) + s2::V2(ba[i], ba[i + 1])) *
+                                       s2::sigmoid_fast2(s2::V2(gv[i], gv[i + 1]) + s2::V2(ba[64 + i], ba[64 + i + 1]));
+                            y = y + s2::V2(xv[i], xv[i + 1]);
+                            xv[i] = y.v.x;
+                            xv[i + 1] = y.v.y;
+                            if (a.cond && valid) {
+                                xv[i] += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i) * l);
+                                xv[i + 1] += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i + 1) * l);
+                            }
                         }
                         stat_merge16(xv, n, mean, M2);
                         n += 16;
@@ -775,7 +794,11 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
                         tmem_wait_ld();
                         const float *bb = b1_s + f0;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i] + bb[i]);
+                        for (int i = 0; i < 16; i += 2) {
+                        const s2::V2 r = s2::gelu_fast2(s2::V2(v[i], v[i + 1]) + s2::V2(bb[i], bb[i + 1]));
+                        v[i] = r.v.x;
+                        v[i + 1] = r.v.y;
+                    }
                         const int kc = f0 >> 6;
                         uint8_t *slot = slots + C::hid_slot(kc) * UM_SLOT;
 #pragma unroll
@@ -1109,10 +1132,17 @@ sashimi_mix_umma256_kernel(MixArgs a) {
                     tmem_wait_ld();
                     const float *ba = bo_g + nc * 128 + p0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float y = (av[i] + __ldg(ba + i)) * sigmoid_fast(gv[i] + __ldg(ba + 64 + i));
-                        if (a.cond && valid) y += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i) * l);
-                        xv[i] += y;
+                    for (int i = 0; i < 16; i += 2) {
+                        // two channels per packed instruction (FADD2 / FMUL2 / FFMA2)
+                        s2::V2 y = (s2::V2(av[i], av[i + 1]) + s2::V2(__ldg(ba + i), __ldg(ba + i + 1))) *
+                                   s2::sigmoid_fast2(s2::V2(gv[i], gv[i + 1]) + s2::V2(__ldg(ba + 64 + i), __ldg(ba + 64 + i + 1)));
+                        y = y + s2::V2(xv[i], xv[i + 1]);
+                        xv[i] = y.v.x;
+                        xv[i + 1] = y.v.y;
+                        if (a.cond && valid) {
+                            xv[i] += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i) * l);
+                            xv[i + 1] += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i + 1) * l);
+                        }
                     }
                     stat_merge16(xv, n, mean, M2);
                     n += 16;
@@ -1166,7 +1196,11 @@ sashimi_mix_umma256_kernel(MixArgs a) {
                 tmem_wait_ld();
                 const float *bb = b1_g + f0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i] + __ldg(bb + i));
+                for (int i = 0; i < 16; i += 2) {
+                        const s2::V2 r = s2::gelu_fast2(s2::V2(v[i], v[i + 1]) + s2::V2(__ldg(bb + i), __ldg(bb + i + 1)));
+                        v[i] = r.v.x;
+                        v[i + 1] = r.v.y;
+                    }
                 uint4 h0, l0, h1, l1;
                 split8(v, h0, l0);
                 split8(v + 8, h1, l1);
