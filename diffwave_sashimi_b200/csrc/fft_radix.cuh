@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "fft_plan.cuh"
+#include "fft_simd2.cuh"
 
 namespace dwb {
 
@@ -49,8 +50,13 @@ struct Radix {
                     const float wr = WR[k], wi = INV ? -WI[k] : WI[k];
                     t = make_float2(o[q].x * wr - o[q].y * wi, o[q].x * wi + o[q].y * wr);
                 }
-                x[q] = make_float2(e[q].x + t.x, e[q].y + t.y);
-                x[q + R / 2] = make_float2(e[q].x - t.x, e[q].y - t.y);
+                if (k == 4) {                        // t is a half-negated swap: scalar adds, no register moves
+                    x[q] = make_float2(e[q].x + t.x, e[q].y + t.y);
+                    x[q + R / 2] = make_float2(e[q].x - t.x, e[q].y - t.y);
+                } else {                             // complex add / sub = one FADD2 each (packed fp32, sm_100a)
+                    x[q] = (s2::V2(e[q]) + s2::V2(t)).v;
+                    x[q + R / 2] = (s2::V2(e[q]) - s2::V2(t)).v;
+                }
             }
         }
     }
