@@ -57,6 +57,7 @@ SIGNATURES = {
     "dwb_s4_kernel_gen": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
     "dwb_fftconv_size": [_I, ctypes.POINTER(_I)],
     "dwb_fftconv_prepare": [_P, _P, _I, _I, _P, _P],
+    "dwb_plan_cond_features": [_P, _P, _I, _I, _I, _P, _P],
     "dwb_fftconv": [_P, _P, _P, _I64, _F, _F, _P, _P, _I, _I, _I, _P],
 }
 

@@ -118,6 +118,14 @@ struct dwb_plan {
     int n_bufs = 0;
     std::vector<WaveLayer> wl;     // wavenet
     int64_t cond_total = 0;        // floats of conditioning features per cond batch element
+    struct CondBlock {             // in-model mel front end of one block (folded weights)
+        float *w[2], *b[2];        // ConvTranspose2d taps [3][2 s_i], bias (1)
+        int s[2];
+        float *Wm_t, *bm;          // mel_conv [mel_bands][Hc], (Hc)
+        int Hc, l;                 // l = 0: the caller's L (wavenet; `off` is then the layer index)
+        int64_t off;
+    };
+    std::vector<CondBlock> cond_blocks;
 
     // workspace (grow-only, keyed on B*L)
     int ws_B = 0, ws_L = 0;
@@ -756,12 +764,49 @@ int dwb_plan_set_tensor(dwb_plan *p, const char *name, const void *data, int dty
     return DWB_OK;
 }
 
+// conditional models: fold the per-block mel front end (skipped when the host did not supply those weights)
+static int finalize_cond(dwb_plan *p, cudaStream_t st) {
+    p->cond_blocks.clear();
+    if (p->cfg.unconditional) return DWB_OK;
+    std::vector<std::pair<std::string, dwb_plan::CondBlock>> todo;
+    if (p->cfg.model == DWB_MODEL_SASHIMI) {
+        for (auto &o : p->ops)
+            if (o.kind == OP_BLOCK) {
+                dwb_plan::CondBlock cb{};
+                cb.Hc = o.H; cb.l = o.l; cb.off = o.cond_off;
+                todo.push_back({o.prefix, cb});
+            }
+    } else {
+        for (size_t i = 0; i < p->wl.size(); ++i) {
+            dwb_plan::CondBlock cb{};
+            cb.Hc = 2 * p->cfg.res_channels; cb.l = 0; cb.off = (int64_t)i;      // layer index: offset = i * 2C * L at call time
+            todo.push_back({"residual_layer.residual_blocks." + std::to_string(i) + ".", cb});
+        }
+    }
+    if (todo.empty() || !find(p, todo[0].first + "upsample_conv2d.0.weight_v")) return DWB_OK;
+    for (auto &t : todo) {
+        dwb_plan::CondBlock cb = t.second;
+        for (int i = 0; i < 2; ++i) {
+            const std::string pre = t.first + "upsample_conv2d." + std::to_string(i);
+            const Tensor *v = find(p, pre + ".weight_v");
+            DWB_REQUIRE(v && v->shape.size() == 4 && v->shape[0] == 1 && v->shape[1] == 1 && v->shape[2] == 3 && v->shape[3] % 2 == 0,
+                        DWB_ERR_INVALID, "`%s.weight_v` must be (1,1,3,2s)", pre.c_str());
+            cb.s[i] = (int)(v->shape[3] / 2);
+            TRY(folded(p, pre, 1, 1, 3 * 2 * cb.s[i], true, &cb.w[i], &cb.b[i], st));
+        }
+        TRY(folded(p, t.first + "mel_conv.conv", cb.Hc, p->cfg.mel_bands, 1, true, &cb.Wm_t, &cb.bm, st));
+        p->cond_blocks.push_back(cb);
+    }
+    return DWB_OK;
+}
+
 int dwb_plan_finalize(dwb_plan *p, void *stream) {
     DWB_REQUIRE(p, DWB_ERR_INVALID, "null plan");
     DWB_REQUIRE(!p->finalized, DWB_ERR_STATE, "plan already finalized");
     DWB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc = p->cfg.model == DWB_MODEL_SASHIMI ? finalize_sashimi(p, st) : finalize_wavenet(p, st);
+    if (rc == DWB_OK) rc = finalize_cond(p, st);
     if (rc != DWB_OK) return rc;
     DWB_CUDA(cudaStreamSynchronize(st));
     p->finalized = true;
@@ -904,6 +949,45 @@ int dwb_plan_cond_layout(dwb_plan *p, int L, int *n_blocks, int *channels, int *
         }
     }
     *n_blocks = n;
+    return DWB_OK;
+}
+
+int dwb_plan_cond_features(dwb_plan *p, const float *mel, int cond_batch, int frames, int L, float *out, void *stream) {
+    DWB_REQUIRE(p && p->finalized, DWB_ERR_STATE, "plan is not finalized");
+    DWB_REQUIRE(mel && out && cond_batch >= 1 && frames >= 1 && L >= 1, DWB_ERR_INVALID, "dwb_plan_cond_features: bad arguments");
+    DWB_REQUIRE(!p->cfg.unconditional, DWB_ERR_STATE, "unconditional model has no conditioning path");
+    DWB_REQUIRE(!p->cond_blocks.empty(), DWB_ERR_MISSING, "upsample_conv2d / mel_conv weights were not supplied to the plan");
+    DWB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = p->cfg.mel_bands;
+    int w1max = 0, w2max = 0;
+    for (auto &cb : p->cond_blocks) {
+        w1max = std::max(w1max, frames * cb.s[0]);
+        w2max = std::max(w2max, frames * cb.s[0] * cb.s[1]);
+    }
+    float *u1 = nullptr, *u2 = nullptr;
+    DWB_CUDA(cudaMalloc(&u1, (size_t)cond_batch * F * w1max * sizeof(float)));
+    cudaError_t e = cudaMalloc(&u2, (size_t)cond_batch * F * w2max * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(u1); return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
+    int rc = DWB_OK;
+    for (auto &cb : p->cond_blocks) {
+        const int l = cb.l ? cb.l : L, W1 = frames * cb.s[0], W2 = W1 * cb.s[1];
+        if (W2 < l) {
+            set_error("upsampled mel has %d samples < %d", W2, l);
+            rc = DWB_ERR_INVALID;
+            break;
+        }
+        if ((rc = mel_upsample_launch(mel, cond_batch, F, frames, cb.s[0], cb.w[0], cb.b[0], u1, st)) != DWB_OK) break;
+        if ((rc = mel_upsample_launch(u1, cond_batch, F, W1, cb.s[1], cb.w[1], cb.b[1], u2, st)) != DWB_OK) break;
+        const int64_t off = cb.l ? cb.off : cb.off * (int64_t)cb.Hc * L;
+        if ((rc = mel_conv_launch(u2, cond_batch, F, W2, cb.Wm_t, cb.bm, cb.Hc, l, out + (size_t)cond_batch * off, st)) != DWB_OK) break;
+        p->launches += 3;
+    }
+    cudaError_t es = cudaStreamSynchronize(st);
+    cudaFree(u1);
+    cudaFree(u2);
+    if (rc != DWB_OK) return rc;
+    if (es != cudaSuccess) return cuda_fail(es, "dwb_plan_cond_features", __FILE__, __LINE__);
     return DWB_OK;
 }
 

@@ -85,6 +85,10 @@ int frag_pack(const float *Wt, int M, int K, uint32_t *fhi, uint32_t *flo, cudaS
 int down_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
 int up_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
 int head_launch(const HeadArgs &a, int B, cudaStream_t st);
+int mel_upsample_launch(const float *in, int rows, int F, int Win, int s, const float *w, const float *bias, float *out,
+                        cudaStream_t st);
+int mel_conv_launch(const float *u, int rows, int K, int Wu, const float *Wt, const float *bias, int Hc, int l, float *out,
+                    cudaStream_t st);
 int head_mma_launch(const HeadArgs &a, int B, cudaStream_t st);
 int wave_block_launch(const WaveBlockArgs &a, int B, cudaStream_t st);
 bool wave_mma_supported(int C, int S);

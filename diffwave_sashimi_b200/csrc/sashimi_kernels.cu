@@ -50,6 +50,67 @@ int fold_weight(const float *v, const float *g, int M, int Kin, int taps, float 
 }
 
 // ---------------------------------------------------------------------------------------
+// mel conditioning front end inside the model (t-independent, once per utterance):
+// ConvTranspose2d(1, 1, (3, 2s), stride (1, s), padding (1, s/2)) + leaky-ReLU(0.4), twice, then a
+// 1x1 mel_bands -> H conv on the first l samples           (models/sashimi.py:133-141,160-175,
+// models/wavenet.py:62-70,98-111).  out[f][x] = b + sum_{kf<3} sum_{kx = (x + s/2) mod s (+ s)}
+// in[f + 1 - kf][(x + s/2 - kx) / s] w[kf][kx]: six taps per output sample.
+// ---------------------------------------------------------------------------------------
+__global__ void mel_upsample_kernel(const float *__restrict__ in, int F, int Win, int s, const float *__restrict__ w,
+                                    const float *__restrict__ bias, float *__restrict__ out, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int Wout = Win * s;
+    const int x = (int)(idx % Wout);
+    const long long r = idx / Wout;
+    const int f = (int)(r % F);
+    const long long b = r / F;
+    const int k0 = (x + s / 2) % s;
+    float acc = bias[0];
+#pragma unroll
+    for (int kf = 0; kf < 3; ++kf) {
+        const int fi = f + 1 - kf;
+        if (fi < 0 || fi >= F) continue;
+        const float *row = in + ((size_t)b * F + fi) * Win;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int kx = k0 + q * s;
+            const int xi = (x + s / 2 - kx) / s;          // exact: x + s/2 - kx is a multiple of s (may be negative)
+            if (x + s / 2 - kx >= 0 && xi < Win) acc = fmaf(row[xi], w[kf * 2 * s + kx], acc);
+        }
+    }
+    out[idx] = acc > 0.f ? acc : 0.4f * acc;
+}
+
+// out[b][m][t] = bias[m] + sum_k Wt[k][m] u[b][k][t],  t < l <= Wu
+__global__ void mel_conv_kernel(const float *__restrict__ u, int K, int Wu, const float *__restrict__ Wt,
+                                const float *__restrict__ bias, int Hc, int l, float *__restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y, b = blockIdx.z;
+    if (t >= l) return;
+    const float *ub = u + (size_t)b * K * Wu + t;
+    float acc = bias[m];
+    for (int k = 0; k < K; ++k) acc = fmaf(Wt[(size_t)k * Hc + m], ub[(size_t)k * Wu], acc);
+    out[((size_t)b * Hc + m) * l + t] = acc;
+}
+
+int mel_upsample_launch(const float *in, int rows, int F, int Win, int s, const float *w, const float *bias, float *out,
+                        cudaStream_t st) {
+    const long long total = (long long)rows * F * Win * s;
+    mel_upsample_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(in, F, Win, s, w, bias, out, total);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+int mel_conv_launch(const float *u, int rows, int K, int Wu, const float *Wt, const float *bias, int Hc, int l, float *out,
+                    cudaStream_t st) {
+    DWB_REQUIRE(Hc <= 65535 && rows <= 65535, DWB_ERR_UNSUPPORTED, "mel_conv: Hc=%d rows=%d exceed the grid", Hc, rows);
+    mel_conv_kernel<<<dim3(ceil_div(l, 128), Hc, rows), 128, 0, st>>>(u, K, Wu, Wt, bias, Hc, l, out);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // diffusion-step embedding: t -> [sin(t f), cos(t f)] -> swish(fc1) -> swish(fc2) -> all per-layer fc_t
 // ---------------------------------------------------------------------------------------
 // one CTA per embedding row (batch element, or step index when building the per-step table)

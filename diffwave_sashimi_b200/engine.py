@@ -4,14 +4,12 @@ All arithmetic on the per-step path happens inside libdwb.  The host side does t
 input-independent pieces the survey keeps in PyTorch:
   * the one-off `C` rewrite of fresh (kernel.L == 0) checkpoints    (models/s4.py:525-551)
   * the FFT node table in the reference's own complex64 recipe       (models/s4.py:553-571)
-  * the t-independent mel upsampling features, once per utterance    (models/sashimi.py:160-175)
 """
 import ctypes
 import math
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from ._lib import Config, check, lib, ptr, stream_ptr
@@ -50,11 +48,6 @@ def setup_C(C, B, P, inv_w_real, w_imag, log_dt, L: int):
     Ct = torch.cat([Cc, Cc.conj()], -1)
     Ct = Ct - torch.einsum("chn,hnm->chm", Ct, acc)
     return torch.view_as_real(Ct[..., :N].contiguous()).float()
-
-
-def _fold(v, g):
-    n = v.reshape(v.shape[0], -1).norm(dim=1).reshape((-1,) + (1,) * (v.dim() - 1))
-    return v * (g / n)
 
 
 class Engine:
@@ -100,7 +93,6 @@ class Engine:
             except Exception:
                 self.close()
                 raise
-        self._sd = sd if not c.unconditional else None   # conditioning weights stay on the host mirror
         self._cond_cache = None
 
     # ---- weights ------------------------------------------------------------------------
@@ -152,8 +144,6 @@ class Engine:
                         ** torch.arange(0, l // 2 + 1, device=self.device)).cpu()
                     self._set(f"nodes.{l}", torch.view_as_real(om).contiguous(), st)
         for name, t in sd.items():
-            if "upsample_conv2d" in name or "mel_conv" in name:
-                continue   # conditioning front-end runs on the host mirror, once per utterance
             self._set(name, t, st)
 
     def _set(self, name, t, st):
@@ -182,31 +172,15 @@ class Engine:
         key = (mel.data_ptr(), tuple(mel.shape), mel._version, L)
         if self._cond_cache is not None and self._cond_cache[0] == key:
             return self._cond_cache[1]
-        sd = self._sd
-        mel = mel.to(self.device, torch.float32)
-        cb = mel.shape[0]
-        if self.sashimi:
-            prefixes = [p for (p, _, _) in self._block_prefixes()]
-        else:
-            prefixes = [f"residual_layer.residual_blocks.{n}." for n in range(self.cfg["num_res_layers"])]
+        mel = mel.to(self.device, torch.float32).contiguous()
+        cb, bands, frames = mel.shape
+        if bands != self._c.mel_bands:
+            raise ValueError(f"mel_spec has {bands} bands, the model expects {self._c.mel_bands}")
         ch, ln, off = self.cond_layout(L)
         total = off[-1] + ch[-1] * ln[-1]
         out = torch.empty(cb * total, dtype=torch.float32, device=self.device)
-        for p, Hc, l, o in zip(prefixes, ch, ln, off):
-            m = mel.unsqueeze(1)
-            for i in range(2):
-                v = sd[f"{p}upsample_conv2d.{i}.weight_v"].to(self.device, torch.float32)
-                g = sd[f"{p}upsample_conv2d.{i}.weight_g"].to(self.device, torch.float32)
-                s = v.shape[-1] // 2
-                m = F.leaky_relu(F.conv_transpose2d(m, _fold(v, g), sd[f"{p}upsample_conv2d.{i}.bias"].to(self.device),
-                                                    stride=(1, s), padding=(1, s // 2)), 0.4)
-            m = m.squeeze(1)
-            if m.shape[-1] < l:
-                raise RuntimeError(f"upsampled mel has {m.shape[-1]} samples < {l}")
-            w = _fold(sd[p + "mel_conv.conv.weight_v"].to(self.device, torch.float32),
-                      sd[p + "mel_conv.conv.weight_g"].to(self.device, torch.float32))[:, :, 0]
-            f = torch.einsum("mk,bkl->bml", w, m[:, :, :l]) + sd[p + "mel_conv.conv.bias"].to(self.device)[None, :, None]
-            out[cb * o: cb * o + cb * Hc * l] = f.reshape(-1)
+        with torch.cuda.device(self.device):
+            check(lib().dwb_plan_cond_features(self._plan, ptr(mel), cb, frames, L, ptr(out), stream_ptr(self.device)))
         self._cond_cache = (key, out)
         return out
 

@@ -117,6 +117,15 @@ int dwb_sample(dwb_plan *plan, const float *x_T, const float *noise, const float
  * Pass NULL arrays to query n_blocks only. */
 int dwb_plan_cond_layout(dwb_plan *plan, int L, int *n_blocks, int *channels, int *lengths, int64_t *offsets);
 
+/* The t-independent conditioning features of every block from a mel spectrogram, in the layout above
+ * (models/sashimi.py:133-141,160-175; models/wavenet.py:62-70,98-111): per block two weight-normed
+ * ConvTranspose2d(1,1,(3,2s),stride (1,s),padding (1,s/2)) + leaky-ReLU(0.4), crop to the FIRST l_i
+ * samples, 1x1 mel_bands -> H_i.  Once per utterance; the result is what dwb_forward / dwb_sample take
+ * as `cond`.  mel (cond_batch, mel_bands, frames) f32 device; out: cond_batch * sum_i H_i l_i floats.
+ * Needs the blocks' upsample_conv2d.* / mel_conv.* tensors (DWB_ERR_MISSING otherwise).  Synchronises. */
+int dwb_plan_cond_features(dwb_plan *plan, const float *mel, int cond_batch, int frames, int L, float *out,
+                           void *stream);
+
 /* ---- introspection / accounting ------------------------------------------------------ */
 /* kernels launched by this plan since creation (graph replays count their node launches) */
 int dwb_plan_launch_count(dwb_plan *plan, int64_t *count);
