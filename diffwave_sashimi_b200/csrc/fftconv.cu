@@ -277,21 +277,26 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
         }
         __syncthreads();
     } else {
-        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;      // coefficients come from L2: one iteration ahead
-        if (tid <= M / 2) {
-            c0 = __ldg(kcr + 2 * tid);
-            c1 = __ldg(kcr + 2 * tid + 1);
-        }
+        // coefficients come from L2 (32 B per pair): GRP iterations' worth are requested at once, so a thread
+        // exposes (M/2)/(NT GRP) round trips instead of (M/2)/NT
+        constexpr int GRP = 4;
 #pragma unroll 1
-        for (int idx = tid; idx <= M / 2; idx += NT) {
-            float4 n0 = c0, n1 = c1;
-            if (idx + NT <= M / 2) {
-                n0 = __ldg(kcr + 2 * (idx + NT));
-                n1 = __ldg(kcr + 2 * (idx + NT) + 1);
+        for (int idx0 = tid; idx0 <= M / 2; idx0 += GRP * NT) {
+            float4 c0[GRP], c1[GRP];
+#pragma unroll
+            for (int u = 0; u < GRP; ++u) {
+                const int idx = idx0 + u * NT;
+                c0[u] = c1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx <= M / 2) {
+                    c0[u] = __ldg(kcr + 2 * idx);
+                    c1[u] = __ldg(kcr + 2 * idx + 1);
+                }
             }
-            pointwise_smem<LOG2M>(s, idx, c0, c1);
-            c0 = n0;
-            c1 = n1;
+#pragma unroll
+            for (int u = 0; u < GRP; ++u) {
+                const int idx = idx0 + u * NT;
+                if (idx <= M / 2) pointwise_smem<LOG2M>(s, idx, c0[u], c1[u]);
+            }
         }
         __syncthreads();
     }
