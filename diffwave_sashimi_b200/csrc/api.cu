@@ -402,6 +402,10 @@ static int finalize_sashimi(dwb_plan *p, cudaStream_t st) {
                 p->launches += 1;
                 const float2 *tw;
                 TRY(fft_twiddles(lg, st, &tw));
+                if (fft_table_mode(lg, l) == 2) {            // created here: not allowed during graph capture
+                    const float2 *tw2;
+                    TRY(fft_pair_twiddles(lg, st, &tw2));
+                }
                 o.k32 = (float *)k32; o.kf = (float *)kf;
                 TRY(scalar_of(p, o.prefix + "norm1.m", &o.ln1_m, st));
                 TRY(scalar_of(p, o.prefix + "norm1.s", &o.ln1_s, st));

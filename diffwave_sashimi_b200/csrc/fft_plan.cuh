@@ -61,6 +61,16 @@ inline bool fft_use_v2(int log2M) {
     return fft_forced_variant() != 1 && (log2M == 14 || (s12 && log2M == 12));
 }
 
+// Layout of the cached pointwise table (kcoef kernels in s4_kernelgen.cu): 0 = v1 (one transform), 1 = split,
+// 64 B per conjugate pair (the four products alpha..delta), 2 = split + compact, 16 B per pair (sum and
+// difference of the two spectrum values; the pair's twiddle comes from a small shared table) — only the
+// packed kernel at n = 32768 reads it.  DWB_FFT_WIDE=1 keeps mode 1 there (A/B measurements).
+inline int fft_table_mode(int log2M, int l) {
+    static const bool wide = getenv("DWB_FFT_WIDE") != nullptr;
+    if (!fft_use_v2(log2M)) return 0;
+    return (log2M == 14 && (l % 4) == 0 && fft_forced_variant() != 2 && !wide) ? 2 : 1;
+}
+
 // shared-memory padding: one float2 of slack per 16 so that the stride-16 and stride-1
 // passes (16 consecutive elements per thread) are bank-conflict free
 __host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 4); }

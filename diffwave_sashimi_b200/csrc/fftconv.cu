@@ -590,6 +590,7 @@ __global__ void twiddle_kernel(float2 *tw, int log2M) {
 struct TwiddleCache {
     std::mutex mu;
     float2 *tw[16][FFT_MAX_LOG2M + 1] = {};
+    float2 *tw2[16][FFT_MAX_LOG2M + 1] = {};      // per-item pair twiddles of the compact pointwise table
 };
 static TwiddleCache g_tw;
 
@@ -612,6 +613,29 @@ int fft_twiddles(int log2M, cudaStream_t st, const float2 **tw) {
         g_tw.tw[dev][log2M] = a;
     }
     *tw = g_tw.tw[dev][log2M];
+    return DWB_OK;
+}
+
+int fft_pair_twiddles_launch(float2 *tw2, int log2M, cudaStream_t st);   // s4_kernelgen.cu
+
+int fft_pair_twiddles(int log2M, cudaStream_t st, const float2 **tw2) {
+    int dev = 0;
+    DWB_CUDA(cudaGetDevice(&dev));
+    DWB_REQUIRE(dev >= 0 && dev < 16, DWB_ERR_UNSUPPORTED, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_tw.mu);
+    if (!g_tw.tw2[dev][log2M]) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        DWB_CUDA(cudaStreamIsCapturing(st, &cs));
+        DWB_REQUIRE(cs == cudaStreamCaptureStatusNone, DWB_ERR_STATE,
+                    "fft pair-twiddle table for M=2^%d must be created before stream capture", log2M);
+        float2 *a = nullptr;
+        DWB_CUDA(cudaMalloc(&a, (size_t)((1 << log2M) / 8) * sizeof(float2)));
+        int rc = fft_pair_twiddles_launch(a, log2M, st);
+        if (rc != DWB_OK) return rc;
+        DWB_CUDA(cudaStreamSynchronize(st));
+        g_tw.tw2[dev][log2M] = a;
+    }
+    *tw2 = g_tw.tw2[dev][log2M];
     return DWB_OK;
 }
 
@@ -655,8 +679,17 @@ int fftconv_launch(const float *x, const float *stats, const float *part_t, long
     int rc = fft_twiddles(lg, st, &tw);
     if (rc != DWB_OK) return rc;
     if (fft_use_v2(lg)) {
+        const int mode = fft_table_mode(lg, l);
+        if (mode == 2) {
+            DWB_REQUIRE(fftconv3_supported(lg, x, stats, g, l), DWB_ERR_UNSUPPORTED,
+                        "fftconv: rows of the n = %d stage must be 16-byte aligned", 2 << lg);
+            const float2 *tw2;
+            rc = fft_pair_twiddles(lg, st, &tw2);
+            if (rc != DWB_OK) return rc;
+            return fftconv3_launch(lg, x, stats, part_t, psb, ln_m, ln_s, kc, tw, tw2, g, scratch, B, H, l, st);
+        }
         if (fft_forced_variant() != 2 && fftconv3_supported(lg, x, stats, g, l))
-            return fftconv3_launch(lg, x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, scratch, B, H, l, st);
+            return fftconv3_launch(lg, x, stats, part_t, psb, ln_m, ln_s, kc, tw, nullptr, g, scratch, B, H, l, st);
         switch (lg) {
             case 10: return launch_fftconv2<10>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
             case 11: return launch_fftconv2<11>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);

@@ -115,11 +115,12 @@ __device__ __forceinline__ void mid_passes(float *re, float *im, const float *mr
     }
 }
 
-template <int LOG2M>
+template <int LOG2M, bool COMPACT>
 __global__ void __launch_bounds__(Fft3Cfg<LOG2M>::NT, Fft3Cfg<LOG2M>::MINB)
 fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
                 long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
-                const float2 *__restrict__ tw /* W_n^i, i < M */, float *g, float *scratch, int B, int H, int l, int resident) {
+                const float2 *__restrict__ tw /* W_n^i, i < M */, const float2 *__restrict__ tw2, float *g, float *scratch, int B, int H,
+                int l, int resident) {
     using Cfg = Fft3Cfg<LOG2M>;
     constexpr int LH = Cfg::LH, Mh = Cfg::Mh, NT = Cfg::NT, NP = Cfg::NP, RL = Cfg::RL;
     constexpr int log2sub0 = LH - 4, sub0 = 1 << log2sub0;         // outer pass: radix 16, span Mh
@@ -244,7 +245,67 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
         mid_passes<LH, false, 1, NP - 2, 0>(re, im, midr, midi, tid);
 
         // ---- centre (scalar): last forward pass + untangle/product/re-tangle + first inverse pass
-        {
+        if constexpr (COMPACT) {
+            // compact table (16 B per pair): all of a thread's items are requested in one round trip
+            static_assert(!COMPACT || RL == 1, "compact table needs the radix-2 centre");
+            constexpr int R = 2, G = Mh / R, NITEM = Mh / (2 * R), IPT = NITEM / NT;
+            const float4 *kh = kcr + (odd ? 2 * NITEM : 0);
+            const float2 w1 = __ldg(tw + 1);                        // W_n^1: odd half frequencies are k + 1
+            float4 sa[IPT], sb[IPT];
+            float2 wv[IPT];
+#pragma unroll
+            for (int u = 0; u < IPT; ++u) {
+                const int item = tid + u * NT;
+                sa[u] = __ldg(kh + 2 * item);
+                sb[u] = __ldg(kh + 2 * item + 1);
+                wv[u] = __ldg(tw2 + item);
+            }
+#pragma unroll
+            for (int u = 0; u < IPT; ++u) {
+                const int item = tid + u * NT;
+                const int ga = 2 * item;
+                const int gb = odd ? (ga ^ (G - 1)) : (ga == 0 ? 1 : ga ^ ((1 << (31 - __clz(ga))) - 1));
+                const int pa = padf(R * ga), pg = padf(R * gb);
+                const float2 ar = *reinterpret_cast<const float2 *>(re + pa), ai = *reinterpret_cast<const float2 *>(im + pa);
+                const float2 br = *reinterpret_cast<const float2 *>(re + pg), bi = *reinterpret_cast<const float2 *>(im + pg);
+                float2 xa[2] = {make_float2(ar.x, ai.x), make_float2(ar.y, ai.y)};
+                float2 xb[2] = {make_float2(br.x, bi.x), make_float2(br.y, bi.y)};
+                Radix<2, false>::run(xa);
+                Radix<2, false>::run(xb);
+                if (!odd && item == 0) {
+                    const float4 *sp = kcr + 4 * NITEM;             // 64 B forms: DC/Nyquist, slot 1, group 1
+                    const float4 dc = __ldg(sp);
+                    const float2 a = xa[0];
+                    const float p0 = 2.f * (a.x + a.y) * dc.x, pM = 2.f * (a.x - a.y) * dc.y;
+                    xa[0] = make_float2(p0 + pM, p0 - pM);
+                    float2 d = xa[1];
+                    pair_map(xa[1], d, __ldg(sp + 1), __ldg(sp + 2));
+                    pair_map(xb[0], xb[1], __ldg(sp + 3), __ldg(sp + 4));
+                } else {
+                    const float2 wa = odd ? cmul(wv[u], w1) : wv[u];
+                    // pair A: w = wa;  pair B: w = -i conj(wa) = (-wa.y, -wa.x)
+                    {
+                        const float4 c0 = make_float4(fmaf(wa.y, sa[u].z, sa[u].x), fmaf(wa.y, sa[u].w, sa[u].y), -wa.x * sa[u].w, wa.x * sa[u].z);
+                        const float4 c1 = make_float4(-c0.z, -c0.w, fmaf(-wa.y, sa[u].z, sa[u].x), fmaf(-wa.y, sa[u].w, sa[u].y));
+                        pair_map(xa[0], xb[1], c0, c1);
+                    }
+                    {
+                        const float wc = -wa.y, ws = -wa.x;
+                        const float4 c0 = make_float4(fmaf(ws, sb[u].z, sb[u].x), fmaf(ws, sb[u].w, sb[u].y), -wc * sb[u].w, wc * sb[u].z);
+                        const float4 c1 = make_float4(-c0.z, -c0.w, fmaf(-ws, sb[u].z, sb[u].x), fmaf(-ws, sb[u].w, sb[u].y));
+                        pair_map(xb[0], xa[1], c0, c1);
+                    }
+                }
+                Radix<2, true>::run(xa);
+                Radix<2, true>::run(xb);
+                *reinterpret_cast<float2 *>(re + pa) = make_float2(xa[0].x, xa[1].x);
+                *reinterpret_cast<float2 *>(im + pa) = make_float2(xa[0].y, xa[1].y);
+                *reinterpret_cast<float2 *>(re + pg) = make_float2(xb[0].x, xb[1].x);
+                *reinterpret_cast<float2 *>(im + pg) = make_float2(xb[0].y, xb[1].y);
+            }
+            __syncthreads();
+        } else {
+
             constexpr int R = 1 << RL, G = Mh / R, NITEM = Mh / (2 * R);
             const float4 *kh = odd ? kcr + (Mh + 2) : kcr;          // odd half: entries Mh/2 + 1 ...
             auto partner = [&](int ga) {
@@ -374,22 +435,22 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
     }
 }
 
-template <int LOG2M>
+template <int LOG2M, bool COMPACT>
 static int launch_fftconv3(const float *x, const float *stats, const float *part_t, long long psb, float ln_m,
-                           float ln_s, const float *kc, const float2 *tw, float *g, float *scratch, int B, int H, int l,
-                           cudaStream_t st) {
+                           float ln_s, const float *kc, const float2 *tw, const float2 *tw2, float *g, float *scratch, int B, int H,
+                           int l, cudaStream_t st) {
     using Cfg = Fft3Cfg<LOG2M>;
     static bool attr_set[16] = {};
     int dev = 0;
     DWB_CUDA(cudaGetDevice(&dev));
     if (Cfg::SMEM > 48 * 1024 && !attr_set[dev & 15]) {
-        DWB_CUDA(cudaFuncSetAttribute(fftconv3_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        DWB_CUDA(cudaFuncSetAttribute((fftconv3_kernel<LOG2M, COMPACT>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_set[dev & 15] = true;
     }
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    fftconv3_kernel<LOG2M><<<dim3(B * H, 1, 1), Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw, g,
-                                                                        scratch, B, H, l, nsm * Cfg::MINB);
+    fftconv3_kernel<LOG2M, COMPACT><<<dim3(B * H, 1, 1), Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw,
+                                                                                 tw2, g, scratch, B, H, l, nsm * Cfg::MINB);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
 }
@@ -400,11 +461,16 @@ bool fftconv3_supported(int lg, const float *x, const float *stats, const float 
 }
 
 int fftconv3_launch(int lg, const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
-                    const float *kc, const float2 *tw, float *g, float *scratch, int B, int H, int l, cudaStream_t st) {
+                    const float *kc, const float2 *tw, const float2 *tw2, float *g, float *scratch, int B, int H, int l,
+                    cudaStream_t st) {
     if (((uintptr_t)scratch & 15) != 0) scratch = nullptr;
+    if (tw2) {
+        DWB_REQUIRE(lg == 14, DWB_ERR_UNSUPPORTED, "fftconv3: compact table only at n = 32768");
+        return launch_fftconv3<14, true>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, tw2, g, scratch, B, H, l, st);
+    }
     switch (lg) {
-        case 12: return launch_fftconv3<12>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, scratch, B, H, l, st);
-        case 14: return launch_fftconv3<14>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, scratch, B, H, l, st);
+        case 12: return launch_fftconv3<12, false>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, nullptr, g, scratch, B, H, l, st);
+        case 14: return launch_fftconv3<14, false>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, nullptr, g, scratch, B, H, l, st);
     }
     set_error("fftconv3: no kernel for log2M=%d", lg);
     return DWB_ERR_UNSUPPORTED;

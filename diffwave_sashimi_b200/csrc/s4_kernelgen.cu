@@ -273,6 +273,77 @@ __global__ void kcoef_kernel(const double2 *__restrict__ Kd, int log2M, int spli
     o[7] = (float)(K1.y * v2 + K2.y * u2);
 }
 
+// Compact table (fft_table_mode == 2; split transform with a radix-2 centre, i.e. log2M - 1 = 1 mod 4).
+// With K1 = K'[k], K2 = conj(K'[M-k]), w = e^{-2 pi i k/n} = (wc, ws):  alpha = S + ws D, delta = S - ws D,
+// beta = i wc D, gamma = -beta, where S = 2 (K1 + K2), D = 2 (K1 - K2).  Per half transform and centre item
+// (groups ga = 2 item, gb = partner(ga)) two float4 (S, D): pair A led by slot 2 ga, pair B led by slot 2 gb;
+// k_B = n/4 - k_A, so w_B = -i conj(w_A) and one twiddle per item suffices (pair_twiddle_kernel).
+// float4 layout per channel: [0, 2 NI) even half, [2 NI, 4 NI) odd half, then 5 entries in the 64 B form for
+// item 0 of the even half: (K'[0], K'[M]), the self-paired slot 1 (two float4), group 1 (two float4).
+__device__ inline void kcoef_full(const double2 *K, int M, int k, float *o) {
+    const int n = 2 * M;
+    const double2 K1 = K[k], K2 = make_double2(K[M - k].x, -K[M - k].y);
+    double ws, wc;
+    sincospi(-2.0 * (double)k / (double)n, &ws, &wc);
+    const double S[2] = {2.0 * (K1.x + K2.x), 2.0 * (K1.y + K2.y)}, D[2] = {2.0 * (K1.x - K2.x), 2.0 * (K1.y - K2.y)};
+    o[0] = (float)(S[0] + ws * D[0]);
+    o[1] = (float)(S[1] + ws * D[1]);
+    o[2] = (float)(-wc * D[1]);
+    o[3] = (float)(wc * D[0]);
+    o[4] = -o[2];
+    o[5] = -o[3];
+    o[6] = (float)(S[0] - ws * D[0]);
+    o[7] = (float)(S[1] - ws * D[1]);
+}
+__global__ void kcoef_compact_kernel(const double2 *__restrict__ Kd, int log2M, float *__restrict__ kc) {
+    const int M = 1 << log2M, LH = log2M - 1, Mh = M / 2, G = Mh / 2, NI = Mh / 4;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, h = blockIdx.y;
+    if (t >= 2 * NI) return;
+    const int odd = t / NI, item = t - odd * NI;
+    const double2 *K = Kd + (size_t)h * (M + 1);
+    float *base = kc + (size_t)h * (M / 2 + 1) * 8;
+    float *o = base + ((size_t)odd * 2 * NI + 2 * item) * 4;
+    const int ga = 2 * item;
+    const int gb = odd ? (ga ^ (G - 1)) : (ga == 0 ? 1 : ga ^ ((1 << (31 - __clz(ga))) - 1));
+    const int lead[2] = {2 * ga, 2 * gb};
+    for (int q = 0; q < 2; ++q) {
+        const int k = 2 * fft_freq(lead[q], LH) + odd;
+        if (k == 0) {                       // even half, item 0, pair A: DC / Nyquist live in the special block
+            o[4 * q] = o[4 * q + 1] = o[4 * q + 2] = o[4 * q + 3] = 0.f;
+            continue;
+        }
+        const double2 K1 = K[k], K2 = make_double2(K[M - k].x, -K[M - k].y);
+        o[4 * q] = (float)(2.0 * (K1.x + K2.x));
+        o[4 * q + 1] = (float)(2.0 * (K1.y + K2.y));
+        o[4 * q + 2] = (float)(2.0 * (K1.x - K2.x));
+        o[4 * q + 3] = (float)(2.0 * (K1.y - K2.y));
+    }
+    if (t == 0) {
+        float *sp = base + (size_t)4 * NI * 4;
+        sp[0] = (float)K[0].x;
+        sp[1] = (float)K[M].x;
+        sp[2] = sp[3] = 0.f;
+        kcoef_full(K, M, 2 * fft_freq(1, LH), sp + 4);          // slot 1: k = M/2, self-paired
+        kcoef_full(K, M, 2 * fft_freq(2, LH), sp + 12);         // group 1: slots 2 (leader), 3
+    }
+}
+// W_n^{k_A(item)} for the even half, k_A = 2 bitrev_{LH}(4 item)
+__global__ void pair_twiddle_kernel(float2 *tw2, int log2M) {
+    const int M = 1 << log2M, LH = log2M - 1, NI = M / 8;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= NI) return;
+    const int k = 2 * fft_freq(4 * item, LH);
+    double sn, cs;
+    sincospi(-2.0 * (double)k / (double)(2 * M), &sn, &cs);
+    tw2[item] = make_float2((float)cs, (float)sn);
+}
+int fft_pair_twiddles_launch(float2 *tw2, int log2M, cudaStream_t st) {
+    const int NI = (1 << log2M) / 8;
+    pair_twiddle_kernel<<<ceil_div(NI, 256), 256, 0, st>>>(tw2, log2M);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
 template <typename T>
 static int fftconv_prepare_any(const T *k, const float *D, int H, int l, float *kc, cudaStream_t st) {
     const int log2M = fft_log2m_for(l);
@@ -283,7 +354,9 @@ static int fftconv_prepare_any(const T *k, const float *D, int H, int l, float *
     kf_kernel<T><<<dim3(ceil_div(M + 1, DFT_THREADS), H), DFT_THREADS, 0, st>>>(k, D, H, l, log2M, Kd);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
-        kcoef_kernel<<<dim3(ceil_div(M / 2 + 1, 256), H), 256, 0, st>>>(Kd, log2M, fft_use_v2(log2M) ? 1 : 0, kc);
+        const int mode = fft_table_mode(log2M, l);
+        if (mode == 2) kcoef_compact_kernel<<<dim3(ceil_div(M / 2, 256), H), 256, 0, st>>>(Kd, log2M, kc);
+        else kcoef_kernel<<<dim3(ceil_div(M / 2 + 1, 256), H), 256, 0, st>>>(Kd, log2M, mode, kc);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
