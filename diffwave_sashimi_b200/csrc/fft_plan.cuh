@@ -62,7 +62,7 @@ inline bool fft_use_v2(int log2M) {
 }
 
 // Layout of the cached pointwise table (kcoef kernels in s4_kernelgen.cu): 0 = v1 (one transform), 1 = split,
-// 64 B per conjugate pair (the four products alpha..delta), 2 = split + compact, 16 B per pair (sum and
+// 32 B per conjugate pair (the four products alpha..delta), 2 = split + compact, 16 B per pair (sum and
 // difference of the two spectrum values; the pair's twiddle comes from a small shared table) — only the
 // packed kernel at n = 32768 reads it.  DWB_FFT_WIDE=1 keeps mode 1 there (A/B measurements).
 inline int fft_table_mode(int log2M, int l) {

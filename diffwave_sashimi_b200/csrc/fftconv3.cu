@@ -273,7 +273,7 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
                 Radix<2, false>::run(xa);
                 Radix<2, false>::run(xb);
                 if (!odd && item == 0) {
-                    const float4 *sp = kcr + 4 * NITEM;             // 64 B forms: DC/Nyquist, slot 1, group 1
+                    const float4 *sp = kcr + 4 * NITEM;             // 32 B forms: DC/Nyquist, slot 1, group 1
                     const float4 dc = __ldg(sp);
                     const float2 a = xa[0];
                     const float p0 = 2.f * (a.x + a.y) * dc.x, pM = 2.f * (a.x - a.y) * dc.y;

@@ -278,7 +278,7 @@ __global__ void kcoef_kernel(const double2 *__restrict__ Kd, int log2M, int spli
 // beta = i wc D, gamma = -beta, where S = 2 (K1 + K2), D = 2 (K1 - K2).  Per half transform and centre item
 // (groups ga = 2 item, gb = partner(ga)) two float4 (S, D): pair A led by slot 2 ga, pair B led by slot 2 gb;
 // k_B = n/4 - k_A, so w_B = -i conj(w_A) and one twiddle per item suffices (pair_twiddle_kernel).
-// float4 layout per channel: [0, 2 NI) even half, [2 NI, 4 NI) odd half, then 5 entries in the 64 B form for
+// float4 layout per channel: [0, 2 NI) even half, [2 NI, 4 NI) odd half, then 5 float4 in the 32 B form for
 // item 0 of the even half: (K'[0], K'[M]), the self-paired slot 1 (two float4), group 1 (two float4).
 __device__ inline void kcoef_full(const double2 *K, int M, int k, float *o) {
     const int n = 2 * M;
