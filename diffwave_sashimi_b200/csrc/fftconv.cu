@@ -691,8 +691,6 @@ int fftconv_launch(const float *x, const float *stats, const float *part_t, long
         if (fft_forced_variant() != 2 && fftconv3_supported(lg, x, stats, g, l))
             return fftconv3_launch(lg, x, stats, part_t, psb, ln_m, ln_s, kc, tw, nullptr, g, scratch, B, H, l, st);
         switch (lg) {
-            case 10: return launch_fftconv2<10>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
-            case 11: return launch_fftconv2<11>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
             case 12: return launch_fftconv2<12>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
             case 14: return launch_fftconv2<14>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
         }
