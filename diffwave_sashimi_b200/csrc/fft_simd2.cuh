@@ -72,21 +72,26 @@ __device__ __forceinline__ C2 cconj(const C2 &a) {
 }
 
 // ---- radix-R DFT in registers, natural order in and out (same recursion as Radix<> in fft_radix.cuh)
-template <int R, bool INV>
+// ZHI: inputs x[R/2..R) are zero and are not read
+template <int R, bool INV, bool ZHI = false>
 struct RadixS {
     static __device__ __forceinline__ void run(C2 *x) {
+        if constexpr (R == 2 && ZHI) {
+            x[1] = x[0];
+            return;
+        }
         constexpr float WR[8] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
                                  0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
         constexpr float WI[8] = {0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
                                  -1.0f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
         C2 e[R / 2], o[R / 2];
 #pragma unroll
-        for (int i = 0; i < R / 2; ++i) {
+        for (int i = 0; i < (ZHI ? R / 4 : R / 2); ++i) {
             e[i] = x[2 * i];
             o[i] = x[2 * i + 1];
         }
-        RadixS<R / 2, INV>::run(e);
-        RadixS<R / 2, INV>::run(o);
+        RadixS<R / 2, INV, ZHI>::run(e);
+        RadixS<R / 2, INV, ZHI>::run(o);
 #pragma unroll
         for (int q = 0; q < R / 2; ++q) {
             constexpr int step = 16 / R;
@@ -115,8 +120,8 @@ struct RadixS {
         }
     }
 };
-template <bool INV>
-struct RadixS<1, INV> {
+template <bool INV, bool ZHI>
+struct RadixS<1, INV, ZHI> {
     static __device__ __forceinline__ void run(C2 *) {}
 };
 
@@ -138,6 +143,14 @@ __device__ __forceinline__ void apply_twiddles16(C2 (&x)[16], const C2 u0, const
         if (HASBASE || q > 0) x[q] = cmul(x[q], u[q]);
         x[8 + q] = cmul(x[8 + q], (HASBASE || q > 0) ? cmul(v8, u[q]) : v8);
     }
+}
+
+// x[q] *= v^q, q < 4
+__device__ __forceinline__ void apply_twiddles4(C2 (&x)[4], const C2 v) {
+    const C2 v2 = cmul(v, v);
+    x[1] = cmul(x[1], v);
+    x[2] = cmul(x[2], v2);
+    x[3] = cmul(x[3], cmul(v2, v));
 }
 
 // x[p] *= W_32^{+-p}, p < 16 (forward: -, inverse: +)

@@ -695,6 +695,11 @@ int fftconv_launch(const float *x, const float *stats, const float *part_t, long
             case 14: return launch_fftconv2<14>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
         }
     }
+    {
+        static const bool v5 = getenv("DWB_FFT5") != nullptr;       // experiment: unsplit packed kernel at n <= 8192
+        if (v5 && !fft_use_v2(lg) && fft_forced_variant() != 1 && fftconv5_supported(lg, x, stats, g, l))
+            return fftconv5_launch(lg, x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+    }
 #define DWB_FFT_CASE(LG) \
     case LG:             \
         return launch_fftconv<LG>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);

@@ -115,6 +115,96 @@ __device__ __forceinline__ void mid_passes(float *re, float *im, const float *mr
     }
 }
 
+// Scalar centre on the planes with the 32 B/pair table: last forward pass (radix 2^RL, sub = 1) + untangle/product/
+// re-tangle + first inverse pass of an N-point (half) transform.  kh: table base of this transform (two float4 per
+// leader slot pair, R float4 per group); kspecial: its self-paired entry N/2; odd: odd-half pairing (complement
+// groups, no DC / self-paired slots).
+template <int N, int RL, int NT>
+__device__ __forceinline__ void centre_wide(float *re, float *im, const float4 *kh, const float4 *kspecial, const bool odd,
+                                            const int tid) {
+    constexpr int R = 1 << RL, G = N / R, NITEM = N / (2 * R);
+    auto partner = [&](int ga) {
+        return odd ? (ga ^ (G - 1)) : (ga == 0 ? 1 : ga ^ ((1 << (31 - __clz(ga))) - 1));
+    };
+    auto load_coef = [&](int item, float4 (&ca)[R], float4 (&cb)[R]) {
+        const float4 *ka = kh + (size_t)R * (2 * item), *kb = kh + (size_t)R * partner(2 * item);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            ca[i] = __ldg(ka + i);
+            cb[i] = __ldg(kb + i);
+        }
+    };
+    // coefficients come from L2 (16 B per point, shared by the rows of a channel): GRP items' worth (64
+    // registers) are requested at once, so a thread exposes IPT / GRP round trips instead of IPT
+    constexpr int IPT = NITEM / NT, GRP = 8 / R;
+    static_assert(IPT % GRP == 0, "centre grouping");
+#pragma unroll 1
+    for (int k0 = 0; k0 < IPT; k0 += GRP) {
+        float4 ca[GRP][R], cb[GRP][R];
+#pragma unroll
+        for (int u = 0; u < GRP; ++u) load_coef(tid + (k0 + u) * NT, ca[u], cb[u]);
+#pragma unroll
+        for (int u = 0; u < GRP; ++u) {
+            const int item = tid + (k0 + u) * NT;
+            const int ga = 2 * item, gb = partner(ga);
+            const int pa = padf(R * ga), pg = padf(R * gb);
+            float2 xa[R], xb[R];
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) {
+                const float2 ar = *reinterpret_cast<const float2 *>(re + pa + 2 * k);
+                const float2 ai = *reinterpret_cast<const float2 *>(im + pa + 2 * k);
+                const float2 br = *reinterpret_cast<const float2 *>(re + pg + 2 * k);
+                const float2 bi = *reinterpret_cast<const float2 *>(im + pg + 2 * k);
+                xa[2 * k] = make_float2(ar.x, ai.x);
+                xa[2 * k + 1] = make_float2(ar.y, ai.y);
+                xb[2 * k] = make_float2(br.x, bi.x);
+                xb[2 * k + 1] = make_float2(br.y, bi.y);
+            }
+            Radix<R, false>::run(xa);
+            Radix<R, false>::run(xb);
+            if (!odd && item == 0) {
+                const float4 s0 = __ldg(kspecial), s1 = __ldg(kspecial + 1);
+                {
+                    const float2 a = xa[0];
+                    const float p0 = 2.f * (a.x + a.y) * ca[u][0].x, pM = 2.f * (a.x - a.y) * ca[u][0].y;
+                    xa[0] = make_float2(p0 + pM, p0 - pM);
+                    float2 d = xa[R / 2];
+                    pair_map(xa[R / 2], d, s0, s1);
+                }
+#pragma unroll
+                for (int c = 2; c < R; c += 2) {
+                    int msb = 0;
+                    while ((2 << msb) <= c) ++msb;
+                    const int c2 = c ^ ((1 << msb) - 1);
+                    pair_map(xa[fft_brev(c, RL)], xa[fft_brev(c2, RL)], ca[u][c], ca[u][c + 1]);
+                }
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) {
+                    const int e = fft_brev(q, RL) >> 1;
+                    pair_map(xb[q], xb[q ^ (R - 1)], cb[u][2 * e], cb[u][2 * e + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) {
+                    const int e = fft_brev(q, RL) >> 1;
+                    pair_map(xa[q], xb[q ^ (R - 1)], ca[u][2 * e], ca[u][2 * e + 1]);
+                    pair_map(xb[q], xa[q ^ (R - 1)], cb[u][2 * e], cb[u][2 * e + 1]);
+                }
+            }
+            Radix<R, true>::run(xa);
+            Radix<R, true>::run(xb);
+#pragma unroll
+            for (int k = 0; k < R / 2; ++k) {
+                *reinterpret_cast<float2 *>(re + pa + 2 * k) = make_float2(xa[2 * k].x, xa[2 * k + 1].x);
+                *reinterpret_cast<float2 *>(im + pa + 2 * k) = make_float2(xa[2 * k].y, xa[2 * k + 1].y);
+                *reinterpret_cast<float2 *>(re + pg + 2 * k) = make_float2(xb[2 * k].x, xb[2 * k + 1].x);
+                *reinterpret_cast<float2 *>(im + pg + 2 * k) = make_float2(xb[2 * k].y, xb[2 * k + 1].y);
+            }
+        }
+    }
+    __syncthreads();
+}
+
 template <int LOG2M, bool COMPACT>
 __global__ void __launch_bounds__(Fft3Cfg<LOG2M>::NT, Fft3Cfg<LOG2M>::MINB)
 fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
@@ -305,89 +395,7 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
             }
             __syncthreads();
         } else {
-
-            constexpr int R = 1 << RL, G = Mh / R, NITEM = Mh / (2 * R);
-            const float4 *kh = odd ? kcr + (Mh + 2) : kcr;          // odd half: entries Mh/2 + 1 ...
-            auto partner = [&](int ga) {
-                return odd ? (ga ^ (G - 1)) : (ga == 0 ? 1 : ga ^ ((1 << (31 - __clz(ga))) - 1));
-            };
-            auto load_coef = [&](int item, float4 (&ca)[R], float4 (&cb)[R]) {
-                const float4 *ka = kh + (size_t)R * (2 * item), *kb = kh + (size_t)R * partner(2 * item);
-#pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    ca[i] = __ldg(ka + i);
-                    cb[i] = __ldg(kb + i);
-                }
-            };
-            // coefficients come from L2 (16 B per point, shared by the rows of a channel): GRP items' worth (64
-            // registers) are requested at once, so a thread exposes IPT / GRP round trips instead of IPT
-            constexpr int IPT = NITEM / NT, GRP = 8 / R;
-            static_assert(IPT % GRP == 0, "centre grouping");
-#pragma unroll 1
-            for (int k0 = 0; k0 < IPT; k0 += GRP) {
-                float4 ca[GRP][R], cb[GRP][R];
-#pragma unroll
-                for (int u = 0; u < GRP; ++u) load_coef(tid + (k0 + u) * NT, ca[u], cb[u]);
-#pragma unroll
-                for (int u = 0; u < GRP; ++u) {
-                    const int item = tid + (k0 + u) * NT;
-                    const int ga = 2 * item, gb = partner(ga);
-                    const int pa = padf(R * ga), pg = padf(R * gb);
-                    float2 xa[R], xb[R];
-#pragma unroll
-                    for (int k = 0; k < R / 2; ++k) {
-                        const float2 ar = *reinterpret_cast<const float2 *>(re + pa + 2 * k);
-                        const float2 ai = *reinterpret_cast<const float2 *>(im + pa + 2 * k);
-                        const float2 br = *reinterpret_cast<const float2 *>(re + pg + 2 * k);
-                        const float2 bi = *reinterpret_cast<const float2 *>(im + pg + 2 * k);
-                        xa[2 * k] = make_float2(ar.x, ai.x);
-                        xa[2 * k + 1] = make_float2(ar.y, ai.y);
-                        xb[2 * k] = make_float2(br.x, bi.x);
-                        xb[2 * k + 1] = make_float2(br.y, bi.y);
-                    }
-                    Radix<R, false>::run(xa);
-                    Radix<R, false>::run(xb);
-                    if (!odd && item == 0) {
-                        const float4 s0 = __ldg(kcr + Mh), s1 = __ldg(kcr + Mh + 1);
-                        {
-                            const float2 a = xa[0];
-                            const float p0 = 2.f * (a.x + a.y) * ca[u][0].x, pM = 2.f * (a.x - a.y) * ca[u][0].y;
-                            xa[0] = make_float2(p0 + pM, p0 - pM);
-                            float2 d = xa[R / 2];
-                            pair_map(xa[R / 2], d, s0, s1);
-                        }
-#pragma unroll
-                        for (int c = 2; c < R; c += 2) {
-                            int msb = 0;
-                            while ((2 << msb) <= c) ++msb;
-                            const int c2 = c ^ ((1 << msb) - 1);
-                            pair_map(xa[fft_brev(c, RL)], xa[fft_brev(c2, RL)], ca[u][c], ca[u][c + 1]);
-                        }
-#pragma unroll
-                        for (int q = 0; q < R / 2; ++q) {
-                            const int e = fft_brev(q, RL) >> 1;
-                            pair_map(xb[q], xb[q ^ (R - 1)], cb[u][2 * e], cb[u][2 * e + 1]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < R / 2; ++q) {
-                            const int e = fft_brev(q, RL) >> 1;
-                            pair_map(xa[q], xb[q ^ (R - 1)], ca[u][2 * e], ca[u][2 * e + 1]);
-                            pair_map(xb[q], xa[q ^ (R - 1)], cb[u][2 * e], cb[u][2 * e + 1]);
-                        }
-                    }
-                    Radix<R, true>::run(xa);
-                    Radix<R, true>::run(xb);
-#pragma unroll
-                    for (int k = 0; k < R / 2; ++k) {
-                        *reinterpret_cast<float2 *>(re + pa + 2 * k) = make_float2(xa[2 * k].x, xa[2 * k + 1].x);
-                        *reinterpret_cast<float2 *>(im + pa + 2 * k) = make_float2(xa[2 * k].y, xa[2 * k + 1].y);
-                        *reinterpret_cast<float2 *>(re + pg + 2 * k) = make_float2(xb[2 * k].x, xb[2 * k + 1].x);
-                        *reinterpret_cast<float2 *>(im + pg + 2 * k) = make_float2(xb[2 * k].y, xb[2 * k + 1].y);
-                    }
-                }
-            }
-            __syncthreads();
+            centre_wide<Mh, RL, NT>(re, im, odd ? kcr + (Mh + 2) : kcr, kcr + Mh, odd != 0, tid);
         }
 
         mid_passes<LH, true, 1, NP - 2, 0>(re, im, midr, midi, tid);
@@ -433,6 +441,215 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
         }
         __syncthreads();          // the next half overwrites the planes
     }
+}
+
+// =====================================================================================================
+// v5: the UNSPLIT transform on packed fp32 for n <= 8192 (M = 1024, 4096), where shared memory is not the
+// occupancy limit: v1's algorithm (one M-point transform per row; the zero upper half of the packed row folded
+// into the first radix-16 pass, only the first l outputs computed, no parked rows) with v3's arithmetic (two
+// butterflies per thread in the lanes of FADD2/FMUL2/FFMA2 over re/im planes).  Plan 16 . 16 (. 4) + the scalar
+// radix-4 centre on the v1 table (fft_table_mode 0).
+// =====================================================================================================
+template <int LOG2M>
+struct Fft5Cfg {
+    static_assert(LOG2M == 10 || LOG2M == 12, "v5 plan");
+    static constexpr int M = 1 << LOG2M;
+    static constexpr int NT = M / 32;                        // one butterfly pair per thread in the radix-16 passes
+    static constexpr bool MID4 = (LOG2M == 12);              // M = 4096: a radix-4 pass between pass 1 and the centre
+    static constexpr int PLANE = M + M / 16 + 2;
+    static constexpr int NTW0 = M / 16, NTW1 = M / 256, NTW2 = 4;            // W_M^j, W_{M/16}^j, W_16^j
+    static constexpr int SMEM = (2 * PLANE + 2 * (NTW0 + NTW1 + NTW2)) * (int)sizeof(float);
+    static constexpr int MINB = (512 / NT > 16) ? 16 : 512 / NT;
+};
+
+// in-place radix-4 pass of span 16 (sub = 4) over the planes: M/8 butterfly pairs, (M/8)/NT per thread
+template <int LOG2M, bool INV>
+__device__ __forceinline__ void mid4_pass(float *re, float *im, const float *twr, const float *twi, int tid) {
+    constexpr int M = 1 << LOG2M, NT = M / 32, NPAIR = M / 8;
+#pragma unroll 1
+    for (int pi = tid; pi < NPAIR; pi += NT) {
+        const int bi = 2 * pi, j = bi & 3;
+        const int pb = padf(((bi >> 2) << 4) + j);           // + 4 p stays inside the 16-float block: no extra padding
+        C2 w1;
+        w1.x = ld2(twr + j);
+        w1.y = ld2(twi + j);
+        if (INV) w1.y = -w1.y;
+        C2 x[4];
+        if (!INV) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                x[p].x = ld2(re + pb + 4 * p);
+                x[p].y = ld2(im + pb + 4 * p);
+            }
+            s2::RadixS<4, false>::run(x);
+            s2::apply_twiddles4(x, w1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                st2(re + pb + 4 * fft_brev(q, 2), x[q].x);
+                st2(im + pb + 4 * fft_brev(q, 2), x[q].y);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                x[q].x = ld2(re + pb + 4 * fft_brev(q, 2));
+                x[q].y = ld2(im + pb + 4 * fft_brev(q, 2));
+            }
+            s2::apply_twiddles4(x, w1);
+            s2::RadixS<4, true>::run(x);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                st2(re + pb + 4 * p, x[p].x);
+                st2(im + pb + 4 * p, x[p].y);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int LOG2M>
+__global__ void __launch_bounds__(Fft5Cfg<LOG2M>::NT, Fft5Cfg<LOG2M>::MINB)
+fftconv5_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
+                long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
+                const float2 *__restrict__ tw /* W_n^i, i < M */, float *__restrict__ g, int B, int H, int l) {
+    using Cfg = Fft5Cfg<LOG2M>;
+    constexpr int M = Cfg::M, NT = Cfg::NT;
+    constexpr int log2sub0 = LOG2M - 4, sub0 = 1 << log2sub0;      // outer pass: radix 16, span M
+    extern __shared__ float sm[];
+    float *re = sm, *im = sm + Cfg::PLANE;
+    float *t0r = im + Cfg::PLANE, *t0i = t0r + Cfg::NTW0;
+    float *t1r = t0i + Cfg::NTW0, *t1i = t1r + Cfg::NTW1;
+    float *t2r = t1i + Cfg::NTW1, *t2i = t2r + Cfg::NTW2;
+    const int tid = threadIdx.x;
+    const int row = blockIdx.x;
+    const int h = row / B, b = row - h * B;
+    const size_t off = ((size_t)b * H + h) * (size_t)l;
+    const float4 *xr4 = reinterpret_cast<const float4 *>(x + off);
+    float *gr = g + off;
+    const float pt = part_t ? part_t[(size_t)b * part_stride_b + h] : 0.f;
+    const float4 *st4 = stats ? reinterpret_cast<const float4 *>(stats + (size_t)b * l * 2) : nullptr;
+    const float4 *kcr = kc + (size_t)h * (M + 2);                  // (M/2 + 1) entries of two float4 (v1 layout)
+    const float lns = st4 ? ln_s : 1.f, lnm = st4 ? ln_m : 0.f;
+    const int half = l >> 1;
+
+    for (int j = tid; j < Cfg::NTW0; j += NT) {
+        const float2 a = tw[2 * j];                                // W_M^j = W_n^{2j}
+        t0r[j] = a.x;
+        t0i[j] = a.y;
+    }
+    for (int j = tid; j < Cfg::NTW1; j += NT) {
+        const float2 a = tw[32 * j];                               // W_{M/16}^j
+        t1r[j] = a.x;
+        t1i[j] = a.y;
+    }
+    for (int j = tid; j < Cfg::NTW2; j += NT) {
+        const float2 a = tw[j * (M / 8)];                          // W_16^j
+        t2r[j] = a.x;
+        t2i[j] = a.y;
+    }
+    __syncthreads();
+
+    const int j0 = 2 * tid, pb0 = padf(j0);
+    C2 one;
+    one.x = V2(1.f);
+    one.y = V2(0.f);
+    // ---- outer forward pass + prologue: packed inputs i = j + p sub0 (+1 in lane 1); p >= 8 lies in the zero padding
+    {
+        C2 xx[16];
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+            float4 xv[4], sa[4], sb[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int i = j0 + ((4 * hb + p) << log2sub0);
+                xv[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sa[p] = make_float4(0.f, 1.f, 0.f, 1.f);
+                sb[p] = sa[p];
+                if (i < half) {
+                    xv[p] = __ldg(xr4 + (i >> 1));
+                    if (st4) {
+                        sa[p] = __ldg(st4 + i);
+                        sb[p] = __ldg(st4 + i + 1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int i = j0 + ((4 * hb + p) << log2sub0);
+                const bool in = i < half;
+                const float add = in ? pt : 0.f;
+                const float y0 = (lns * sa[p].y) * (xv[p].x - sa[p].x + lnm) + add;
+                const float y1 = (lns * sa[p].w) * (xv[p].y - sa[p].z + lnm) + add;
+                const float y2 = (lns * sb[p].y) * (xv[p].z - sb[p].x + lnm) + add;
+                const float y3 = (lns * sb[p].w) * (xv[p].w - sb[p].z + lnm) + add;
+                xx[4 * hb + p].x = V2(in ? y0 : 0.f, in ? y2 : 0.f);
+                xx[4 * hb + p].y = V2(in ? y1 : 0.f, in ? y3 : 0.f);
+            }
+        }
+        s2::RadixS<16, false, true>::run(xx);
+        C2 v;
+        v.x = ld2(t0r + j0);
+        v.y = ld2(t0i + j0);
+        s2::apply_twiddles16<false>(xx, one, v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int c = fft_brev(q, 4), o = c * sub0 + 2 * ((c * sub0) >> 5);
+            st2(re + pb0 + o, xx[q].x);
+            st2(im + pb0 + o, xx[q].y);
+        }
+    }
+    __syncthreads();
+    mid_pass<LOG2M, 1, false>(re, im, t1r, t1i, tid);
+    if constexpr (Cfg::MID4) mid4_pass<LOG2M, false>(re, im, t2r, t2i, tid);
+    centre_wide<M, 2, NT>(re, im, kcr, kcr + M, false, tid);
+    if constexpr (Cfg::MID4) mid4_pass<LOG2M, true>(re, im, t2r, t2i, tid);
+    mid_pass<LOG2M, 1, true>(re, im, t1r, t1i, tid);
+    // ---- outer inverse pass + epilogue: only outputs p < 8 can fall inside the row
+    {
+        C2 xx[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int c = fft_brev(q, 4), o = c * sub0 + 2 * ((c * sub0) >> 5);
+            xx[q].x = ld2(re + pb0 + o);
+            xx[q].y = ld2(im + pb0 + o);
+        }
+        C2 v;
+        v.x = ld2(t0r + j0);
+        v.y = -ld2(t0i + j0);
+        s2::apply_twiddles16<false>(xx, one, v);
+        s2::RadixS<16, true>::run(xx);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int i = j0 + (p << log2sub0);
+            if (i < half) {
+                const V2 r = s2::gelu_fast2(xx[p].x), q = s2::gelu_fast2(xx[p].y);
+                *reinterpret_cast<float4 *>(gr + 2 * i) = make_float4(r.v.x, q.v.x, r.v.y, q.v.y);
+            }
+        }
+    }
+}
+
+template <int LOG2M>
+static int launch_fftconv5(const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
+                           const float *kc, const float2 *tw, float *g, int B, int H, int l, cudaStream_t st) {
+    using Cfg = Fft5Cfg<LOG2M>;
+    fftconv5_kernel<LOG2M><<<B * H, Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw, g, B, H, l);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+bool fftconv5_supported(int lg, const float *x, const float *stats, const float *g, int l) {
+    const uintptr_t a = (uintptr_t)x | (uintptr_t)stats | (uintptr_t)g;
+    return (lg == 10 || lg == 12) && (l % 4) == 0 && (a & 15) == 0;
+}
+
+int fftconv5_launch(int lg, const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
+                    const float *kc, const float2 *tw, float *g, int B, int H, int l, cudaStream_t st) {
+    switch (lg) {
+        case 10: return launch_fftconv5<10>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+        case 12: return launch_fftconv5<12>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, g, B, H, l, st);
+    }
+    set_error("fftconv5: no kernel for log2M=%d", lg);
+    return DWB_ERR_UNSUPPORTED;
 }
 
 template <int LOG2M, bool COMPACT>

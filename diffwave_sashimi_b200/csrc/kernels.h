@@ -101,6 +101,9 @@ bool fftconv3_supported(int log2M, const float *x, const float *stats, const flo
 int fftconv3_launch(int log2M, const float *x, const float *stats, const float *part_t, long long psb, float ln_m,
                     float ln_s, const float *kf, const float2 *tw, const float2 *tw2 /* compact table: pair twiddles, else null */,
                     float *g, float *scratch, int B, int H, int l, cudaStream_t st);
+bool fftconv5_supported(int log2M, const float *x, const float *stats, const float *g, int l);
+int fftconv5_launch(int log2M, const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
+                    const float *kf, const float2 *tw, float *g, int B, int H, int l, cudaStream_t st);
 int fft_pair_twiddles(int log2M, cudaStream_t st, const float2 **tw2);
 int s4_generate(const float *C, const float *Bp, const float *P, const float *inv_w_real, const float *w_imag,
                 const float *log_dt, const float *omega, int H, int N, int l, double *khat, double *k64, float *k32,
