@@ -141,3 +141,47 @@ def test_fftconv_is_linear_before_gelu_and_shift_covariant(dwb):
 def test_fftconv_rejects_too_long(dwb):
     with pytest.raises(RuntimeError):
         dwb.ops.fftconv_size(20000)
+
+
+_VARIANT_SNIPPET = r'''
+import sys, torch
+sys.path.insert(0, {root!r})
+sys.path.insert(0, {tests!r})
+import diffwave_sashimi_b200 as dwb
+from oracle import diffwave_oracle as O
+worst = 0.0
+for (B, H, l) in [(2, 2, 16000), (2, 3, 4000), (2, 2, 1000)]:
+    g = torch.Generator().manual_seed(l)
+    x = torch.randn(B, H, l, generator=g) * 2 + 0.3
+    k = torch.randn(2, H, l, generator=g) * torch.exp(-torch.arange(l) / (0.2 * l + 3))[None, None] * 0.3
+    D = torch.randn(H, generator=g)
+    stats = torch.stack([torch.randn(B, l, generator=g) * 0.1, torch.rand(B, l, generator=g) + 0.5], -1)
+    part = torch.randn(B, H, generator=g)
+    kf = dwb.ops.fftconv_prepare(k.cuda(), D.cuda())
+    out = dwb.ops.fftconv(x.cuda(), kf, stats.cuda(), part.cuda(), ln_m=0.05, ln_s=1.3).cpu().double()
+    y = (1.3 * stats[..., 1].double())[:, None, :] * (x.double() - stats[..., 0].double()[:, None, :] + 0.05) + part.double()[:, :, None]
+    ref = torch.nn.functional.gelu(O.s4_apply(k.double(), D.double().reshape(1, -1), y))
+    worst = max(worst, ((out - ref).norm() / ref.norm()).item())
+print("WORST", worst)
+'''
+
+
+@pytest.mark.parametrize("env", [{"DWB_FFT": "v1"}, {"DWB_FFT": "v2"}, {"DWB_FFT_WIDE": "1"}, {"DWB_FFT12": "1"},
+                                 {"DWB_FFT5": "1"}])
+def test_fftconv_variants(env):
+    """Every S4-convolution kernel family behind the environment switches (read once per process, hence the
+    subprocess): scalar one-transform (v1), scalar split (v2), packed split with the 32 B table, packed split at
+    n = 8192, packed unsplit below n = 32768.  The default (packed split, 16 B table, at n = 32768; v1 below) is what
+    test_fftconv_vs_oracle exercises."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _VARIANT_SNIPPET.format(root=root, tests=os.path.join(root, "tests"))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float([ln for ln in r.stdout.splitlines() if ln.startswith("WORST")][-1].split()[1])
+    print(env, "worst rel_l2", worst)
+    assert worst < 2e-5
