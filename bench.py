@@ -13,10 +13,11 @@ Printed JSON (one line, rank 0):
   value      clips/s over all GPUs, inputs resident in HBM, one CUDA-graph launch per step
   e2e        same metric through the public API with HOST buffers: pinned x_T/noise H2D copies and
              the D2H read of x_0 inside the timed region
-  roofline   whole hot path against measured HBM bandwidth: algorithmic bytes (SURVEY.md §8(d),
-             dwb_plan_work) x T x B per step / step time; `kernels` lists every kernel category's
-             share of an eager forward, timed with CUDA events on the launching stream, and the
-             achieved GB/s of the dominant one
+  roofline   the dominant kernel (largest share of a forward, timed live with CUDA events around every launch
+             on the launching stream: dwb_plan_profile) against measured HBM bandwidth: achieved = algorithmic
+             bytes per launch (SURVEY.md 8(d): 2*4*H*l*B for the S4 convolution) / its mean launch time;
+             `traffic` = dram read+write bytes per launch from the committed ncu capture (profiles/ncu_traffic.json);
+             `whole_loop` = dwb_plan_work bytes x T x B per step / step time; `kernels` lists every category
   cpu_baseline  the oracle port of the reference's CPU path (fp32, S4 kernels regenerated every
              step exactly as the reference does), timed on this host for a bounded sample
 `--impl reference` runs only that CPU arm (rank 0), same metric/config.
