@@ -142,3 +142,54 @@ def test_split_transform_pairings_and_compact_table(l, log2M):
         outs.append(np.fft.ifft(Zp) * Mh)
     zz = outs[0] + np.exp(2j * np.pi * np.arange(Mh) / M) * outs[1]     # a[i] + W_M^{-i} b[i]
     np.testing.assert_allclose(unpack(zz, l), reference_conv(y, k0, k1), rtol=0, atol=1e-10)
+
+
+def test_plane_padding_offset_identity():
+    """mid_pass (fftconv3.cu) addresses element base + c*sub of a butterfly as padf(base) + c*sub + 2*((c*sub) >> 5)
+    with a compile-time second term: valid for every span the plans use (sub a power of two, base = blk*16*sub + j,
+    j < sub), and the re/im plane entries of butterflies j, j+1 (j even) are adjacent and 8-byte aligned."""
+    padf = lambda i: i + 2 * (i >> 5)
+    for log2sub in range(1, 11):
+        sub = 1 << log2sub
+        S = 16 * sub
+        for blk in (0, 1, 3, 7):
+            for j in range(0, min(sub, 64), 2):
+                base = blk * S + j
+                for c in range(16):
+                    assert padf(base + c * sub) == padf(base) + c * sub + 2 * ((c * sub) >> 5)
+                    assert padf(base + c * sub) % 2 == 0 and padf(base + c * sub + 1) == padf(base + c * sub) + 1
+    # radix-4 pass of span 16 (mid4_pass): + 4p stays inside the 16-float block
+    for blk in range(64):
+        for j in (0, 2):
+            base = blk * 16 + j
+            for p in range(4):
+                assert padf(base + 4 * p) == padf(base) + 4 * p
+
+
+@pytest.mark.parametrize("log2M,radices", [(13, (4, 4, 4, 1)), (12, (4, 4, 2, 2)), (10, (4, 4, 2)), (11, (4, 4, 3))])
+def test_dif_passes_leave_plain_bit_reversal(log2M, radices):
+    """Forward passes (any radix split): u_q = sum_p x[j + p sub] w_R^{pq}, stored times W_S^{jq} at j + brev(q) sub.
+    After all passes slot p holds X[brev(p)], whatever the radices — the property that lets one pointwise table serve
+    every plan and gives the partner maps of the untangle step."""
+    assert sum(radices) == log2M
+    M = 1 << log2M
+    rng = np.random.default_rng(log2M)
+    x = rng.standard_normal(M) + 1j * rng.standard_normal(M)
+    s = x.copy()
+    span_log = log2M
+    for lr in radices:
+        R, S = 1 << lr, 1 << span_log
+        sub = S // R
+        out = np.empty_like(s)
+        for blk in range(M // S):
+            for j in range(sub):
+                base = blk * S + j
+                xin = s[base + sub * np.arange(R)]
+                u = np.fft.fft(xin)                                   # radix-R DFT
+                u = u * np.exp(-2j * np.pi * j * np.arange(R) / S)    # twiddle W_S^{jq}
+                for q in range(R):
+                    out[base + brev(q, lr) * sub] = u[q]
+        s = out
+        span_log -= lr
+    X = np.fft.fft(x)
+    np.testing.assert_allclose(s, X[[brev(p, log2M) for p in range(M)]], atol=1e-8)
