@@ -249,11 +249,12 @@ static int launch_mma(const MixArgs &a, int B, cudaStream_t st) {
 }
 
 bool mix_mma_supported(int H, int F, int l) {
-    return F == 2 * H && (l % 2 == 0) && (H == 64 || H == 128 || H == 256 || H == 512);
+    return F == 2 * H && (l % 2 == 0) && (H == 32 || H == 64 || H == 128 || H == 256 || H == 512);
 }
 
 int mix_mma_launch(const MixArgs &a, int B, cudaStream_t st) {
     switch (a.H) {
+        case 32: return launch_mma<32, 2, 64, 2, 4>(a, B, st);
         case 64: return launch_mma<64, 2, 64, 4, 2>(a, B, st);
         case 128: return launch_mma<128, 2, 64, 8, 1>(a, B, st);
         case 256: return launch_mma<256, 2, 32, 8, 1>(a, B, st);
