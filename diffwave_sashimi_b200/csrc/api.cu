@@ -7,6 +7,8 @@
 //   generate.py:23-55   sampling()                                         -> dwb_sample
 #include <stdarg.h>
 #include <stdlib.h>
+#include <string.h>
+#include <algorithm>
 
 #include <map>
 #include <string>
@@ -76,18 +78,16 @@ struct WaveLayer {
     float *Wd_t, *bd, *Wr_t, *br, *Ws_t, *bs;
     uint4 *Wd_f[2], *Wr_f[2], *Ws_f[2];
     bool mma;
+    bool umma;                     // tcgen05 path (wave_umma.cu)
+    uint8_t *Wimg;
     int part_off;
     int64_t cond_off;
 };
 
-struct GraphKey {
-    const void *xT = nullptr, *noise = nullptr, *cond = nullptr, *out = nullptr;
-    int cond_batch = 0, T = 0, B = 0, L = 0;
-    std::vector<float> coef;
-    bool operator==(const GraphKey &o) const {
-        return xT == o.xT && noise == o.noise && cond == o.cond && out == o.out && cond_batch == o.cond_batch &&
-               T == o.T && B == o.B && L == o.L && coef == o.coef;
-    }
+struct StepKey {              // what the captured one-step graph depends on
+    const void *cond = nullptr;
+    int cond_batch = 0, B = 0, L = 0;
+    bool operator==(const StepKey &o) const { return cond == o.cond && cond_batch == o.cond_batch && B == o.B && L == o.L; }
 };
 
 }  // namespace dwb
@@ -134,12 +134,17 @@ struct dwb_plan {
     float *skip_acc = nullptr;     // wavenet
     std::vector<void *> ws_owned;
 
-    // sampler
-    float *table_emb = nullptr, *table_part = nullptr, *table_t = nullptr;   // (T, .) per-step fc_t outputs
+    // sampler: per-step records (T, Mtot + 4) = [fc_t outputs of every layer | c1, sqrt(alpha), sigma, noise slot];
+    // the record of the current step is copied to rec_cur, which is what the captured ONE-STEP graph reads, so
+    // the graph depends on neither T, the step, nor any caller buffer (x lives in x_cur, noise behind noise_base)
+    float *table_emb = nullptr, *table_part = nullptr, *table_t = nullptr, *step_tab = nullptr;
     int table_T = 0;
+    std::vector<float> tab_coef;
+    float *x_cur = nullptr, *rec_cur = nullptr;     // workspace: (B,1,L) state, (Mtot + 4) current record
+    const float **noise_base = nullptr;             // workspace: device word holding the call's noise base pointer
     cudaGraphExec_t graph_exec = nullptr;
     cudaStream_t cap_stream = nullptr;   // capture happens on a plan-owned stream (the legacy default stream cannot capture)
-    GraphKey graph_key;
+    StepKey graph_key;
     int64_t graph_nodes = 0;
 };
 
@@ -486,7 +491,14 @@ static int finalize_wavenet(dwb_plan *p, cudaStream_t st) {
         TRY(folded(p, pre + "dilated_conv_layer.conv", 2 * C, C, 3, true, &w.Wd_t, &w.bd, st));
         TRY(folded(p, pre + "res_conv", C, C, 1, true, &w.Wr_t, &w.br, st));
         TRY(folded(p, pre + "skip_conv", S, C, 1, true, &w.Ws_t, &w.bs, st));
-        w.mma = p->use_mma && wave_mma_supported(C, S);
+        w.umma = p->use_mma && p->use_umma && wave_umma_supported(C, S);
+        if (w.umma) {
+            void *d;
+            TRY(dev_alloc(p, wave_umma_image_bytes(C, S), &d)); w.Wimg = (uint8_t *)d;
+            TRY(wave_umma_pack(C, S, w.Wd_t, w.Wr_t, w.Ws_t, w.Wimg, st));
+            p->launches += 1;
+        }
+        w.mma = !w.umma && p->use_mma && wave_mma_supported(C, S);
         if (w.mma) {
             auto pack = [&](const float *Wt, int M, int K, uint4 **f) -> int {
                 for (int q = 0; q < 2; ++q) {
@@ -543,6 +555,9 @@ static int ensure_workspace(dwb_plan *p, int B, int L) {
     }
     TRY(dev_alloc(p, (size_t)B * c.embed_out * sizeof(float), &d, true)); p->emb_buf = (float *)d;
     TRY(dev_alloc(p, (size_t)B * p->Mtot * sizeof(float), &d, true)); p->part_buf = (float *)d;
+    TRY(dev_alloc(p, (size_t)B * L * sizeof(float), &d, true)); p->x_cur = (float *)d;
+    TRY(dev_alloc(p, (size_t)(p->Mtot + 4) * sizeof(float), &d, true)); p->rec_cur = (float *)d;
+    TRY(dev_alloc(p, sizeof(float *), &d, true)); p->noise_base = (const float **)d;
     p->ws_B = B;
     p->ws_L = L;
     return DWB_OK;
@@ -579,9 +594,10 @@ static int stage_of(const dwb_plan *p, int l) {   // 0 = top stage, 1 = after fi
     return s;
 }
 
-struct StepUpdate {           // fused DDPM update in the head, or plain eps
-    const float *x = nullptr, *noise = nullptr;
-    float c1 = 0, sqrt_alpha = 1, sigma = 0;
+struct StepUpdate {           // fused DDPM update in the head (coefficients read from device memory), or plain eps
+    const float *x = nullptr;
+    const float *ctl = nullptr;                 // device: c1, sqrt(alpha), sigma, noise slot (int bits, -1 = none)
+    const float *const *noise_base = nullptr;   // device: noise of slot i at *noise_base + i * B * L
 };
 
 // one network evaluation; part = (rows, Mtot) fc_t outputs with batch stride psb (0 = shared row)
@@ -648,7 +664,10 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
             a.Wd_t = w.Wd_t; a.bd = w.bd; a.Wr_t = w.Wr_t; a.br = w.br; a.Ws_t = w.Ws_t; a.bs = w.bs;
             a.skip = p->skip_acc; a.first = n == 0;
             a.C = C; a.S = S; a.L = L; a.dilation = w.dilation;
-            if (w.mma) {
+            if (w.umma) {
+                a.Wimg = w.Wimg;
+                TRY(wave_block_umma_launch(a, B, st));
+            } else if (w.mma) {
                 a.Wd_fh = w.Wd_f[0]; a.Wd_fl = w.Wd_f[1]; a.Wr_fh = w.Wr_f[0]; a.Wr_fl = w.Wr_f[1];
                 a.Ws_fh = w.Ws_f[0]; a.Ws_fl = w.Ws_f[1];
                 TRY(wave_block_mma_launch(a, B, st));
@@ -664,7 +683,7 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
     }
     h.Wf_t = p->Wf_t; h.bf = p->bf; h.wz = p->wz; h.bz = p->bz;
     h.out = out; h.l = L;
-    if (upd) { h.upd_x = upd->x; h.noise = upd->noise; h.c1 = upd->c1; h.sqrt_alpha = upd->sqrt_alpha; h.sigma = upd->sigma; }
+    if (upd) { h.upd_x = upd->x; h.ctl = upd->ctl; h.noise_base = upd->noise_base; }
     h.Wf_fh = p->Wf_f[0]; h.Wf_fl = p->Wf_f[1];
     if (h.Wf_fh) TRY(head_mma_launch(h, B, st));
     else TRY(head_launch(h, B, st));
@@ -738,7 +757,7 @@ int dwb_plan_destroy(dwb_plan *p) {
     for (auto &kv : p->tensors) cudaFree(kv.second.dev);
     for (void *d : p->owned) cudaFree(d);
     for (void *d : p->ws_owned) cudaFree(d);
-    cudaFree(p->table_emb); cudaFree(p->table_part); cudaFree(p->table_t);
+    cudaFree(p->table_emb); cudaFree(p->table_part); cudaFree(p->table_t); cudaFree(p->step_tab);
     delete p;
     return DWB_OK;
 }
@@ -831,6 +850,90 @@ int dwb_forward(dwb_plan *p, const float *x, const float *t, const float *cond, 
     return run_network(p, x, p->part_buf, p->Mtot, cond, cond_batch, eps, nullptr, B, L, st);
 }
 
+// (T, Mtot + 4) per-step records; rebuilt when T or the schedule changes.  Synchronises.
+static int ensure_step_table(dwb_plan *p, const float *coef_host, int T, cudaStream_t st) {
+    const dwb_config &c = p->cfg;
+    if (p->table_T == T && p->tab_coef.size() == (size_t)3 * T && std::equal(coef_host, coef_host + 3 * T, p->tab_coef.begin()))
+        return DWB_OK;
+    DWB_CUDA(cudaStreamSynchronize(st));
+    const size_t rec = (size_t)p->Mtot + 4;
+    if (p->table_T != T) {
+        cudaFree(p->table_emb); cudaFree(p->table_part); cudaFree(p->table_t); cudaFree(p->step_tab);
+        p->table_emb = p->table_part = p->table_t = p->step_tab = nullptr;
+        p->table_T = 0;
+        DWB_CUDA(cudaMalloc(&p->table_emb, (size_t)T * c.embed_out * sizeof(float)));
+        DWB_CUDA(cudaMalloc(&p->table_part, (size_t)T * p->Mtot * sizeof(float)));
+        DWB_CUDA(cudaMalloc(&p->table_t, (size_t)T * sizeof(float)));
+        DWB_CUDA(cudaMalloc(&p->step_tab, (size_t)T * rec * sizeof(float)));
+        std::vector<float> ts(T);
+        for (int i = 0; i < T; ++i) ts[i] = (float)i;            // same step for the whole batch (generate.py:50)
+        DWB_CUDA(cudaMemcpy(p->table_t, ts.data(), T * sizeof(float), cudaMemcpyHostToDevice));
+        TRY(embed_launch(p->table_t, T, c.embed_in, c.embed_mid, c.embed_out, p->eW1, p->eb1, p->eW2, p->eb2, p->Wt_all,
+                         p->bt_all, p->Mtot, p->table_emb, p->table_part, st));
+        p->launches += 2;
+        DWB_CUDA(cudaMemcpy2DAsync(p->step_tab, rec * sizeof(float), p->table_part, (size_t)p->Mtot * sizeof(float),
+                                   (size_t)p->Mtot * sizeof(float), T, cudaMemcpyDeviceToDevice, st));
+        DWB_CUDA(cudaStreamSynchronize(st));
+        p->table_T = T;
+    }
+    std::vector<float> ctl((size_t)4 * T);
+    for (int t = 0; t < T; ++t) {
+        ctl[4 * t + 0] = coef_host[t];
+        ctl[4 * t + 1] = coef_host[T + t];
+        ctl[4 * t + 2] = coef_host[2 * T + t];
+        const int slot = t > 0 ? T - 1 - t : -1;                 // draw i is used at step T-1-i; no draw at t = 0
+        memcpy(&ctl[4 * t + 3], &slot, sizeof(int));
+    }
+    DWB_CUDA(cudaMemcpy2D(p->step_tab + p->Mtot, rec * sizeof(float), ctl.data(), 4 * sizeof(float), 4 * sizeof(float), T,
+                          cudaMemcpyHostToDevice));
+    p->tab_coef.assign(coef_host, coef_host + 3 * T);
+    return DWB_OK;
+}
+
+// steps t_start, t_start-1, ..., t_start-n_steps+1 of the reverse loop on p->x_cur
+static int run_steps(dwb_plan *p, const float *noise, const float *cond, int cond_batch, const float *coef_host, int T,
+                     int t_start, int n_steps, int B, int L, int use_graph, cudaStream_t st) {
+    TRY(ensure_step_table(p, coef_host, T, st));
+    const size_t BL = (size_t)B * L, rec = (size_t)p->Mtot + 4;
+    // slot i of the whole run lives at base + i*BL; the caller's pointer is slot T-1-t_start (never dereferenced below it)
+    const float *base = noise ? noise - (ptrdiff_t)(T - 1 - t_start) * (ptrdiff_t)BL : nullptr;
+    DWB_CUDA(cudaMemcpyAsync(p->noise_base, &base, sizeof(base), cudaMemcpyHostToDevice, st));   // pageable: staged before return
+    StepUpdate u;
+    u.x = p->x_cur; u.ctl = p->rec_cur + p->Mtot; u.noise_base = p->noise_base;
+    auto one_step = [&](cudaStream_t s) { return run_network(p, p->x_cur, p->rec_cur, 0, cond, cond_batch, p->x_cur, &u, B, L, s); };
+    if (use_graph) {
+        StepKey key;
+        key.cond = cond; key.cond_batch = cond_batch; key.B = B; key.L = L;
+        if (!p->graph_exec || !(key == p->graph_key)) {
+            if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+            if (!p->cap_stream) DWB_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+            const int64_t before = p->launches;
+            DWB_CUDA(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+            int rc = one_step(p->cap_stream);
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamEndCapture(p->cap_stream, &graph);
+            if (rc != DWB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+            p->graph_nodes = p->launches - before;
+            p->launches = before;
+            e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { p->graph_exec = nullptr; return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+            p->graph_key = key;
+        }
+    }
+    for (int i = 0; i < n_steps; ++i) {
+        const int t = t_start - i;
+        DWB_CUDA(cudaMemcpyAsync(p->rec_cur, p->step_tab + (size_t)t * rec, rec * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (use_graph) {
+            DWB_CUDA(cudaGraphLaunch(p->graph_exec, st));
+            p->launches += p->graph_nodes;
+        } else
+            TRY(one_step(st));
+    }
+    return DWB_OK;
+}
+
 int dwb_sample(dwb_plan *p, const float *x_T, const float *noise, const float *cond, int cond_batch,
                const float *coef_host, int T, float *out, int B, int L, int use_graph, void *stream) {
     DWB_REQUIRE(p && x_T && out && coef_host, DWB_ERR_INVALID, "dwb_sample: null pointer");
@@ -840,68 +943,27 @@ int dwb_sample(dwb_plan *p, const float *x_T, const float *noise, const float *c
     DWB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     TRY(ensure_workspace(p, B, L));
-    const dwb_config &c = p->cfg;
+    const size_t bytes = (size_t)B * L * sizeof(float);
+    DWB_CUDA(cudaMemcpyAsync(p->x_cur, x_T, bytes, cudaMemcpyDeviceToDevice, st));
+    TRY(run_steps(p, noise, cond, cond_batch, coef_host, T, T - 1, T, B, L, use_graph, st));
+    DWB_CUDA(cudaMemcpyAsync(out, p->x_cur, bytes, cudaMemcpyDeviceToDevice, st));
+    return DWB_OK;
+}
 
-    GraphKey key;
-    key.xT = x_T; key.noise = noise; key.cond = cond; key.out = out; key.cond_batch = cond_batch;
-    key.T = T; key.B = B; key.L = L;
-    key.coef.assign(coef_host, coef_host + 3 * T);
-    if (use_graph && p->graph_exec && key == p->graph_key) {
-        DWB_CUDA(cudaGraphLaunch(p->graph_exec, st));
-        p->launches += p->graph_nodes;
-        return DWB_OK;
-    }
-
-    // per-step t-embedding table: same step for the whole batch (generate.py:50)
-    if (p->table_T != T) {
-        DWB_CUDA(cudaStreamSynchronize(st));
-        if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
-        cudaFree(p->table_emb); cudaFree(p->table_part); cudaFree(p->table_t);
-        p->table_emb = p->table_part = p->table_t = nullptr;
-        p->table_T = 0;
-        DWB_CUDA(cudaMalloc(&p->table_emb, (size_t)T * c.embed_out * sizeof(float)));
-        DWB_CUDA(cudaMalloc(&p->table_part, (size_t)T * p->Mtot * sizeof(float)));
-        DWB_CUDA(cudaMalloc(&p->table_t, (size_t)T * sizeof(float)));
-        std::vector<float> ts(T);
-        for (int i = 0; i < T; ++i) ts[i] = (float)i;
-        DWB_CUDA(cudaMemcpyAsync(p->table_t, ts.data(), T * sizeof(float), cudaMemcpyHostToDevice, st));
-        DWB_CUDA(cudaStreamSynchronize(st));
-        TRY(embed_launch(p->table_t, T, c.embed_in, c.embed_mid, c.embed_out, p->eW1, p->eb1, p->eW2, p->eb2, p->Wt_all,
-                         p->bt_all, p->Mtot, p->table_emb, p->table_part, st));
-        p->launches += 2;
-        p->table_T = T;
-    }
-    const size_t BL = (size_t)B * L;
-    auto body = [&](cudaStream_t st) -> int {
-        DWB_CUDA(cudaMemcpyAsync(out, x_T, BL * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        for (int t = T - 1; t >= 0; --t) {
-            StepUpdate u;
-            u.x = out;
-            u.c1 = coef_host[t]; u.sqrt_alpha = coef_host[T + t]; u.sigma = coef_host[2 * T + t];
-            u.noise = t > 0 ? noise + (size_t)(T - 1 - t) * BL : nullptr;
-            TRY(run_network(p, out, p->table_part + (size_t)t * p->Mtot, 0, cond, cond_batch, out, &u, B, L, st));
-        }
-        return DWB_OK;
-    };
-    if (!use_graph) return body(st);
-
-    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
-    if (!p->cap_stream) DWB_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
-    const int64_t before = p->launches;
-    DWB_CUDA(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = body(p->cap_stream);
-    cudaGraph_t graph = nullptr;
-    cudaError_t e = cudaStreamEndCapture(p->cap_stream, &graph);
-    if (rc != DWB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
-    p->graph_nodes = p->launches - before;
-    p->launches = before;
-    e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { p->graph_exec = nullptr; return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
-    p->graph_key = key;
-    DWB_CUDA(cudaGraphLaunch(p->graph_exec, st));
-    p->launches += p->graph_nodes;
+int dwb_sample_steps(dwb_plan *p, float *x, const float *noise, const float *cond, int cond_batch, const float *coef_host,
+                     int T, int t_start, int n_steps, int B, int L, int use_graph, void *stream) {
+    DWB_REQUIRE(p && x && coef_host, DWB_ERR_INVALID, "dwb_sample_steps: null pointer");
+    DWB_REQUIRE(T >= 1 && n_steps >= 1 && t_start < T && t_start - n_steps + 1 >= 0, DWB_ERR_INVALID,
+                "dwb_sample_steps: steps [%d, %d] outside [0, %d)", t_start - n_steps + 1, t_start, T);
+    DWB_REQUIRE(noise || (t_start == 0 && n_steps == 1), DWB_ERR_INVALID, "noise is required for steps t > 0");
+    TRY(check_run(p, B, L, cond, cond_batch));
+    DWB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ensure_workspace(p, B, L));
+    const size_t bytes = (size_t)B * L * sizeof(float);
+    DWB_CUDA(cudaMemcpyAsync(p->x_cur, x, bytes, cudaMemcpyDeviceToDevice, st));
+    TRY(run_steps(p, noise, cond, cond_batch, coef_host, T, t_start, n_steps, B, L, use_graph, st));
+    DWB_CUDA(cudaMemcpyAsync(x, p->x_cur, bytes, cudaMemcpyDeviceToDevice, st));
     return DWB_OK;
 }
 

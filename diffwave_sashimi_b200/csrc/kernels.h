@@ -41,9 +41,12 @@ struct HeadArgs {
     const uint4 *Wf_fh, *Wf_fl;    // split-bf16 A fragments of Wf (frag_pack) or null -> fp32 SIMT kernel
     const float *wz;               // (C)
     float bz;
-    // optional fused DDPM update: out = (upd_x - c1 eps)/sqrt_alpha (+ sigma noise)
-    const float *upd_x, *noise;
-    float c1, sqrt_alpha, sigma;
+    // optional fused DDPM update: out = (upd_x - c1 eps)/sqrt_alpha (+ sigma noise); the step's coefficients come
+    // from device memory so that ONE captured step graph serves every step: ctl = {c1, sqrt_alpha, sigma, noise slot
+    // (int bits, -1 = no noise)}, noise of slot i at *noise_base + i * B * l
+    const float *upd_x;
+    const float *ctl;
+    const float *const *noise_base;
     float *out;                    // (B,l)
     int C, l;
 };
@@ -58,6 +61,7 @@ struct WaveBlockArgs {
     const float *Wr_t, *br;        // [C][C], (C)
     const float *Ws_t, *bs;        // [C][S], (S)
     const uint4 *Wd_fh, *Wd_fl, *Wr_fh, *Wr_fl, *Ws_fh, *Ws_fl;   // split-bf16 A fragments, or null
+    const uint8_t *Wimg;           // tcgen05 path (wave_umma.cu): packed shared-memory image of the three weights, or null
     float *h_out;                  // (B,C,L)
     float *skip;                   // (B,S,L) accumulated in place
     int first;                     // 1: skip is written, not accumulated
@@ -93,6 +97,10 @@ int head_mma_launch(const HeadArgs &a, int B, cudaStream_t st);
 int wave_block_launch(const WaveBlockArgs &a, int B, cudaStream_t st);
 bool wave_mma_supported(int C, int S);
 int wave_block_mma_launch(const WaveBlockArgs &a, int B, cudaStream_t st);
+bool wave_umma_supported(int C, int S);
+size_t wave_umma_image_bytes(int C, int S);
+int wave_umma_pack(int C, int S, const float *Wd_t, const float *Wr_t, const float *Ws_t, uint8_t *img, cudaStream_t st);
+int wave_block_umma_launch(const WaveBlockArgs &a, int B, cudaStream_t st);
 
 int fftconv_launch(const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
                    const float *kf, float *g, int B, int H, int l, cudaStream_t st, float *scratch = nullptr);

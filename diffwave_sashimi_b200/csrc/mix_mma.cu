@@ -470,8 +470,10 @@ head_mma_kernel(HeadArgs a) {
         const size_t o = (size_t)b * l + t0 + tid;
         if (a.upd_x) {
             // x <- (x - c1 eps) / sqrt(alpha) (+ sigma z)           generate.py:52-54
-            float xn = (a.upd_x[o] - a.c1 * e) / a.sqrt_alpha;
-            if (a.noise) xn += a.sigma * a.noise[o];
+            const float c1 = __ldg(a.ctl), sqrt_alpha = __ldg(a.ctl + 1), sigma = __ldg(a.ctl + 2);
+            const int slot = __float_as_int(__ldg(a.ctl + 3));
+            float xn = (a.upd_x[o] - c1 * e) / sqrt_alpha;
+            if (slot >= 0) xn += sigma * (*a.noise_base)[(size_t)slot * gridDim.y * l + o];
             a.out[o] = xn;
         } else {
             a.out[o] = e;

@@ -1,4 +1,4 @@
-// sm_100a primitives used by the tcgen05 channel-mixing kernels (mix_umma.cu, wave_umma.cu):
+// sm_100a primitives used by the tcgen05 kernels (mix_umma.cu, wave_umma.cu):
 // mbarriers, 1-D bulk async copies (TMA engine, no tensor map), TMEM allocation, tcgen05.mma
 // with shared-memory descriptors, tcgen05.ld/st for the epilogues.  Inline PTX only.
 //

@@ -170,27 +170,41 @@ def test_tensor_core_mixing_vs_oracle_fp64(dwb, d, L, B, pool, monkeypatch):
     assert e2 < 1e-4 and em < 1e-4 and s2 < 2e-5
 
 
-@pytest.mark.parametrize("C,S,N,cycle,L,B", [(64, 32, 7, 7, 500, 2), (128, 256, 4, 4, 1000, 1), (48, 80, 3, 3, 130, 3)])
-def test_wavenet_tensor_core_vs_oracle_fp64(dwb, C, S, N, cycle, L, B, monkeypatch):
-    """WaveNet blocks on the split-bf16 mma path: dilations reach past the 64-sample tile (2^6) so the
-    three taps come from different tiles and the zero padding at both ends is exercised."""
+@pytest.mark.parametrize("C,S,N,cycle,L,B,cond", [
+    (64, 32, 7, 7, 500, 2, False), (128, 256, 4, 4, 1000, 1, False), (48, 80, 3, 3, 130, 3, False),
+    # tcgen05 layer (wave_umma.cu): dilations past the 128-step tile, ragged last tile, both widths, mel features
+    (256, 256, 10, 10, 700, 2, False), (128, 128, 9, 9, 1300, 2, False), (256, 128, 3, 3, 257, 1, False),
+    (128, 256, 5, 5, 640, 2, True)])
+def test_wavenet_tensor_core_vs_oracle_fp64(dwb, C, S, N, cycle, L, B, cond, monkeypatch):
+    """WaveNet blocks on the tensor-core paths (tcgen05 for C in {128, 256}, split-bf16 mma.sync otherwise):
+    dilations reach past the time tile so the three taps come from different tiles and the zero padding
+    at both ends is exercised.  The exact-fp32 SIMT path (DWB_MIX=simt) and the mma.sync path
+    (DWB_MIX=mma) must agree with the fp64 oracle as well."""
     from oracle.refshim import MODEL_CFGS
     cfg = dict(MODEL_CFGS["wnet_h128_d30"], res_channels=C, skip_channels=S, num_res_layers=N, dilation_cycle=cycle)
+    mel = None
+    if cond:
+        cfg.update(unconditional=False, mel_upsample=[4, 4])
     sd = dwb.init.seeded_state_dict(cfg, seed=2)
     g = torch.Generator().manual_seed(4)
     x = torch.randn(B, 1, L, generator=g)
     t = torch.tensor([[11.0], [199.0], [0.0]])[:B]
-    ref = O.forward(cfg, sd, x, t)
-    net = _model(dwb, cfg, sd)
-    with torch.no_grad():
-        eps = net((x.cuda(), t.cuda())).cpu()
-    monkeypatch.setenv("DWB_MIX", "simt")
-    net2 = _model(dwb, cfg, sd)
-    with torch.no_grad():
-        eps2 = net2((x.cuda(), t.cuda())).cpu()
-    monkeypatch.delenv("DWB_MIX")
-    print(f"wnet C={C}: mma rel_l2 {rel_l2(eps, ref):.2e} simt rel_l2 {rel_l2(eps2, ref):.2e}")
-    assert rel_l2(eps, ref) < 1e-4 and rel_max(eps, ref) < 1e-4 and rel_l2(eps2, ref) < 2e-5
+    if cond:
+        mel = torch.randn(1, 80, L // 16, generator=g)
+    ref = O.forward(cfg, sd, x, t, mel=mel)
+    out = {}
+    for mode in (None, "mma", "simt"):
+        if mode:
+            monkeypatch.setenv("DWB_MIX", mode)
+        net = _model(dwb, cfg, sd)
+        with torch.no_grad():
+            out[mode] = net((x.cuda(), t.cuda()), mel_spec=None if mel is None else mel.cuda()).cpu()
+        if mode:
+            monkeypatch.delenv("DWB_MIX")
+    print(f"wnet C={C} S={S}: default rel_l2 {rel_l2(out[None], ref):.2e} rel_max {rel_max(out[None], ref):.2e}; "
+          f"mma.sync {rel_l2(out['mma'], ref):.2e}; simt {rel_l2(out['simt'], ref):.2e}")
+    assert rel_l2(out[None], ref) < 1e-4 and rel_max(out[None], ref) < 1e-4
+    assert rel_l2(out["mma"], ref) < 1e-4 and rel_l2(out["simt"], ref) < 2e-5
 
 
 def test_batch_elements_are_independent(dwb):
