@@ -10,4 +10,5 @@ Public API (mirrors the reference's names):
 from . import init, ops  # noqa: F401
 from .engine import Engine  # noqa: F401
 from .models import Sashimi, WaveNet, construct_model, model_identifier  # noqa: F401
-from .sampler import calc_diffusion_hyperparams, draw_noise, sampling, step_coefficients  # noqa: F401
+from .sampler import (GlobalNoise, PerClipNoise, calc_diffusion_hyperparams, clip_seed, draw_noise,  # noqa: F401
+                      sampling, step_coefficients)

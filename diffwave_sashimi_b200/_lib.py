@@ -46,6 +46,7 @@ SIGNATURES = {
     "dwb_plan_finalize": [_P, _P],
     "dwb_forward": [_P, _P, _P, _P, _I, _P, _I, _I, _P],
     "dwb_sample": [_P, _P, _P, _P, _I, ctypes.POINTER(_F), _I, _P, _I, _I, _I, _P],
+    "dwb_sample_steps": [_P, _P, _P, _P, _I, ctypes.POINTER(_F), _I, _I, _I, _I, _I, _I, _P],
     "dwb_plan_cond_layout": [_P, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I64)],
     "dwb_plan_launch_count": [_P, ctypes.POINTER(_I64)],
     "dwb_plan_s4_blocks": [_P, ctypes.POINTER(_I)],

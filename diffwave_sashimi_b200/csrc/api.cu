@@ -116,6 +116,11 @@ struct dwb_plan {
 
     std::vector<Op> ops;           // sashimi
     int n_bufs = 0;
+    // S4 pointwise tables for sequence lengths other than cfg.L (models/s4.py:1387: L_kernel = min(L, l_max)), one entry
+    // per block in op order.  r < l: the kernel's first r taps (kf).  r > l: overlap-save, one table per direction.
+    struct LenTab { float *kf = nullptr, *kf_c = nullptr, *kf_a = nullptr; };
+    std::map<int, std::vector<LenTab>> len_tabs;
+    std::vector<int> len_lru;      // most recent last; at most 2 lengths are kept
     std::vector<WaveLayer> wl;     // wavenet
     int64_t cond_total = 0;        // floats of conditioning features per cond batch element
     struct CondBlock {             // in-model mel front end of one block (folded weights)
@@ -523,6 +528,9 @@ static int finalize_wavenet(dwb_plan *p, cudaStream_t st) {
     return DWB_OK;
 }
 
+// length of an op's input when the model runs on L samples instead of cfg.L (same pooling ratios)
+static inline int run_len(const dwb_plan *p, int l_cfg, int L) { return (int)((int64_t)l_cfg * L / p->cfg.L); }
+
 static int ensure_workspace(dwb_plan *p, int B, int L) {
     const dwb_config &c = p->cfg;
     const bool sash = c.model == DWB_MODEL_SASHIMI;
@@ -538,8 +546,9 @@ static int ensure_workspace(dwb_plan *p, int B, int L) {
         const size_t act = (size_t)B * c.d_model * L * sizeof(float);   // H*l never exceeds d_model*L when expand <= pool
         size_t maxact = act;
         for (auto &o : p->ops) {
-            maxact = std::max(maxact, (size_t)B * o.H * o.l * sizeof(float));
-            if (o.kind != OP_BLOCK) maxact = std::max(maxact, (size_t)B * o.Ho * (o.kind == OP_DOWN ? o.l / o.s : o.l * o.s) * sizeof(float));
+            const size_t r = (size_t)run_len(p, o.l, L);
+            maxact = std::max(maxact, (size_t)B * o.H * r * sizeof(float));
+            if (o.kind != OP_BLOCK) maxact = std::max(maxact, (size_t)B * o.Ho * (o.kind == OP_DOWN ? r / o.s : r * o.s) * sizeof(float));
         }
         for (int i = 0; i < p->n_bufs; ++i) {
             TRY(dev_alloc(p, maxact, &d, true)); p->bufs.push_back((float *)d);
@@ -588,6 +597,60 @@ struct Prof {
 };
 #define PROF(c) do { if (prof) TRY(prof->mark(c)); } while (0)
 
+static void free_len_tabs(std::vector<dwb_plan::LenTab> &v) {
+    for (auto &t : v) { cudaFree(t.kf); cudaFree(t.kf_c); cudaFree(t.kf_a); }
+    v.clear();
+}
+
+// tables for run length L != cfg.L, built from the cached fp32 kernels (the reference convolves with fp32 kernels too).
+// Not during stream capture; synchronises when it builds.
+static int ensure_len_tabs(dwb_plan *p, int L, cudaStream_t st) {
+    if (p->cfg.model != DWB_MODEL_SASHIMI || L == p->cfg.L) return DWB_OK;
+    auto touch = [&]() {
+        auto &lru = p->len_lru;
+        lru.erase(std::remove(lru.begin(), lru.end(), L), lru.end());
+        lru.push_back(L);
+    };
+    if (p->len_tabs.count(L)) { touch(); return DWB_OK; }
+    DWB_CUDA(cudaDeviceSynchronize());
+    while (p->len_lru.size() >= 2) {
+        free_len_tabs(p->len_tabs[p->len_lru.front()]);
+        p->len_tabs.erase(p->len_lru.front());
+        p->len_lru.erase(p->len_lru.begin());
+    }
+    std::vector<dwb_plan::LenTab> tabs;
+    int rc = DWB_OK;
+    for (auto &o : p->ops) {
+        dwb_plan::LenTab t;
+        if (o.kind == OP_BLOCK && rc == DWB_OK) {
+            const int r = run_len(p, o.l, L);
+            const Tensor *D = find(p, o.prefix + "layer.D");
+            auto make = [&](int taps, int dir, float **out) -> int {
+                const int lg = fft_log2m_for(taps);
+                DWB_REQUIRE(lg > 0, DWB_ERR_UNSUPPORTED, "stage length %d exceeds the in-shared-memory FFT (max %d)", taps, 1 << FFT_MAX_LOG2M);
+                DWB_CUDA(cudaMalloc(out, (size_t)o.H * fft_table_floats(lg) * sizeof(float)));
+                TRY(fftconv_prepare_f32(o.k32, o.l, (const float *)D->dev, o.H, taps, dir, *out, st));
+                const float2 *tw;
+                TRY(fft_twiddles(lg, st, &tw));
+                if (dir == 0 && fft_table_mode(lg, taps) == 2) TRY(fft_pair_twiddles(lg, st, &tw));
+                p->launches += 2;
+                return DWB_OK;
+            };
+            if (r < 1) { set_error("sequence length %d leaves an empty stage", L); rc = DWB_ERR_INVALID; }
+            else if (r <= o.l) rc = make(r, 0, &t.kf);
+            else {
+                rc = make(o.l, 1, &t.kf_c);
+                if (rc == DWB_OK) rc = make(o.l, 2, &t.kf_a);
+            }
+        }
+        tabs.push_back(t);
+    }
+    if (rc != DWB_OK) { free_len_tabs(tabs); return rc; }
+    p->len_tabs[L] = tabs;
+    touch();
+    return DWB_OK;
+}
+
 static int stage_of(const dwb_plan *p, int l) {   // 0 = top stage, 1 = after first pool, ...
     int s = 0, cur = p->cfg.L;
     while (cur > l && s < p->cfg.n_pool) { cur /= p->cfg.pool[s]; ++s; }
@@ -610,25 +673,40 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
         p->launches += 1;
         PROF(DWB_PROF_INIT);
         int last = 0;
+        const std::vector<dwb_plan::LenTab> *lt = nullptr;
+        if (L != c.L) {
+            auto it = p->len_tabs.find(L);
+            DWB_REQUIRE(it != p->len_tabs.end(), DWB_ERR_STATE, "tables for length %d were not prepared", L);
+            lt = &it->second;
+        }
+        int64_t cond_off = 0;
+        size_t oi = 0;
         for (auto &o : p->ops) {
+            const int r = run_len(p, o.l, L);                  // = o.l when L == cfg.L
             if (o.kind == OP_BLOCK) {
-                TRY(fftconv_launch(p->bufs[o.in_buf], p->stat_bufs[o.in_buf], part + o.part_off, psb, o.ln1_m, o.ln1_s,
-                                   o.kf, p->g_buf, B, o.H, o.l, st, p->bufs[o.out_buf]));   // the block's output buffer is free scratch here
+                float *scratch = p->bufs[o.out_buf];           // the block's output buffer is free scratch here
+                if (lt && r > o.l)
+                    TRY(fftconv_ols_launch(p->bufs[o.in_buf], p->stat_bufs[o.in_buf], part + o.part_off, psb, o.ln1_m, o.ln1_s,
+                                           (*lt)[oi].kf_c, (*lt)[oi].kf_a, p->g_buf, scratch, B, o.H, r, o.l, st));
+                else
+                    TRY(fftconv_launch(p->bufs[o.in_buf], p->stat_bufs[o.in_buf], part + o.part_off, psb, o.ln1_m, o.ln1_s,
+                                       lt ? (*lt)[oi].kf : o.kf, p->g_buf, B, o.H, r, st, scratch));
                 PROF(DWB_PROF_FFTCONV0 + std::min(stage_of(p, o.l), 3));
                 MixArgs a{};
                 a.g = p->g_buf; a.x = p->bufs[o.in_buf];
                 a.skip = o.skip_buf >= 0 ? p->bufs[o.skip_buf] : nullptr;
-                a.cond = cond ? cond + (size_t)cond_batch * o.cond_off : nullptr;
+                a.cond = cond ? cond + (size_t)cond_batch * cond_off : nullptr;
+                cond_off += (int64_t)o.H * r;
                 a.cond_stride_b = cond_batch > 1 ? 1 : 0;
                 a.Wo_t = o.Wo_t; a.bo = o.bo; a.W1_t = o.W1_t; a.b1 = o.b1; a.W2_t = o.W2_t; a.b2 = o.b2;
                 a.ln2_m = o.ln2_m; a.ln2_s = o.ln2_s;
                 a.out = p->bufs[o.out_buf]; a.stats_out = p->stat_bufs[o.out_buf];
-                a.H = o.H; a.F = o.F; a.l = o.l;
+                a.H = o.H; a.F = o.F; a.l = r;
                 a.Wo_fh = o.Wo_f[0]; a.Wo_fl = o.Wo_f[1]; a.W1_fh = o.W1_f[0]; a.W1_fl = o.W1_f[1];
                 a.W2_fh = o.W2_f[0]; a.W2_fl = o.W2_f[1];
                 a.Wimg = o.Wimg; a.bimg = o.bimg;
                 TRY(o.umma ? mix_umma_launch(a, B, st) : (o.mma ? mix_mma_launch(a, B, st) : mix_launch(a, B, st)));
-                p->launches += 2;
+                p->launches += (lt && r > o.l) ? 3 : 2;
                 PROF(DWB_PROF_MIX0 + std::min(stage_of(p, o.l), 3));
             } else {
                 PoolArgs a{};
@@ -636,7 +714,7 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
                 a.skip = o.skip_buf >= 0 ? p->bufs[o.skip_buf] : nullptr;
                 a.W_t = o.Wp_t; a.bias = o.bp;
                 a.out = p->bufs[o.out_buf]; a.stats_out = p->stat_bufs[o.out_buf];
-                a.Hi = o.H; a.Ho = o.Ho; a.s = o.s; a.li = o.l;
+                a.Hi = o.H; a.Ho = o.Ho; a.s = o.s; a.li = r;
                 a.W_fh = o.Wp_f[0]; a.W_fl = o.Wp_f[1];
                 if (o.mma) TRY(o.kind == OP_DOWN ? down_pool_mma_launch(a, B, st) : up_pool_mma_launch(a, B, st));
                 else TRY(o.kind == OP_DOWN ? down_pool_launch(a, B, st) : up_pool_launch(a, B, st));
@@ -644,6 +722,7 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
                 PROF(DWB_PROF_POOL);
             }
             last = o.out_buf;
+            ++oi;
         }
         h.x = p->bufs[last]; h.stats = p->stat_bufs[last];
         h.ln_m = p->norm_m; h.ln_s = p->norm_s; h.prescale = 1.f;
@@ -696,9 +775,11 @@ static int check_run(dwb_plan *p, int B, int L, const float *cond, int cond_batc
     DWB_REQUIRE(p && p->finalized, DWB_ERR_STATE, "plan is not finalized");
     DWB_REQUIRE(B >= 1 && L >= 1, DWB_ERR_INVALID, "bad sizes B=%d L=%d", B, L);
     DWB_REQUIRE(B <= 65535, DWB_ERR_UNSUPPORTED, "batch %d > 65535", B);
-    if (p->cfg.model == DWB_MODEL_SASHIMI)
-        DWB_REQUIRE(L == p->cfg.L, DWB_ERR_UNSUPPORTED,
-                    "sequence length %d differs from the configured L=%d (kernel truncation / overlap-save not built yet)", L, p->cfg.L);
+    if (p->cfg.model == DWB_MODEL_SASHIMI) {
+        int prod = 1;
+        for (int q = 0; q < p->cfg.n_pool; ++q) prod *= p->cfg.pool[q];
+        DWB_REQUIRE(L % prod == 0, DWB_ERR_INVALID, "sequence length %d is not divisible by the pooling factor %d", L, prod);
+    }
     if (cond) {
         DWB_REQUIRE(!p->cfg.unconditional, DWB_ERR_INVALID, "conditioning passed to an unconditional model");
         DWB_REQUIRE(cond_batch == 1 || cond_batch == B, DWB_ERR_INVALID, "cond_batch must be 1 or B");
@@ -757,6 +838,7 @@ int dwb_plan_destroy(dwb_plan *p) {
     for (auto &kv : p->tensors) cudaFree(kv.second.dev);
     for (void *d : p->owned) cudaFree(d);
     for (void *d : p->ws_owned) cudaFree(d);
+    for (auto &kv : p->len_tabs) free_len_tabs(kv.second);
     cudaFree(p->table_emb); cudaFree(p->table_part); cudaFree(p->table_t); cudaFree(p->step_tab);
     delete p;
     return DWB_OK;
@@ -815,6 +897,9 @@ static int finalize_cond(dwb_plan *p, cudaStream_t st) {
             DWB_REQUIRE(v && v->shape.size() == 4 && v->shape[0] == 1 && v->shape[1] == 1 && v->shape[2] == 3 && v->shape[3] % 2 == 0,
                         DWB_ERR_INVALID, "`%s.weight_v` must be (1,1,3,2s)", pre.c_str());
             cb.s[i] = (int)(v->shape[3] / 2);
+            DWB_REQUIRE(cb.s[i] % 2 == 0, DWB_ERR_UNSUPPORTED,
+                        "`%s`: odd upsampling stride %d (ConvTranspose2d with padding s/2 then yields W*s + 1 columns; not built)",
+                        pre.c_str(), cb.s[i]);
             TRY(folded(p, pre, 1, 1, 3 * 2 * cb.s[i], true, &cb.w[i], &cb.b[i], st));
         }
         TRY(folded(p, t.first + "mel_conv.conv", cb.Hc, p->cfg.mel_bands, 1, true, &cb.Wm_t, &cb.bm, st));
@@ -843,6 +928,7 @@ int dwb_forward(dwb_plan *p, const float *x, const float *t, const float *cond, 
     DWB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     TRY(ensure_workspace(p, B, L));
+    TRY(ensure_len_tabs(p, L, st));
     const dwb_config &c = p->cfg;
     TRY(embed_launch(t, B, c.embed_in, c.embed_mid, c.embed_out, p->eW1, p->eb1, p->eW2, p->eb2, p->Wt_all, p->bt_all,
                      p->Mtot, p->emb_buf, p->part_buf, st));
@@ -943,6 +1029,7 @@ int dwb_sample(dwb_plan *p, const float *x_T, const float *noise, const float *c
     DWB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     TRY(ensure_workspace(p, B, L));
+    TRY(ensure_len_tabs(p, L, st));
     const size_t bytes = (size_t)B * L * sizeof(float);
     DWB_CUDA(cudaMemcpyAsync(p->x_cur, x_T, bytes, cudaMemcpyDeviceToDevice, st));
     TRY(run_steps(p, noise, cond, cond_batch, coef_host, T, T - 1, T, B, L, use_graph, st));
@@ -960,6 +1047,7 @@ int dwb_sample_steps(dwb_plan *p, float *x, const float *noise, const float *con
     DWB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     TRY(ensure_workspace(p, B, L));
+    TRY(ensure_len_tabs(p, L, st));
     const size_t bytes = (size_t)B * L * sizeof(float);
     DWB_CUDA(cudaMemcpyAsync(p->x_cur, x, bytes, cudaMemcpyDeviceToDevice, st));
     TRY(run_steps(p, noise, cond, cond_batch, coef_host, T, t_start, n_steps, B, L, use_graph, st));
@@ -974,6 +1062,7 @@ int dwb_plan_profile(dwb_plan *p, const float *x, const float *t, const float *c
     DWB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     TRY(ensure_workspace(p, B, L));
+    TRY(ensure_len_tabs(p, L, st));
     const dwb_config &c = p->cfg;
     for (int i = 0; i < DWB_PROF_NCAT; ++i) { ms[i] = 0; counts[i] = 0; }
     for (int it = 0; it < iters; ++it) {
@@ -1003,9 +1092,13 @@ int dwb_plan_cond_layout(dwb_plan *p, int L, int *n_blocks, int *channels, int *
     DWB_REQUIRE(p && p->finalized && n_blocks, DWB_ERR_STATE, "plan is not finalized");
     int n = 0;
     if (p->cfg.model == DWB_MODEL_SASHIMI) {
+        DWB_REQUIRE(L >= 1, DWB_ERR_INVALID, "dwb_plan_cond_layout: L=%d", L);
+        int64_t off = 0;
         for (auto &o : p->ops)
             if (o.kind == OP_BLOCK) {
-                if (channels) { channels[n] = o.H; lengths[n] = o.l; offsets[n] = o.cond_off; }
+                const int r = run_len(p, o.l, L);
+                if (channels) { channels[n] = o.H; lengths[n] = r; offsets[n] = off; }
+                off += (int64_t)o.H * r;
                 ++n;
             }
     } else {
@@ -1036,8 +1129,9 @@ int dwb_plan_cond_features(dwb_plan *p, const float *mel, int cond_batch, int fr
     cudaError_t e = cudaMalloc(&u2, (size_t)cond_batch * F * w2max * sizeof(float));
     if (e != cudaSuccess) { cudaFree(u1); return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
     int rc = DWB_OK;
+    int64_t run_off = 0;
     for (auto &cb : p->cond_blocks) {
-        const int l = cb.l ? cb.l : L, W1 = frames * cb.s[0], W2 = W1 * cb.s[1];
+        const int l = cb.l ? run_len(p, cb.l, L) : L, W1 = frames * cb.s[0], W2 = W1 * cb.s[1];
         if (W2 < l) {
             set_error("upsampled mel has %d samples < %d", W2, l);
             rc = DWB_ERR_INVALID;
@@ -1045,7 +1139,8 @@ int dwb_plan_cond_features(dwb_plan *p, const float *mel, int cond_batch, int fr
         }
         if ((rc = mel_upsample_launch(mel, cond_batch, F, frames, cb.s[0], cb.w[0], cb.b[0], u1, st)) != DWB_OK) break;
         if ((rc = mel_upsample_launch(u1, cond_batch, F, W1, cb.s[1], cb.w[1], cb.b[1], u2, st)) != DWB_OK) break;
-        const int64_t off = cb.l ? cb.off : cb.off * (int64_t)cb.Hc * L;
+        const int64_t off = cb.l ? run_off : cb.off * (int64_t)cb.Hc * L;
+        run_off += (int64_t)cb.Hc * l;
         if ((rc = mel_conv_launch(u2, cond_batch, F, W2, cb.Wm_t, cb.bm, cb.Hc, l, out + (size_t)cond_batch * off, st)) != DWB_OK) break;
         p->launches += 3;
     }
@@ -1112,25 +1207,6 @@ int dwb_plan_mix_block(dwb_plan *p, int block, int exact, const float *g, const 
             if (exact) return mix_launch(a, B, (cudaStream_t)stream);
             return o.umma ? mix_umma_launch(a, B, (cudaStream_t)stream)
                           : (o.mma ? mix_mma_launch(a, B, (cudaStream_t)stream) : mix_launch(a, B, (cudaStream_t)stream));
-        }
-    set_error("block %d out of range", block);
-    return DWB_ERR_INVALID;
-}
-
-/* debug only (not part of include/dwb.h): tcgen05 mixing of `block` with per-CTA phase timestamps */
-int dwb_debug_mix_trace(dwb_plan *p, int block, const float *g, const float *x, float *out, float *stats_out, int B,
-                        long long *trace, void *stream) {
-    DWB_REQUIRE(p && p->finalized, DWB_ERR_STATE, "plan is not finalized");
-    int n = 0;
-    for (auto &o : p->ops)
-        if (o.kind == OP_BLOCK) {
-            if (n++ != block) continue;
-            DWB_REQUIRE(o.umma, DWB_ERR_UNSUPPORTED, "block %d is not on the tcgen05 path", block);
-            MixArgs a{};
-            a.g = g; a.x = x; a.bo = o.bo; a.b1 = o.b1; a.b2 = o.b2;
-            a.ln2_m = o.ln2_m; a.ln2_s = o.ln2_s; a.out = out; a.stats_out = stats_out;
-            a.H = o.H; a.F = o.F; a.l = o.l; a.Wimg = o.Wimg; a.bimg = o.bimg; a.trace = trace;
-            return mix_umma_launch(a, B, (cudaStream_t)stream);
         }
     set_error("block %d out of range", block);
     return DWB_ERR_INVALID;

@@ -114,11 +114,22 @@ struct FftCfg {
     static constexpr bool FUSED = RL != 4;                     // last pass done in registers with the pointwise stage
 };
 
-template <int LOG2M>
-__global__ void __launch_bounds__(FftCfg<LOG2M>::NT)
-fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
-               long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
-               const float2 *__restrict__ tw /* W_n^i, i < M */, float *__restrict__ g, int B, int H, int l) {
+// Overlap-save mode (sequences longer than the kernel, models/s4.py:1387 with L > l_max): the row has r samples,
+// the two-sided kernel Lk taps per direction (n = 2M >= 2 Lk), P = n - Lk outputs per block; blockIdx.y = block j.
+// The two directions are separate passes over separate windows because one window of n samples would leave only
+// n - 2 Lk valid outputs:  anticausal pass (anti = 1): window [jP, jP + n), outputs at window positions [0, P) are
+// written raw to `g` (the partial sums);  causal pass: window [jP - Lk, jP - Lk + n), outputs at positions
+// [Lk, n) = times [jP, jP + P), g = gelu(value + partial[t]).  D and the 1/(4M) scale live in the causal table.
+struct OlsArgs {
+    const float *partial;
+    int r, Lk, P, anti;
+};
+
+template <int LOG2M, bool OLS>
+__device__ __forceinline__ void
+fftconv_body(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
+             long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
+             const float2 *__restrict__ tw /* W_n^i, i < M */, float *__restrict__ g, int B, int H, int l, const OlsArgs ols) {
     using Cfg = FftCfg<LOG2M>;
     constexpr int M = 1 << LOG2M, NT = Cfg::NT, NP = Cfg::NP, RL = Cfg::RL;
     constexpr int log2sub0 = LOG2M - 4, sub0 = 1 << log2sub0;      // pass 0: radix 16, span M
@@ -167,6 +178,33 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
                            (lns * sv.w) * (xv.y - sv.z + lnm) + (t0 + 1 < l ? pt : 0.f));
     };
 
+    // overlap-save: first sample of this block's window (may be negative: zero padding)
+    const int w0 = OLS ? (ols.anti ? (int)blockIdx.y * ols.P : (int)blockIdx.y * ols.P - ols.Lk) : 0;
+    auto ols_in = [&](int i) {                                   // y at window positions 2i, 2i+1 (0 outside the row)
+        float2 y = make_float2(0.f, 0.f);
+        const int t0 = w0 + 2 * i;
+        if (t0 >= 0 && t0 < l) y.x = (lns * (st ? st[2 * t0 + 1] : 1.f)) * (xr[t0] - (st ? st[2 * t0] : 0.f) + lnm) + pt;
+        if (t0 + 1 >= 0 && t0 + 1 < l)
+            y.y = (lns * (st ? st[2 * t0 + 3] : 1.f)) * (xr[t0 + 1] - (st ? st[2 * t0 + 2] : 0.f) + lnm) + pt;
+        return y;
+    };
+
+    if constexpr (OLS) {
+        // ---- pass 0 forward on a FULL window: all 16 inputs of a butterfly are live
+        for (int j = tid; j < Cfg::NTW; j += NT) stw[j] = tw[2 * j];
+        __syncthreads();
+#pragma unroll 1
+        for (int bi = tid; bi < sub0; bi += NT) {
+            float2 xx[16];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) xx[p] = ols_in(bi + (p << log2sub0));
+            Radix<16, false, false>::run(xx);
+            if (log2sub0 > 0) apply_twiddles<16>(xx, stw[bi]);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) s[fft_pad(bi + (fft_brev(q, 4) << log2sub0))] = xx[q];
+        }
+        __syncthreads();
+    } else
     // ---- pass 0 forward, fused with the prologue: inputs i = j + p sub0; p >= 8 lies in the zero padding
     {
         float2 xv[8];
@@ -315,17 +353,49 @@ fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, con
             apply_twiddles<16>(xx, make_float2(w1.x, -w1.y));
         }
         Radix<16, true>::run(xx);
+        if constexpr (OLS) {
+            const int tb = (int)blockIdx.y * ols.P - (ols.anti ? 0 : ols.Lk);      // time of window position 0
+            const int lo = ols.anti ? 0 : ols.Lk, hi = ols.anti ? ols.P : 2 * M;   // valid window positions [lo, hi)
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int i = bi + (p << log2sub0);
-            if (vec) {
-                if (i < half) reinterpret_cast<float2 *>(gr)[i] = make_float2(gelu_fast(xx[p].x), gelu_fast(xx[p].y));
-            } else {
-                if (2 * i < l) gr[2 * i] = gelu_fast(xx[p].x);
-                if (2 * i + 1 < l) gr[2 * i + 1] = gelu_fast(xx[p].y);
+            for (int p = 0; p < 16; ++p) {
+                const int pos = 2 * (bi + (p << log2sub0));
+                const float v[2] = {xx[p].x, xx[p].y};
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int t = tb + pos + e;
+                    if (pos + e >= lo && pos + e < hi && t < l)
+                        gr[t] = ols.anti ? v[e] : gelu_fast(v[e] + (ols.partial ? ols.partial[off + t] : 0.f));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const int i = bi + (p << log2sub0);
+                if (vec) {
+                    if (i < half) reinterpret_cast<float2 *>(gr)[i] = make_float2(gelu_fast(xx[p].x), gelu_fast(xx[p].y));
+                } else {
+                    if (2 * i < l) gr[2 * i] = gelu_fast(xx[p].x);
+                    if (2 * i + 1 < l) gr[2 * i + 1] = gelu_fast(xx[p].y);
+                }
             }
         }
     }
+}
+
+template <int LOG2M>
+__global__ void __launch_bounds__(FftCfg<LOG2M>::NT)
+fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
+               long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
+               const float2 *__restrict__ tw /* W_n^i, i < M */, float *__restrict__ g, int B, int H, int l) {
+    fftconv_body<LOG2M, false>(x, stats, part_t, part_stride_b, ln_m, ln_s, kc, tw, g, B, H, l, OlsArgs{});
+}
+
+template <int LOG2M>
+__global__ void __launch_bounds__(FftCfg<LOG2M>::NT)
+fftconv_ols_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
+                   long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
+                   const float2 *__restrict__ tw, float *g, int B, int H, OlsArgs ols) {
+    fftconv_body<LOG2M, true>(x, stats, part_t, part_stride_b, ln_m, ln_s, kc, tw, g, B, H, ols.r, ols);
 }
 
 // =====================================================================================================
@@ -669,6 +739,54 @@ static int launch_fftconv2(const float *x, const float *stats, const float *part
     fftconv2_kernel<LOG2M><<<B * H, Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw, g, B, H, l);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
+}
+
+template <int LOG2M>
+static int launch_fftconv_ols(const float *x, const float *stats, const float *part_t, long long psb, float ln_m,
+                              float ln_s, const float *kc, const float2 *tw, float *g, int B, int H, const OlsArgs &o,
+                              cudaStream_t st) {
+    using Cfg = FftCfg<LOG2M>;
+    static bool attr_set[16] = {};
+    int dev = 0;
+    DWB_CUDA(cudaGetDevice(&dev));
+    if (Cfg::SMEM > 48 * 1024 && !attr_set[dev & 15]) {
+        DWB_CUDA(cudaFuncSetAttribute(fftconv_ols_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_set[dev & 15] = true;
+    }
+    const dim3 grid(B * H, ceil_div(o.r, o.P));
+    fftconv_ols_kernel<LOG2M><<<grid, Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw, g, B, H, o);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+// rows of r > Lk samples against the Lk-tap two-sided kernel: anticausal pass into `partial`, causal pass adds it,
+// applies D and GELU.  kc_c / kc_a: v1-layout (mode 0) tables of (k0, 0, D) and (0, k1, no D) at n = 2 M(Lk).
+int fftconv_ols_launch(const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
+                       const float *kc_c, const float *kc_a, float *g, float *partial, int B, int H, int r, int Lk,
+                       cudaStream_t st) {
+    const int lg = fft_log2m_for(Lk);
+    DWB_REQUIRE(lg > 0, DWB_ERR_UNSUPPORTED, "fftconv: kernel length %d unsupported (max %d)", Lk, 1 << FFT_MAX_LOG2M);
+    DWB_REQUIRE(partial && partial != g && partial != x, DWB_ERR_INVALID, "fftconv_ols: needs a distinct partial-sum buffer");
+    DWB_REQUIRE((int64_t)B * H <= 0x7fffffff && ceil_div(r, (2 << lg) - Lk) <= 65535, DWB_ERR_UNSUPPORTED, "fftconv_ols: grid too large");
+    const float2 *tw;
+    int rc = fft_twiddles(lg, st, &tw);
+    if (rc != DWB_OK) return rc;
+    OlsArgs o{};
+    o.r = r; o.Lk = Lk; o.P = (2 << lg) - Lk;
+#define DWB_OLS_CASE(LG)                                                                                             \
+    case LG:                                                                                                         \
+        o.anti = 1; o.partial = nullptr;                                                                             \
+        rc = launch_fftconv_ols<LG>(x, stats, part_t, psb, ln_m, ln_s, kc_a, tw, partial, B, H, o, st);              \
+        if (rc != DWB_OK) return rc;                                                                                 \
+        o.anti = 0; o.partial = partial;                                                                             \
+        return launch_fftconv_ols<LG>(x, stats, part_t, psb, ln_m, ln_s, kc_c, tw, g, B, H, o, st);
+    switch (lg) {
+        DWB_OLS_CASE(4) DWB_OLS_CASE(5) DWB_OLS_CASE(6) DWB_OLS_CASE(7) DWB_OLS_CASE(8) DWB_OLS_CASE(9)
+        DWB_OLS_CASE(10) DWB_OLS_CASE(11) DWB_OLS_CASE(12) DWB_OLS_CASE(13) DWB_OLS_CASE(14)
+    }
+#undef DWB_OLS_CASE
+    set_error("fftconv_ols: no kernel for log2M=%d", lg);
+    return DWB_ERR_UNSUPPORTED;
 }
 
 int fftconv_launch(const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,

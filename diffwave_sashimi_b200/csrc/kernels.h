@@ -117,5 +117,11 @@ int s4_generate(const float *C, const float *Bp, const float *P, const float *in
                 const float *log_dt, const float *omega, int H, int N, int l, double *khat, double *k64, float *k32,
                 cudaStream_t st, int64_t *launches);
 int fftconv_prepare_f64(const double *k64, const float *D, int H, int l, float *kf, cudaStream_t st);
+// table from the fp32 kernels k (2,H,ld) using their first l taps; dir 0: both directions (fftconv_launch's table for
+// length l), 1: causal only with D, 2: anticausal only without D (the two v1-layout tables of fftconv_ols_launch)
+int fftconv_prepare_f32(const float *k32, int ld, const float *D, int H, int l, int dir, float *kf, cudaStream_t st);
+int fftconv_ols_launch(const float *x, const float *stats, const float *part_t, long long psb, float ln_m, float ln_s,
+                       const float *kc_c, const float *kc_a, float *g, float *partial, int B, int H, int r, int Lk,
+                       cudaStream_t st);
 
 }  // namespace dwb

@@ -345,7 +345,7 @@ int fft_pair_twiddles_launch(float2 *tw2, int log2M, cudaStream_t st) {
 }
 
 template <typename T>
-static int fftconv_prepare_any(const T *k, const float *D, int H, int l, float *kc, cudaStream_t st) {
+static int fftconv_prepare_any(const T *k, const float *D, int H, int l, float *kc, cudaStream_t st, int force_mode = -1) {
     const int log2M = fft_log2m_for(l);
     DWB_REQUIRE(log2M > 0, DWB_ERR_UNSUPPORTED, "fftconv: stage length %d unsupported (max %d)", l, 1 << FFT_MAX_LOG2M);
     const int M = 1 << log2M;
@@ -354,7 +354,7 @@ static int fftconv_prepare_any(const T *k, const float *D, int H, int l, float *
     kf_kernel<T><<<dim3(ceil_div(M + 1, DFT_THREADS), H), DFT_THREADS, 0, st>>>(k, D, H, l, log2M, Kd);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) {
-        const int mode = fft_table_mode(log2M, l);
+        const int mode = force_mode >= 0 ? force_mode : fft_table_mode(log2M, l);
         if (mode == 2) kcoef_compact_kernel<<<dim3(ceil_div(M / 2, 256), H), 256, 0, st>>>(Kd, log2M, kc);
         else kcoef_kernel<<<dim3(ceil_div(M / 2 + 1, 256), H), 256, 0, st>>>(Kd, log2M, mode, kc);
         e = cudaGetLastError();
@@ -466,6 +466,21 @@ int s4_generate(const float *C, const float *Bp, const float *P, const float *in
 
 int fftconv_prepare_f64(const double *k64, const float *D, int H, int l, float *kf, cudaStream_t st) {
     return fftconv_prepare_any<double>(k64, D, H, l, kf, st);
+}
+
+int fftconv_prepare_f32(const float *k32, int ld, const float *D, int H, int l, int dir, float *kf, cudaStream_t st) {
+    DWB_REQUIRE(l >= 1 && l <= ld && dir >= 0 && dir <= 2, DWB_ERR_INVALID, "fftconv_prepare_f32: l=%d ld=%d dir=%d", l, ld, dir);
+    float *tmp = nullptr;                                        // (2,H,l): truncated rows, one direction zeroed
+    DWB_CUDA(cudaMalloc(&tmp, (size_t)2 * H * l * sizeof(float)));
+    cudaError_t e = cudaMemcpy2DAsync(tmp, (size_t)l * sizeof(float), k32, (size_t)ld * sizeof(float), (size_t)l * sizeof(float),
+                                      (size_t)2 * H, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess && dir == 1) e = cudaMemsetAsync(tmp + (size_t)H * l, 0, (size_t)H * l * sizeof(float), st);
+    if (e == cudaSuccess && dir == 2) e = cudaMemsetAsync(tmp, 0, (size_t)H * l * sizeof(float), st);
+    int rc = e == cudaSuccess ? fftconv_prepare_any<float>(tmp, dir == 2 ? nullptr : D, H, l, kf, st, dir == 0 ? -1 : 0)
+                              : cuda_fail(e, "fftconv_prepare_f32", __FILE__, __LINE__);
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    return rc;
 }
 }  // namespace dwb
 

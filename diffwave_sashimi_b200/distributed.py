@@ -2,9 +2,9 @@
 the T-step loop, one all_gather at sample collection.
 
 The reference launches one independent process per GPU with no communication at all
-(generate.py:217-227) and every process draws from its own unseeded generator.  Here the noise of
-the GLOBAL batch is defined once (reference draw order on one seeded CPU generator) and each rank
-takes its contiguous slice, so 1-GPU and N-GPU runs produce identical clips.
+(generate.py:217-227) and every process draws from its own unseeded generator.  Here every clip of
+the GLOBAL batch owns a generator seeded from (seed, global clip index) and consumed in the
+reference's order, so a rank draws only its own clips and 1-GPU and N-GPU runs produce identical clips.
 """
 import os
 
@@ -31,17 +31,21 @@ def shard_range(n_clips, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def draw_noise_sharded(global_size, T, seed, rank, world, chunk=None):
-    """(x_T, noise) for this rank's clips of a global batch `global_size` = (B, 1, L).
-    The stream is the reference's (x_T, then one (B,1,L) draw per step, generate.py:47,54) on a CPU
-    generator seeded with `seed`; every rank draws the same stream and keeps rows [lo, hi)."""
+def draw_noise_sharded(global_size, T, seed, rank, world):
+    """(x_T, noise) for this rank's clips [lo, hi) of a global batch `global_size` = (B, 1, L), materialised.
+    Clip c draws from its own generator seeded with clip_seed(seed, c) in the reference's order (x_T, then one
+    draw per step, generate.py:47,54), so a rank draws only its own rows and 1-GPU and N-GPU runs give
+    identical clips.  `generate_sharded` streams the same draws instead of materialising them."""
+    from .sampler import PerClipNoise, clip_seed
     B = global_size[0]
     lo, hi = shard_range(B, rank, world)
-    g = torch.Generator().manual_seed(seed)
-    x_T = torch.normal(0, 1, size=global_size, generator=g)[lo:hi].clone()
+    src = PerClipNoise([clip_seed(seed, c) for c in range(lo, hi)])
+    x_T = torch.empty((hi - lo,) + tuple(global_size[1:]))
     noise = torch.empty((max(T - 1, 0), hi - lo) + tuple(global_size[1:]))
-    for i in range(T - 1):
-        noise[i] = torch.normal(0, 1, size=global_size, generator=g)[lo:hi]
+    if hi > lo:
+        src.fill(x_T)
+        for i in range(T - 1):
+            src.fill(noise[i])
     return x_T, noise
 
 
@@ -62,11 +66,14 @@ def gather_samples(local, n_clips, rank, world):
 
 @torch.no_grad()
 def generate_sharded(net, n_clips, L, diffusion_hyperparams, seed, condition=None, rank=0, world=1):
-    """Global batch of n_clips through `sampling` semantics, sharded over ranks; returns the full
-    (n_clips, 1, L) batch on every rank."""
-    from .sampler import step_coefficients
+    """Global batch of n_clips through `sampling`, sharded over ranks; returns the full (n_clips, 1, L) batch on
+    every rank.  Per-clip noise streams (sampler.PerClipNoise): the result does not depend on `world`."""
+    from .sampler import PerClipNoise, clip_seed, sampling
+    lo, hi = shard_range(n_clips, rank, world)
     eng = net._engine_get()
-    T = diffusion_hyperparams["T"]
-    x_T, noise = draw_noise_sharded((n_clips, 1, L), T, seed, rank, world)
-    local = eng.sample(x_T.to(eng.device), noise.to(eng.device), step_coefficients(diffusion_hyperparams), condition)
+    if hi > lo:
+        src = PerClipNoise([clip_seed(seed, c) for c in range(lo, hi)])
+        local = sampling(net, (hi - lo, 1, L), diffusion_hyperparams, condition, verbose=False, noise=src)
+    else:
+        local = torch.empty((0, 1, L), device=eng.device)
     return gather_samples(local, n_clips, rank, world)

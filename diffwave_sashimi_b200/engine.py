@@ -24,12 +24,31 @@ def reference_nodes(l: int) -> torch.Tensor:
     return omega ** torch.arange(0, l // 2 + 1)
 
 
-@torch.no_grad()
-def setup_C(C, B, P, inv_w_real, w_imag, log_dt, L: int):
-    """C <- [C~ (I - dA^L)][:N], C~ = [C, conj C], dA the bilinear discretisation of
-    A = diag(w~) - P~ P~^H at step dt (models/s4.py:525-551).  complex128, batched over H."""
+def block_prefixes(cfg):
+    """[(state_dict prefix, H, l)] of every DiffWaveBlock in execution order (layout of Sashimi.__init__,
+    models/sashimi.py:224-275)."""
+    H, l, out, i = cfg["d_model"], cfg["L"], [], 0
+    for p in cfg["pool"]:
+        if cfg.get("unet", True):
+            for _ in range(cfg["n_layers"]):
+                out.append((f"d_layers.{i}.", H, l)); i += 1
+        i += 1
+        l //= p; H *= cfg["expand"]
+    for j in range(cfg["n_layers"]):
+        out.append((f"c_layers.{j}.", H, l))
+    i = 0
+    for p in list(cfg["pool"])[::-1]:
+        H //= cfg["expand"]; l *= p
+        i += 1
+        for _ in range(cfg["n_layers"]):
+            out.append((f"u_layers.{i}.", H, l)); i += 1
+    return out
+
+
+def _dA_power(P, inv_w_real, w_imag, log_dt, L: int):
+    """dA^L (H, 2N, 2N) complex128: dA the bilinear discretisation of A = diag(w~) - P~ P~^H at step dt over the
+    full conjugate-pair state (models/s4.py:815-904), raised by repeated squaring (:206-224)."""
     cd = torch.complex128
-    Cc = torch.view_as_complex(C.double().contiguous()).to(cd)            # (2,H,N)
     Pc = torch.view_as_complex(P.double().contiguous())[0].to(cd)         # (H,N)
     w = torch.complex(-torch.exp(inv_w_real.double()), w_imag.double())   # (H,N)
     dt = torch.exp(log_dt.double())
@@ -45,9 +64,59 @@ def setup_C(C, B, P, inv_w_real, w_imag, log_dt, L: int):
             acc = base @ acc
         base = base @ base
         e >>= 1
+    return acc
+
+
+@torch.no_grad()
+def setup_C(C, B, P, inv_w_real, w_imag, log_dt, L: int):
+    """C <- [C~ (I - dA^L)][:N], C~ = [C, conj C] (models/s4.py:525-551).  complex128, batched over H."""
+    cd = torch.complex128
+    Cc = torch.view_as_complex(C.double().contiguous()).to(cd)            # (2,H,N)
+    acc = _dA_power(P, inv_w_real, w_imag, log_dt, L)
     Ct = torch.cat([Cc, Cc.conj()], -1)
     Ct = Ct - torch.einsum("chn,hnm->chm", Ct, acc)
-    return torch.view_as_real(Ct[..., :N].contiguous()).float()
+    return torch.view_as_real(Ct[..., : Cc.shape[-1]].contiguous()).float()
+
+
+@torch.no_grad()
+def double_C(C, B, P, inv_w_real, w_imag, log_dt, L: int):
+    """Kernel-length doubling of a checkpoint whose kernels were set up for length L (models/s4.py:531-534,
+    `double_length`): C <- C~ (I + dA^L), the inverse bookkeeping of `setup_C`, so that the stored parameter again
+    means C~ (I - dA^{2L}) of the original C~.  complex128, batched over H."""
+    cd = torch.complex128
+    Cc = torch.view_as_complex(C.double().contiguous()).to(cd)
+    dA_L = _dA_power(P, inv_w_real, w_imag, log_dt, L)
+    Ct = torch.cat([Cc, Cc.conj()], -1)
+    Ct = Ct + torch.einsum("chn,hnm->chm", Ct, dA_L)
+    return torch.view_as_real(Ct[..., : Cc.shape[-1]].contiguous()).float()
+
+
+@torch.no_grad()
+def rewrite_fresh_kernels(blocks, sd):
+    """In `sd`: bring every S4 kernel to its stage length l.  kernel.L == 0 (fresh model): the one-off C rewrite
+    the reference does on its first forward (models/s4.py:525-551); kernel.L = l / 2^k (checkpoint trained on
+    shorter segments): k doublings (s4.py:531-534).  Runs on whatever device the tensors live on.
+    Yields (key prefix, new C, l) for every rewritten block."""
+    for (p, H, l) in blocks:
+        k = p + "layer.kernel.kernel."
+        Lcur = int(sd[k + "L"])
+        if Lcur == l:
+            continue
+        args = (sd[k + "B"], sd[k + "P"], sd[k + "inv_w_real"], sd[k + "w_imag"], sd[k + "log_dt"])
+        if Lcur == 0:
+            newC = setup_C(sd[k + "C"], *args, l)
+        else:
+            if Lcur > l or l % Lcur or (l // Lcur) & (l // Lcur - 1):
+                raise ValueError(f"{k}L = {Lcur} cannot be doubled to the stage length {l} (models/s4.py:531-534 doubles; "
+                                 f"a kernel set up for a LONGER length cannot be shortened exactly)")
+            newC = sd[k + "C"]
+            while Lcur < l:
+                newC = double_C(newC, *args, Lcur)
+                Lcur *= 2
+        newC = newC.to(sd[k + "C"].device)
+        sd[k + "C"] = newC
+        sd[k + "L"] = torch.tensor(l)
+        yield k, newC, l
 
 
 class Engine:
@@ -97,48 +166,18 @@ class Engine:
 
     # ---- weights ------------------------------------------------------------------------
     def _block_prefixes(self):
-        from .models import Sashimi  # noqa: F401  (layout mirrors Sashimi.__init__)
-        cfg = self.cfg
-        H, l, out, i = cfg["d_model"], cfg["L"], [], 0
-        for p in cfg["pool"]:
-            if cfg.get("unet", True):
-                for _ in range(cfg["n_layers"]):
-                    out.append((f"d_layers.{i}.", H, l)); i += 1
-            i += 1
-            l //= p; H *= cfg["expand"]
-        for j in range(cfg["n_layers"]):
-            out.append((f"c_layers.{j}.", H, l))
-        i = 0
-        for p in list(cfg["pool"])[::-1]:
-            H //= cfg["expand"]; l *= p
-            i += 1
-            for _ in range(cfg["n_layers"]):
-                out.append((f"u_layers.{i}.", H, l)); i += 1
-        return out
+        return block_prefixes(self.cfg)
 
     @torch.no_grad()
     def _load(self, sd, module, nodes):
         st = stream_ptr(self.device)
         if self.sashimi:
-            lengths = set()
-            for (p, H, l) in self._block_prefixes():
-                k = p + "layer.kernel.kernel."
-                lengths.add(l)
-                Lcur = int(sd[k + "L"])
-                if Lcur == 0:      # fresh checkpoint: the reference rewrites C on its first forward
-                    newC = setup_C(sd[k + "C"], sd[k + "B"], sd[k + "P"], sd[k + "inv_w_real"], sd[k + "w_imag"],
-                                   sd[k + "log_dt"], l).to(sd[k + "C"].device)
-                    sd[k + "C"] = newC
-                    sd[k + "L"] = torch.tensor(l)
-                    if module is not None:   # keep the module's state identical to the reference's after a forward
-                        tgt = dict(module.named_parameters())[k + "C"]
-                        tgt.copy_(newC)
-                        dict(module.named_buffers())[k + "L"].fill_(l)
-                elif Lcur != l:
-                    raise NotImplementedError(
-                        f"{k}L = {Lcur} but the stage length is {l}: kernel length doubling (s4.py:531-534) is not built")
+            for k, newC, l in rewrite_fresh_kernels(self._block_prefixes(), sd):
+                if module is not None:   # keep the module's state identical to the reference's after a forward
+                    dict(module.named_parameters())[k + "C"].copy_(newC)
+                    dict(module.named_buffers())[k + "L"].fill_(l)
             if nodes != "exact":
-                for l in sorted(lengths):
+                for l in sorted({l for (_, _, l) in self._block_prefixes()}):
                     om = reference_nodes(l) if nodes == "reference" else (
                         torch.tensor(np.exp(-2j * np.pi / l), dtype=torch.complex64, device=self.device)
                         ** torch.arange(0, l // 2 + 1, device=self.device)).cpu()
@@ -169,9 +208,12 @@ class Engine:
         """(cond_batch, sum_i H_i l_i) conditioning features from a mel (cb, 80, frames): per block
         two weight-normed ConvTranspose2d + leaky-ReLU(0.4), crop to the FIRST l_i samples, 1x1
         80 -> H_i (models/sashimi.py:160-175, models/wavenet.py:98-111).  t-independent."""
-        key = (mel.data_ptr(), tuple(mel.shape), mel._version, L)
-        if self._cond_cache is not None and self._cond_cache[0] == key:
-            return self._cond_cache[1]
+        # the cache entry keeps the source tensor alive and is matched by identity: a freed mel's address (and
+        # _version 0) is routinely handed to the next same-shape allocation, so pointer keys would alias utterances
+        c = self._cond_cache
+        if c is not None and c["mel"] is mel and c["version"] == mel._version and c["L"] == L:
+            return c["out"]
+        src = mel
         mel = mel.to(self.device, torch.float32).contiguous()
         cb, bands, frames = mel.shape
         if bands != self._c.mel_bands:
@@ -181,7 +223,7 @@ class Engine:
         out = torch.empty(cb * total, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(lib().dwb_plan_cond_features(self._plan, ptr(mel), cb, frames, L, ptr(out), stream_ptr(self.device)))
-        self._cond_cache = (key, out)
+        self._cond_cache = {"mel": src, "version": src._version, "L": L, "out": out}
         return out
 
     # ---- hot path -----------------------------------------------------------------------
@@ -227,6 +269,45 @@ class Engine:
             check(lib().dwb_sample(self._plan, ptr(x_T), ptr(noise) if T > 1 else None, ptr(cond), cb, cp, T, ptr(out),
                                    B, L, int(use_graph), stream_ptr(self.device)))
         return out
+
+    @torch.no_grad()
+    def sample_steps(self, x, noise, coef, t_start, n_steps, mel_spec=None, use_graph=True):
+        """Advance x (B,1,L), in place, by the reverse steps t_start, t_start-1, ... (n_steps of them) of the
+        schedule `coef` (3,T).  noise (n_draws,B,1,L) on the device: draw i is used at step t_start - i and none
+        at t = 0.  The streaming form of `sample` (dwb_sample_steps): `sampling()` draws the noise of later
+        steps on the CPU generator while earlier steps run."""
+        B, _, L = x.shape
+        T = coef.shape[1]
+        assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
+        need = n_steps if t_start - n_steps + 1 > 0 else n_steps - 1
+        if need > 0:
+            assert noise.is_cuda and noise.is_contiguous() and noise.dtype == torch.float32 and noise.shape[0] >= need
+        cond, cb = self._cond(mel_spec, L)
+        coef = coef.detach().to("cpu", torch.float32).contiguous()
+        cp = coef.numpy().ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        with torch.cuda.device(self.device):
+            check(lib().dwb_sample_steps(self._plan, ptr(x), ptr(noise) if need > 0 else None, ptr(cond), cb, cp, T,
+                                         t_start, n_steps, B, L, int(use_graph), stream_ptr(self.device)))
+        return x
+
+    def staging(self, B, L, steps):
+        """Reusable staging for `sampling()`: two pinned host chunks of `steps` noise draws, their device twins, a
+        pinned x_T, a copy stream and the events that order their reuse.  Kept per (B, L, steps) so repeated calls
+        neither page-fault nor pin 800 MB again."""
+        key = (B, L, steps)
+        st = getattr(self, "_staging", None)
+        if st is None or st["key"] != key:
+            with torch.cuda.device(self.device):
+                st = {"key": key,
+                      "host": [torch.empty((steps, B, 1, L), pin_memory=True) for _ in range(2)],
+                      "dev": [torch.empty((steps, B, 1, L), device=self.device) for _ in range(2)],
+                      "x_host": torch.empty((B, 1, L), pin_memory=True),
+                      "copied": [None, None],       # event: H2D of host[i] finished -> host[i] may be redrawn
+                      "consumed": [None, None],     # event: the steps reading dev[i] finished -> dev[i] may be overwritten
+                      "x_copied": None,
+                      "stream": torch.cuda.Stream(device=self.device)}
+            self._staging = st
+        return st
 
     @torch.no_grad()
     def profile(self, audio, diffusion_steps, mel_spec=None, iters=3):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DWB_VERSION 100
+#define DWB_VERSION 200
 
 enum dwb_status {
     DWB_OK = 0,
@@ -107,10 +107,21 @@ int dwb_forward(dwb_plan *plan, const float *x, const float *t, const float *con
  *                              row 2 = sigma_t      (utils.py:121-151, computed by the caller in
  *                              torch fp32 so the tables are bit-identical to the reference's)
  *   out        (B,1,L)
- *   use_graph  1: the whole T-step loop is captured once into a CUDA graph (cached on
- *                 (B, L, T, pointers)) and replayed; 0: plain stream launches */
+ *   use_graph  1: ONE diffusion step (every kernel of a network evaluation + the fused DDPM update) is captured once
+ *                 into a CUDA graph and replayed T times.  The step's fc_t rows and coefficients are read from a
+ *                 plan-owned device record refreshed by a stream-ordered copy before each replay, x lives in a
+ *                 plan-owned buffer and the noise pointer behind a device word, so the graph is keyed on
+ *                 (B, L, cond, cond_batch) only: new x_T / noise / out buffers, another T or schedule never re-capture.
+ *              0: plain stream launches */
 int dwb_sample(dwb_plan *plan, const float *x_T, const float *noise, const float *cond, int cond_batch,
                const float *coef_host, int T, float *out, int B, int L, int use_graph, void *stream);
+
+/* Streaming form of dwb_sample: advance x (B,1,L), in place, by the n_steps reverse steps t_start, t_start-1, ...
+ * of a T-step schedule.  noise (n_draws,B,1,L): draw i is used at step t_start - i (no draw is read at t = 0).
+ * Lets the caller produce the noise of later steps (generate.py:54 draws it on the CPU, one draw per step) while
+ * earlier steps run:   x = x_T;  for each chunk: dwb_sample_steps(x, chunk_noise, ..., t_start, n_steps). */
+int dwb_sample_steps(dwb_plan *plan, float *x, const float *noise, const float *cond, int cond_batch,
+                     const float *coef_host, int T, int t_start, int n_steps, int B, int L, int use_graph, void *stream);
 
 /* conditioning feature layout: number of blocks and, per block, channels H_i and length l_i;
  * features for block i are (cond_batch, H_i, l_i) f32 at float offset cond_batch * offset_i.

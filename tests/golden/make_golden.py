@@ -79,8 +79,11 @@ def save(name, **arrs):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--extra", action="store_true", help="round-2 fixtures only (new files; the round-1 files are left untouched)")
     args = ap.parse_args()
     ns = refshim.load(parity=True)
+    if args.extra:
+        return make_extra(ns)
 
     # --- schedule ---------------------------------------------------------------------
     for tag, kw in (("T200", dict(T=200, beta_0=1e-4, beta_T=0.02)), ("T50", dict(T=50, beta_0=1e-4, beta_T=0.05)),
@@ -194,6 +197,109 @@ def make_full(ns):
             for tv in (tval, 0.0):
                 outs[f"eps_t{int(tv)}"] = net((x, tv * torch.ones(B, 1)), mel_spec=mel).numpy()
         save(name, cfg=np.array(repr(dict(cfg))), seed=0, xseed=5, **outs)
+
+
+def make_extra(ns):
+    """Round-2 fixtures (all from the unmodified reference):
+      full2_<cfg>.npz            eps at B=2 with DISTINCT steps per row, t = (1, T-1), all five BASELINE configs
+      trajfull_<cfg>.npz         x_0 of the complete T-step generate.sampling() at BASELINE size with the last conv
+                                 rescaled so that std(eps) ~ 1 (otherwise x_0 is all injected noise)
+      lengths_<tiny>.npz         eps of tiny models at sequence lengths below and above the configured l_max
+                                 (kernel truncation / L > l_max, models/s4.py:1387,1403-1406)
+      full_unet_d32_cond_L51200  the LJSpeech vocoder config on a 200-frame utterance (generate.py:135-156)
+      s4double_*.npz             kernel-length doubling of a set-up kernel (models/s4.py:531-534)
+    """
+    import diffwave_sashimi_b200 as dwb
+    only = os.environ.get("GOLDEN_EXTRA", "").split(",") if os.environ.get("GOLDEN_EXTRA") else None
+    want = lambda tag: only is None or tag in only
+
+    if want("double"):
+        for H, L in ((2, 250), (3, 64)):
+            torch.manual_seed(3)
+            s4 = ns.s4.S4(H, l_max=L, bidirectional=True).eval()
+            with torch.no_grad():
+                s4.kernel(L=L, rate=1.0)                   # _setup_C at L
+                sd1 = {k: v.clone() for k, v in s4.state_dict().items()}
+                k2, _ = s4.kernel(L=2 * L, rate=1.0)       # doubles to 2L (s4.py:723-724 -> :531-534)
+                sd2 = {k: v.clone() for k, v in s4.state_dict().items()}
+                k4, _ = s4.kernel(L=4 * L, rate=1.0)
+                sd4 = {k: v.clone() for k, v in s4.state_dict().items()}
+            save(f"s4double_H{H}_L{L}", k2=k2.numpy(), k4=k4.numpy(),
+                 **{"sd0/" + kk: v.numpy() for kk, v in sd1.items()}, **{"sd1/" + kk: v.numpy() for kk, v in sd2.items()},
+                 **{"sd/" + kk: v.numpy() for kk, v in sd4.items()})
+
+    if want("lengths"):
+        for name, lens, hop in (("tiny_unet", (128, 64, 512, 1024, 2304), None), ("tiny_snet", (160, 640), None),
+                                ("tiny_unet_cond", (256, 1024, 2048), 256)):
+            spec = TINY[name]
+            cfg, net = build(ns, spec["base"], spec["over"])
+            with torch.no_grad():                           # same settled weights as <name>.npz
+                g = torch.Generator().manual_seed(11)
+                x = torch.randn(spec["B"], 1, spec["L"], generator=g)
+                t = torch.tensor([[3.], [17.], [0.]])[:spec["B"]]
+                mel = torch.randn(*spec["mel"], generator=g) if "mel" in spec else None
+                net((x, t), mel_spec=mel)
+            arrs = {}
+            for Lr in lens:
+                g = torch.Generator().manual_seed(100 + Lr)
+                x = torch.randn(2, 1, Lr, generator=g)
+                t = torch.tensor([[5.], [40.]])
+                mel = torch.randn(1, 80, Lr // hop + 1, generator=g) if hop else None
+                with torch.no_grad():
+                    eps = net((x, t), mel_spec=mel)
+                arrs[f"x_{Lr}"], arrs[f"eps_{Lr}"] = x.numpy(), eps.numpy()
+                if mel is not None:
+                    arrs[f"mel_{Lr}"] = mel.numpy()
+            save("lengths_" + name, t=t.numpy(), **arrs)
+
+    T_OF = {"wnet_h128_d30": 200, "unet_d64": 200, "unet_d32_cond": 50, "unet_d128": 200, "wnet_h256_d36": 200}
+    if want("full2"):
+        for name, (base, _, _, melshape) in FULL.items():
+            T = T_OF[base]
+            cfg = refshim.Cfg(refshim.MODEL_CFGS[base])
+            net = ns.models.construct_model(cfg).eval()
+            net.load_state_dict(dwb.init.seeded_state_dict(dict(cfg), seed=0))
+            g = torch.Generator().manual_seed(6)
+            x = torch.randn(2, 1, 16000, generator=g)
+            mel = torch.randn(*melshape, generator=g) if melshape else None
+            t = torch.tensor([[1.0], [float(T - 1)]])
+            with torch.no_grad():
+                eps = net((x, t), mel_spec=mel).numpy()
+            save(name.replace("full_", "full2_"), cfg=np.array(repr(dict(cfg))), seed=0, xseed=6, t=t.numpy(), eps=eps)
+
+    if want("long"):
+        base, frames = "unet_d32_cond", 200
+        cfg = refshim.Cfg(refshim.MODEL_CFGS[base])
+        net = ns.models.construct_model(cfg).eval()
+        net.load_state_dict(dwb.init.seeded_state_dict(dict(cfg), seed=0))
+        g = torch.Generator().manual_seed(7)
+        Lr = frames * 256
+        x = torch.randn(1, 1, Lr, generator=g)
+        mel = torch.randn(1, 80, frames, generator=g)
+        with torch.no_grad():
+            eps = net((x, torch.full((1, 1), 25.0)), mel_spec=mel).numpy()
+        save("full_unet_d32_cond_L51200", cfg=np.array(repr(dict(cfg))), seed=0, xseed=7, frames=frames, t=25.0, eps=eps)
+
+    if want("traj"):
+        for base, melshape, beta_T in (("unet_d32_cond", (1, 80, 63), 0.05), ("unet_d64", None, 0.02)):
+            T = T_OF[base]
+            cfg = refshim.Cfg(refshim.MODEL_CFGS[base])
+            net = ns.models.construct_model(cfg).eval()
+            net.load_state_dict(dwb.init.seeded_state_dict(dict(cfg), seed=0))
+            g = torch.Generator().manual_seed(8)
+            mel = torch.randn(*melshape, generator=g) if melshape else None
+            x = torch.randn(1, 1, 16000, generator=g)
+            with torch.no_grad():
+                e = net((x, torch.full((1, 1), float(T // 2))), mel_spec=mel)
+                scale = float(1.0 / e.std())
+                net.final_conv[2].conv.weight.mul_(scale)
+                net.final_conv[2].conv.bias.mul_(scale)
+                e2 = net((x, torch.full((1, 1), float(T // 2))), mel_spec=mel)
+            dh = ns.utils.calc_diffusion_hyperparams(T=T, beta_0=1e-4, beta_T=beta_T, fast=True)
+            torch.manual_seed(4242)
+            x0 = ns.generate.sampling(net, (1, 1, 16000), dh, condition=mel)
+            save("trajfull_" + base, cfg=np.array(repr(dict(cfg))), seed=0, melseed=8, noise_seed=4242, T=T, beta_0=1e-4,
+                 beta_T=beta_T, final_scale=scale, eps_std_after=float(e2.std()), x0=x0.numpy())
 
 
 if __name__ == "__main__":

@@ -37,7 +37,7 @@ def test_header_symbols_exported_and_bound(dwb):
         assert hasattr(lib, s), f"{s} declared in dwb.h but not exported"
     # every declared entry has a ctypes signature in the binding (and nothing extra)
     assert sorted(list(_lib.SIGNATURES) + ["dwb_last_error"]) == syms
-    assert _lib.lib().dwb_version() == 100
+    assert _lib.lib().dwb_version() == 200
 
 
 def test_struct_layout_matches_header(dwb):
@@ -135,6 +135,29 @@ def test_noise_draw_order_matches_reference(dwb):
         assert torch.equal(noise[i], ref[i + 1])
     ox, on = O.draw_noise(99, (2, 1, 50), 5)
     assert torch.equal(ox, x_T) and torch.equal(on, noise)
+
+
+def test_noise_sources_match_reference_draws(dwb):
+    """`sampling()` fills reusable pinned buffers in place; that must consume the generators exactly like the
+    reference's `torch.normal(0, 1, size=size)` per step (generate.py:47,54)."""
+    from diffwave_sashimi_b200.sampler import GlobalNoise, PerClipNoise, clip_seed, chunk_steps_for
+    size = (3, 1, 160)
+    torch.manual_seed(7)
+    ref = [torch.normal(0, 1, size=size) for _ in range(4)]
+    torch.manual_seed(7)
+    src, buf = GlobalNoise(), torch.empty((4,) + size)
+    for i in range(4):
+        src.fill(buf[i])
+    assert torch.equal(buf, torch.stack(ref))
+    seeds = [clip_seed(11, c) for c in range(3)]
+    assert len(set(seeds)) == 3 and all(0 <= s < 2 ** 63 for s in seeds)
+    pc, got = PerClipNoise(seeds), torch.empty((2,) + size)
+    pc.fill(got[0]); pc.fill(got[1])
+    for c, sd in enumerate(seeds):
+        torch.manual_seed(sd)
+        a, b = torch.normal(0, 1, size=(1, 1, 160)), torch.normal(0, 1, size=(1, 1, 160))
+        assert torch.equal(got[0, c:c + 1], a) and torch.equal(got[1, c:c + 1], b)
+    assert chunk_steps_for(64, 16000, 200) == 8 and chunk_steps_for(1, 16, 1) == 1 and chunk_steps_for(2, 1000, 5) == 4
 
 
 @pytest.mark.parametrize("H,L", [(4, 64), (3, 100), (2, 250), (2, 1000)])

@@ -59,10 +59,13 @@ def test_two_ranks_match_one(n_clips):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    # single-process reference of the same global batch (and the oracle's draw order)
+    # single-process run of the same global batch; every clip's stream is the reference's draw order for a
+    # batch of ONE clip under that clip's seed (oracle restatement of generate.py:47,54)
+    from diffwave_sashimi_b200.sampler import clip_seed
     x_T, noise = D.draw_noise_sharded((n_clips, 1, L), T, seed, 0, 1)
-    ox, on = O.draw_noise(seed, (n_clips, 1, L), T)
-    assert torch.equal(x_T, ox) and torch.equal(noise, on)
+    for c in range(n_clips):
+        ox, on = O.draw_noise(clip_seed(seed, c), (1, 1, L), T)
+        assert torch.equal(x_T[c:c + 1], ox) and torch.equal(noise[:, c:c + 1], on)
     assert torch.equal(full, _fake_sampler(x_T, noise))
     assert tmax == 2.0
 
