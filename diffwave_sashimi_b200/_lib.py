@@ -55,6 +55,9 @@ SIGNATURES = {
     "dwb_plan_work": [_P, _I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
     "dwb_plan_profile": [_P, _P, _P, _P, _I, _P, _I, _I, _I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64), _P],
     "dwb_cauchy_sym_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "dwb_cauchy_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "dwb_cauchy_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "dwb_cauchy_sym_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "dwb_s4_kernel_gen": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
     "dwb_fftconv_size": [_I, ctypes.POINTER(_I)],
     "dwb_fftconv_prepare": [_P, _P, _I, _I, _P, _P],

@@ -30,16 +30,85 @@ def cauchy_mult_sym_fwd(v, z, w):
     return out
 
 
+def _c64(t):
+    return ptr(torch.view_as_real(t))
+
+
+def _check_vzw(name, v, z, w, dout=None):
+    if v.dim() != 2 or w.shape != v.shape or z.dim() != 1 or (dout is not None and dout.shape != (v.shape[0], z.shape[0])):
+        raise RuntimeError(f"{name}: v, w must be (batch, N), z (L)" + (", dout (batch, L)" if dout is not None else ""))
+
+
+def cauchy_mult_fwd(v, z, w):
+    """`cauchy_mult.cauchy_mult_fwd(v, z, w)` (cauchy.cpp:27-38): out[b,l] = sum_n v/(z - w), N the FULL state size."""
+    v, z, w = _cuda(v, torch.complex64), _cuda(z, torch.complex64), _cuda(w, torch.complex64)
+    _check_vzw("cauchy_mult_fwd", v, z, w)
+    out = torch.empty(v.shape[0], z.shape[0], dtype=torch.complex64, device=v.device)
+    with torch.cuda.device(v.device):
+        check(lib().dwb_cauchy_fwd(_c64(v), _c64(z), _c64(w), _c64(out), v.shape[0], v.shape[1], z.shape[0], stream_ptr(v.device)))
+    return out
+
+
+def _bwd(fn, name, v, z, w, dout):
+    v, z, w, dout = (_cuda(t, torch.complex64) for t in (v, z, w, dout))
+    _check_vzw(name, v, z, w, dout)
+    dv, dw = torch.empty_like(v), torch.empty_like(w)
+    with torch.cuda.device(v.device):
+        check(fn(_c64(v), _c64(z), _c64(w), _c64(dout), _c64(dv), _c64(dw), v.shape[0], v.shape[1], z.shape[0],
+                 stream_ptr(v.device)))
+    return dv, dw
+
+
+def cauchy_mult_bwd(v, z, w, dout):
+    """`cauchy_mult.cauchy_mult_bwd(v, z, w, dout)` -> (dv, dw)   (cauchy.cpp:40-53)"""
+    return _bwd(lib().dwb_cauchy_bwd, "cauchy_mult_bwd", v, z, w, dout)
+
+
+def cauchy_mult_sym_bwd(v, z, w, dout):
+    """`cauchy_mult.cauchy_mult_sym_bwd(v, z, w, dout)` -> (dv, dw)   (cauchy.cpp:68-82)"""
+    return _bwd(lib().dwb_cauchy_sym_bwd, "cauchy_mult_sym_bwd", v, z, w, dout)
+
+
+class _CauchyMultiply(torch.autograd.Function):
+    """extensions/cauchy/cauchy.py:65-86 on libdwb (no restriction on N or L)."""
+
+    @staticmethod
+    def forward(ctx, v, z, w):
+        ctx.save_for_backward(v, z, w)
+        return cauchy_mult_fwd(v, z, w)
+
+    @staticmethod
+    def backward(ctx, dout):
+        v, z, w = ctx.saved_tensors
+        dv, dw = cauchy_mult_bwd(v, z, w, dout.contiguous())
+        return dv, None, dw
+
+
+class _CauchyMultiplySymmetric(torch.autograd.Function):
+    """extensions/cauchy/cauchy.py:89-111 on libdwb."""
+
+    @staticmethod
+    def forward(ctx, v, z, w):
+        ctx.save_for_backward(v, z, w)
+        return cauchy_mult_sym_fwd(v, z, w)
+
+    @staticmethod
+    def backward(ctx, dout):
+        v, z, w = ctx.saved_tensors
+        dv, dw = cauchy_mult_sym_bwd(v, z, w, dout.contiguous())
+        return dv, None, dw
+
+
 def cauchy_mult(v, z, w, symmetric=True):
-    """Shape-handling wrapper with the semantics of extensions/cauchy/cauchy.py:46-63."""
-    if not symmetric:
-        raise NotImplementedError("only the symmetric forward is on the inference path (models/s4.py:758)")
+    """Shape-handling, differentiable wrapper with the semantics of extensions/cauchy/cauchy.py:46-63
+    (symmetric: v, w are the HALF spectra, as models/s4.py:758 passes them)."""
     v, w = torch.broadcast_tensors(v, w)
     shape = v.shape
     z = z.squeeze()
     assert z.dim() == 1
     N = v.size(-1)
-    y = cauchy_mult_sym_fwd(v.reshape(-1, N), z, w.reshape(-1, N))
+    fn = _CauchyMultiplySymmetric if symmetric else _CauchyMultiply
+    y = fn.apply(v.contiguous().view(-1, N), z.contiguous(), w.contiguous().view(-1, N))
     return y.view(*shape[:-1], z.size(-1))
 
 

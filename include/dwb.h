@@ -174,6 +174,19 @@ int dwb_plan_profile(dwb_plan *plan, const float *x, const float *t, const float
 int dwb_cauchy_sym_fwd(const float *v, const float *z, const float *w, float *out,
                        int batch, int N, int L, void *stream);
 
+/* The other three entries of the reference module `cauchy_mult` (extensions/cauchy/cauchy.cpp:86-95), same layouts:
+ *   dwb_cauchy_fwd      out[b,l] = sum_n v[b,n] / (z[l] - w[b,n])       (cauchy_mult_fwd; N = FULL state size, any N >= 1,
+ *                                                                         any L: the reference needs N = 64, L % 32 == 0)
+ *   dwb_cauchy_bwd      dv (batch,N), dw (batch,N) from dout (batch,L)    (cauchy_mult_bwd,     cauchy_cuda.cu:139-239)
+ *   dwb_cauchy_sym_bwd  the same for the symmetric op, N = half size      (cauchy_mult_sym_bwd, cauchy_cuda.cu:377-487)
+ * Gradients follow PyTorch's complex convention (conjugate Wirtinger), i.e. what the reference's autograd.Functions
+ * return from backward (extensions/cauchy/cauchy.py:82-86,107-111). */
+int dwb_cauchy_fwd(const float *v, const float *z, const float *w, float *out, int batch, int N, int L, void *stream);
+int dwb_cauchy_bwd(const float *v, const float *z, const float *w, const float *dout, float *dv, float *dw,
+                   int batch, int N, int L, void *stream);
+int dwb_cauchy_sym_bwd(const float *v, const float *z, const float *w, const float *dout, float *dv, float *dw,
+                       int batch, int N, int L, void *stream);
+
 /* S4 NPLR kernel generation for one layer (models/s4.py:674-807, rank 1, bidirectional):
  * parameters exactly as stored in the state_dict (f32): C (2,H,N,2) B (1,H,N,2) P (1,H,N,2)
  * inv_w_real (H,N) w_imag (H,N) log_dt (H); omega (l/2+1,2) complex64 nodes or NULL for exact

@@ -126,6 +126,104 @@ def test_baseline_size_vs_reference_golden(dwb, name):
         assert e2 < TOL and em < TOL
 
 
+FULL_T = {"wnet_h128_d30": 200, "unet_d64": 200, "unet_d32_cond": 50, "unet_d128": 200, "wnet_h256_d36": 200}
+
+
+@pytest.mark.parametrize("name", list(FULL))
+def test_baseline_size_batch_of_distinct_steps(dwb, name):
+    """B = 2 with a DIFFERENT diffusion step per row, t = (1, T-1): the per-row fc_t path at BASELINE size."""
+    from oracle.refshim import MODEL_CFGS
+    fname, melshape = FULL[name]
+    g = load_golden(fname.replace("full_", "full2_"))
+    cfg = dict(MODEL_CFGS[name])
+    net = _model(dwb, cfg, dwb.init.seeded_state_dict(cfg, seed=0))
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 1, 16000, generator=gen)
+    mel = torch.randn(*melshape, generator=gen) if melshape else None
+    t = torch.from_numpy(g["t"])
+    assert t.flatten().tolist() == [1.0, float(FULL_T[name] - 1)]
+    with torch.no_grad():
+        eps = net((x.cuda(), t.cuda()), mel_spec=None if mel is None else mel.cuda()).cpu()
+    for b in range(2):
+        e2, em = rel_l2(eps[b], g["eps"][b]), rel_max(eps[b], g["eps"][b])
+        print(f"{name} B=2 row {b} t={t[b].item():.0f}: rel_l2 {e2:.2e} rel_max {em:.2e}")
+        assert e2 < TOL and em < TOL
+
+
+@pytest.mark.parametrize("name,melshape", [("unet_d32_cond", (1, 80, 63)), ("unet_d64", None)])
+def test_full_trajectory_vs_reference(dwb, name, melshape):
+    """x_0 of the COMPLETE T-step loop at BASELINE size against generate.sampling() of the unmodified reference on the
+    same seeded CPU noise, with the last conv rescaled so that std(eps) ~ 1 (otherwise x_0 is all injected noise and
+    cannot see the network)."""
+    from oracle.refshim import MODEL_CFGS
+    path = os.path.join(GOLDEN, f"trajfull_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip("full trajectory golden not generated")
+    g = load_golden(f"trajfull_{name}")
+    cfg = dict(MODEL_CFGS[name])
+    sd = dwb.init.seeded_state_dict(cfg, seed=0)
+    sc = float(g["final_scale"])
+    sd["final_conv.2.conv.weight"] = sd["final_conv.2.conv.weight"] * sc
+    sd["final_conv.2.conv.bias"] = sd["final_conv.2.conv.bias"] * sc
+    net = _model(dwb, cfg, sd)
+    gen = torch.Generator().manual_seed(int(g["melseed"]))
+    mel = torch.randn(*melshape, generator=gen).cuda() if melshape else None
+    T = int(g["T"])
+    dh = dwb.calc_diffusion_hyperparams(T, float(g["beta_0"]), float(g["beta_T"]), fast=True)
+    torch.manual_seed(int(g["noise_seed"]))
+    x0 = dwb.sampling(net, (1, 1, 16000), dh, condition=mel, verbose=False).cpu()
+    e2, em = rel_l2(x0, g["x0"]), rel_max(x0, g["x0"])
+    print(f"full trajectory {name} T={T}: rel_l2 {e2:.2e} rel_max {em:.2e} (eps std {float(g['eps_std_after']):.2f}, x0 std {x0.std():.2f})")
+    assert e2 < TOL and em < TOL
+
+
+LENGTHS = [("tiny_unet", 128), ("tiny_unet", 64), ("tiny_unet", 512), ("tiny_unet", 1024), ("tiny_unet", 2304),
+           ("tiny_snet", 160), ("tiny_snet", 640), ("tiny_unet_cond", 256), ("tiny_unet_cond", 1024), ("tiny_unet_cond", 2048)]
+
+
+@pytest.mark.parametrize("name,Lr", LENGTHS)
+def test_other_sequence_lengths_vs_reference_golden(dwb, name, Lr):
+    """L < l_max: the cached kernel's first L taps; L > l_max: overlap-save blocks of the l_max-tap kernel
+    (models/s4.py:1387,1403-1406).  One plan serves every length."""
+    g, gl = load_golden(name), load_golden("lengths_" + name)
+    net = _model(dwb, g["cfg"], g["sd"])
+    t = torch.from_numpy(gl["t"]).cuda()
+    for L2 in (Lr, g["x"].shape[-1], Lr):          # other length, configured length, other length again (cached tables)
+        if L2 == g["x"].shape[-1]:
+            x, ref = torch.from_numpy(g["x"]), g["eps"]
+            tt = torch.from_numpy(g["t"]).cuda()
+            mel = torch.from_numpy(g["mel"]).cuda() if "mel" in g else None
+        else:
+            x, ref, tt = torch.from_numpy(gl[f"x_{L2}"]), gl[f"eps_{L2}"], t
+            mel = torch.from_numpy(gl[f"mel_{L2}"]).cuda() if f"mel_{L2}" in gl else None
+        with torch.no_grad():
+            eps = net((x.cuda(), tt), mel_spec=mel).cpu()
+        e2, em = rel_l2(eps, ref), rel_max(eps, ref)
+        print(f"{name} L={L2}: rel_l2 {e2:.2e} rel_max {em:.2e}")
+        assert e2 < 1e-4 and em < 1e-4
+
+
+def test_long_utterance_vocoder_vs_reference_golden(dwb):
+    """configs[3] on a 200-frame utterance: L = 51200 = 3.2 l_max (generate.py:156 audio_length = frames * hop)."""
+    from oracle.refshim import MODEL_CFGS
+    g = load_golden("full_unet_d32_cond_L51200")
+    cfg = dict(MODEL_CFGS["unet_d32_cond"])
+    net = _model(dwb, cfg, dwb.init.seeded_state_dict(cfg, seed=0))
+    gen = torch.Generator().manual_seed(7)
+    frames = int(g["frames"])
+    x = torch.randn(1, 1, frames * 256, generator=gen)
+    mel = torch.randn(1, 80, frames, generator=gen)
+    with torch.no_grad():
+        eps = net((x.cuda(), torch.full((1, 1), float(g["t"])).cuda()), mel_spec=mel.cuda()).cpu()
+    e2, em = rel_l2(eps, g["eps"]), rel_max(eps, g["eps"])
+    print(f"unet_d32_cond L=51200: rel_l2 {e2:.2e} rel_max {em:.2e}")
+    assert e2 < TOL and em < TOL
+    dh = dwb.calc_diffusion_hyperparams(4, 1e-4, 0.05, fast=True)      # and the sampler at that length
+    torch.manual_seed(1)
+    x0 = dwb.sampling(net, (2, 1, frames * 256), dh, condition=mel.cuda(), verbose=False)
+    assert bool(torch.isfinite(x0).all())
+
+
 @pytest.mark.parametrize("name,B", [("unet_d64", 2), ("wnet_h128_d30", 1)])
 def test_baseline_size_vs_oracle_fp64(dwb, name, B):
     from oracle.refshim import MODEL_CFGS
@@ -225,9 +323,9 @@ def test_errors(dwb):
     from oracle.refshim import MODEL_CFGS
     g = load_golden("tiny_unet")
     net = _model(dwb, g["cfg"], g["sd"])
-    with pytest.raises(RuntimeError):        # wrong length for this plan
+    with pytest.raises(RuntimeError):        # length not divisible by the pooling factor (4 * 4)
         with torch.no_grad():
-            net((torch.zeros(1, 1, 128).cuda(), torch.zeros(1, 1).cuda()))
+            net((torch.zeros(1, 1, 136).cuda(), torch.zeros(1, 1).cuda()))
     with pytest.raises(RuntimeError):        # conditioning on an unconditional model
         with torch.no_grad():
             net((torch.zeros(1, 1, 256).cuda(), torch.zeros(1, 1).cuda()), mel_spec=torch.zeros(1, 80, 2).cuda())

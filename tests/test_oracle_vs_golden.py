@@ -107,6 +107,46 @@ def test_trajectory(name):
     assert rel_l2(x0_nonet, g["x0"]) > 1e-2
 
 
+LENGTHS = [("tiny_unet", 128), ("tiny_unet", 64), ("tiny_unet", 512), ("tiny_unet", 1024), ("tiny_unet", 2304),
+           ("tiny_snet", 160), ("tiny_snet", 640), ("tiny_unet_cond", 256), ("tiny_unet_cond", 1024), ("tiny_unet_cond", 2048)]
+
+
+@pytest.mark.parametrize("name,Lr", LENGTHS)
+def test_other_sequence_lengths(name, Lr):
+    """L < l_max (kernel truncated) and L > l_max (whole kernel, FFT of size l_max + L): models/s4.py:1387,1403-1406."""
+    g, gl = load_golden(name), load_golden("lengths_" + name)
+    x, t = torch.from_numpy(gl[f"x_{Lr}"]), torch.from_numpy(gl["t"])
+    mel = torch.from_numpy(gl[f"mel_{Lr}"]) if f"mel_{Lr}" in gl else None
+    eps = O.forward(g["cfg"], g["sd"], x, t, mel)
+    assert rel_l2(eps, gl[f"eps_{Lr}"]) < TOL and rel_max(eps, gl[f"eps_{Lr}"]) < TOL
+
+
+@pytest.mark.parametrize("H,L", [(2, 250), (3, 64)])
+def test_kernel_length_doubling(H, L):
+    """models/s4.py:531-534: C <- C~ (I + dA^L) takes a kernel set up for L to 2L (and again to 4L); the host
+    mirror's double_C must reproduce the reference's stored C, and the doubled kernel its k."""
+    import diffwave_sashimi_b200.engine as E
+    g = load_golden(f"s4double_H{H}_L{L}")
+    p = "kernel.kernel."
+    s1, s2, s4 = g["sd0"], g["sd1"], g["sd"]
+    assert (int(s1[p + "L"]), int(s2[p + "L"]), int(s4[p + "L"])) == (L, 2 * L, 4 * L)
+    args = (s1[p + "B"], s1[p + "P"], s1[p + "inv_w_real"], s1[p + "w_imag"], s1[p + "log_dt"])
+    C2 = E.double_C(s1[p + "C"], *args, L)
+    assert rel_max(C2, s2[p + "C"]) < 1e-4
+    C4 = E.double_C(C2, *args, 2 * L)
+    assert rel_max(C4, s4[p + "C"]) < 1e-4
+    sd = {"layer." + k: v for k, v in s4.items()}
+    sd["layer." + p + "C"] = C4
+    assert rel_max(O.s4_kernel(sd, "layer.", 4 * L, nodes="reference"), g["k4"]) < 5e-5
+    # rewrite_fresh_kernels: a checkpoint stored at L loaded into a model whose stage length is 4L
+    blocks = [("blk.", H, 4 * L)]
+    sdm = {"blk.layer." + k: v.clone() for k, v in s1.items()}
+    out = list(E.rewrite_fresh_kernels(blocks, sdm))
+    assert len(out) == 1 and int(sdm["blk.layer." + p + "L"]) == 4 * L and rel_max(sdm["blk.layer." + p + "C"], s4[p + "C"]) < 1e-4
+    with pytest.raises(ValueError):
+        list(E.rewrite_fresh_kernels([("blk.", H, 3 * L)], {"blk.layer." + k: v.clone() for k, v in s1.items()}))
+
+
 def test_names():
     assert O.model_name(dict(_name_="wavenet", res_channels=256, num_res_layers=36)) == "wnet_h256_d36"
     assert O.model_name(dict(_name_="sashimi", unet=True, d_model=64, n_layers=6, pool=[4, 4], expand=2, ff=2)) \
