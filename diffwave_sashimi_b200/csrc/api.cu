@@ -1212,6 +1212,19 @@ int dwb_plan_mix_block(dwb_plan *p, int block, int exact, const float *g, const 
     return DWB_ERR_INVALID;
 }
 
+/* debug (declared in dwb.h under "debug"): layer `layer` of a WaveNet plan on caller tensors with per-CTA phase timestamps */
+int dwb_debug_wave_trace(dwb_plan *p, int layer, const float *h, const float *part, float *h_out, float *skip, int B, int L,
+                         long long *trace, void *stream) {
+    DWB_REQUIRE(p && p->finalized && p->cfg.model == DWB_MODEL_WAVENET, DWB_ERR_STATE, "needs a finalized WaveNet plan");
+    DWB_REQUIRE(layer >= 0 && layer < (int)p->wl.size() && p->wl[layer].umma, DWB_ERR_UNSUPPORTED, "layer %d is not on the tcgen05 path", layer);
+    const WaveLayer &w = p->wl[layer];
+    WaveBlockArgs a{};
+    a.h = h; a.h_out = h_out; a.part_t = part; a.part_stride_b = 0; a.bd = w.bd; a.br = w.br; a.bs = w.bs;
+    a.skip = skip; a.first = 0; a.C = p->cfg.res_channels; a.S = p->cfg.skip_channels; a.L = L; a.dilation = w.dilation;
+    a.Wimg = w.Wimg; a.trace = trace;
+    return wave_block_umma_launch(a, B, (cudaStream_t)stream);
+}
+
 int dwb_plan_work(dwb_plan *p, int L, double *bytes, double *flops) {
     DWB_REQUIRE(p && p->finalized && bytes && flops, DWB_ERR_STATE, "plan is not finalized");
     const dwb_config &c = p->cfg;

@@ -62,6 +62,7 @@ struct WaveBlockArgs {
     const float *Ws_t, *bs;        // [C][S], (S)
     const uint4 *Wd_fh, *Wd_fl, *Wr_fh, *Wr_fl, *Ws_fh, *Ws_fl;   // split-bf16 A fragments, or null
     const uint8_t *Wimg;           // tcgen05 path (wave_umma.cu): packed shared-memory image of the three weights, or null
+    long long *trace;              // debug: per-CTA phase timestamps (16 clock64 values per CTA), or null
     float *h_out;                  // (B,C,L)
     float *skip;                   // (B,S,L) accumulated in place
     int first;                     // 1: skip is written, not accumulated

@@ -87,6 +87,10 @@ wave_block_umma_kernel(WaveBlockArgs a) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, t0 = blockIdx.x * WU_TT, L = a.L, d = a.dilation;
+    long long *trace = a.trace ? a.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+#define WU_TRACE(slot) do { if (trace && tid == 0) trace[slot] = clock64(); } while (0)
+#define WU_TRACE_MMA(slot) do { if (trace) trace[slot] = clock64(); } while (0)
+    WU_TRACE(0);
     if (tid == 0) {
         for (int i = 0; i < W::NSW; ++i) {
             mbar_init(wfull + i, 1);
@@ -108,6 +112,7 @@ wave_block_umma_kernel(WaveBlockArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tptr;
+    WU_TRACE(1);
 
     if (warp == 8) {
         // ================= weight producer =====================================================
@@ -156,8 +161,10 @@ wave_block_umma_kernel(WaveBlockArgs a) {
                     done_stage();
                 }
                 mma_commit(uempty + us);
+                if (kc == 0) WU_TRACE_MMA(8);
             }
             mma_commit(acc1_ready);
+            WU_TRACE_MMA(9);
             // ---- phase 2: [W_res; W_skip] o, 128 output rows at a time, A = packed o in TMEM
 #pragma unroll 1
             for (int j = 0; j < W::NJ; ++j) {
@@ -184,7 +191,9 @@ wave_block_umma_kernel(WaveBlockArgs a) {
                     done_stage();
                 }
                 mma_commit(d2_ready + j);
+                if (j == 0) WU_TRACE_MMA(10);
             }
+            WU_TRACE_MMA(11);
         }
     } else {
         // ================= loaders, then epilogue: one time step per thread =====================
@@ -224,8 +233,10 @@ wave_block_umma_kernel(WaveBlockArgs a) {
         }
 
         // ---- E1: o = tanh(ga) sigmoid(gb) -> packed bf16 hi/lo over the consumed tanh columns
+        WU_TRACE(2);
         mbar_wait(acc1_ready, 0);
         tc_fence_after();
+        WU_TRACE(3);
         const float *cb = a.cond ? a.cond + (size_t)(a.cond_stride_b ? b : 0) * 2 * C * L + (valid ? t : 0) : nullptr;
 #pragma unroll 1
         for (int kc = 0; kc < W::KC; ++kc) {
@@ -257,6 +268,7 @@ wave_block_umma_kernel(WaveBlockArgs a) {
             mbar_arrive(o_ready + kc);
         }
 
+        WU_TRACE(4);
         // ---- E2: per 128-row chunk of [res; skip]: global input prefetched, accumulator from TMEM
         const float rs = 0.70710678118654752440f;
         float pre[64];
@@ -282,6 +294,8 @@ wave_block_umma_kernel(WaveBlockArgs a) {
             const bool res = n0 < C;
             mbar_wait(d2_ready + j, 0);
             tc_fence_after();
+            if (j == 0) WU_TRACE(5);
+            if (j == W::NJ - 1) WU_TRACE(6);
             const uint32_t col = tl + W::D2 + 128 * buf + cg * 64;
             const float *bias = res ? a.br + n0 : a.bs + (n0 - C);
             float *op = res ? a.h_out + ((size_t)b * C + n0) * L + (valid ? t : 0)
@@ -309,12 +323,14 @@ wave_block_umma_kernel(WaveBlockArgs a) {
             if (j + 1 < W::NJ) prefetch(j + 1);
         }
     }
+    WU_TRACE(7);
     tc_fence_before();
     __syncthreads();
     if (warp == 9) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
+    WU_TRACE(12);
 }
 
 // finalize: folded fp32 weights (transposed [K][M]) -> the streamed shared-memory image.

@@ -4,8 +4,10 @@
     python generate.py experiment=sc09 model=sashimi_small generate.n_samples=32 generate.batch_size=16
     python -m torch.distributed.run --nproc-per-node 8 generate.py ...        # one process per GPU
 
-Differences from the reference are confined to what runs underneath: the T-step reverse loop is one
-CUDA graph inside libdwb, and multi-GPU runs shard one globally defined batch (so N-GPU output ==
+Differences from the reference are confined to what runs underneath: every diffusion step is a replay of one
+CUDA graph inside libdwb with the CPU noise drawn a chunk of steps ahead, utterances of any length run on one
+plan (kernel truncation below, overlap-save above the training segment length), the wav -> mel front end runs on
+the GPU, and multi-GPU runs shard one globally defined batch with per-clip noise streams (so N-GPU output ==
 1-GPU output) instead of spawning unsynchronised, unseeded processes.
 `generate.random_init=true` writes samples from a seeded fresh model when no checkpoint exists
 (useful on a box without weights; the reference would raise)."""
@@ -46,10 +48,16 @@ def generate(rank, world, diffusion_cfg, model_cfg, dataset_cfg, ckpt_iter="max"
 
     cond = None
     if mel_name is not None:
-        if mel_path is None:
-            raise NotImplementedError("wav -> mel front end needs librosa (not in this image); pass generate.mel_path "
-                                      "with a precomputed '<mel_name>.wav.pt' spectrogram")
-        cond = torch.load(os.path.join(mel_path, f"{mel_name}.wav.pt")).unsqueeze(0).cuda()
+        if mel_path is not None:       # pre-generated spectrogram (generate.py:136-142 of the reference)
+            cond = torch.load(os.path.join(mel_path, f"{mel_name}.wav.pt")).unsqueeze(0).cuda()
+        else:                          # wav -> mel on the GPU (reference: dataloaders.mel2samp.Mel2Samp.get_mel, :143-155)
+            from diffwave_sashimi_b200 import mel as M
+            stft = M.TacotronSTFT(**{k: dataset_cfg[k] for k in ("filter_length", "hop_length", "win_length", "sampling_rate",
+                                                                "mel_fmin", "mel_fmax")})
+            audio, sr = M.load_wav_to_torch(os.path.join(dataset_cfg["data_path"], f"{mel_name}.wav"))
+            if sr != dataset_cfg["sampling_rate"]:
+                raise ValueError(f"{sr} SR doesn't match target {dataset_cfg['sampling_rate']} SR")
+            cond = M.get_mel(stft, audio.cuda()).unsqueeze(0)
         audio_length = cond.shape[-1] * dataset_cfg["hop_length"]
     else:
         audio_length = dataset_cfg["segment_length"]

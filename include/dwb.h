@@ -209,6 +209,23 @@ int dwb_fftconv_prepare(const float *k, const float *D, int H, int l, float *kf,
 int dwb_fftconv(const float *x, const float *stats, const float *part_t, int64_t part_stride_b,
                 float ln_m, float ln_s, const float *kf, float *g, int B, int H, int l, void *stream);
 
+/* ---- debug ---------------------------------------------------------------------------------------------------
+ * One tcgen05 WaveNet layer on caller tensors, writing 16 clock64 phase timestamps per CTA to `trace`
+ * ((B * ceil(L/128)) x 16 int64; tools/trace_wave.py prints the phase durations). */
+int dwb_debug_wave_trace(dwb_plan *plan, int layer, const float *h, const float *part, float *h_out, float *skip, int B, int L,
+                         long long *trace, void *stream);
+
+/* ---- mel front end (the step before the path for conditional generation) ------------------------------------
+ * mel = log(clamp(mel_basis @ |STFT(audio * in_scale)|, clip))     dataloaders/stft.py:100-161,211-244, mel2samp.py:78-84
+ *   audio     (B,T) f32 device; in_scale = 1/32768 for int16-valued wav data (MAX_WAV_VALUE), 1 for [-1,1] data
+ *   basis_t   (n_fft, 2*(n_fft/2+1)) f32 device: the reference's windowed Fourier basis `forward_basis`
+ *             (real rows then imaginary rows of fft(eye(n_fft))[:n_fft/2+1] times the zero-centred window), transposed
+ *   mel_basis (n_mels, n_fft/2+1) f32 device   (librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax))
+ *   out       (B, n_mels, frames), frames = T/hop + 1 (dwb_mel_frames); reflect padding n_fft/2, stride hop */
+int dwb_mel_frames(int T, int n_fft, int hop, int *frames);
+int dwb_mel_spectrogram(const float *audio, int B, int T, float in_scale, const float *basis_t, int n_fft, int hop,
+                        const float *mel_basis, int n_mels, float clip, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -252,6 +252,37 @@ def make_extra(ns):
                     arrs[f"mel_{Lr}"] = mel.numpy()
             save("lengths_" + name, t=t.numpy(), **arrs)
 
+    if want("mel"):
+        # dataloaders/stft.py imports librosa (absent here) for two helpers: pad_center (a no-op at win_length ==
+        # filter_length) and filters.mel, for which torchaudio's independent implementation of the same Slaney
+        # filterbank stands in.  Everything else (windowed Fourier basis, reflect padding, conv1d, magnitude, log) is
+        # the reference's own code.
+        import torchaudio
+        lb = types.ModuleType("librosa")
+        lb.util = types.SimpleNamespace(pad_center=lambda w, size: np.pad(w, ((size - len(w)) // 2, size - len(w) - (size - len(w)) // 2)),
+                                        tiny=lambda x: np.finfo(np.float32).tiny)
+        lb.filters = types.SimpleNamespace(mel=lambda sr, n_fft, n_mels, fmin, fmax: torchaudio.functional.melscale_fbanks(
+            n_fft // 2 + 1, fmin, fmax, n_mels, sr, norm="slaney", mel_scale="slaney").T.numpy())
+        sys.modules["librosa"] = lb
+        import importlib.util           # the package __init__ pulls in dataset downloaders; load the one file
+        spec = importlib.util.spec_from_file_location("ref_stft", os.path.join(refshim.REF_ROOT, "dataloaders", "stft.py"))
+        ref_stft = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref_stft)
+        arrs = {}
+        for tag, kw, T in (("lj", dict(filter_length=1024, hop_length=256, win_length=1024, n_mel_channels=80,
+                                        sampling_rate=22050, mel_fmin=0.0, mel_fmax=8000.0), 16000),
+                           ("small", dict(filter_length=256, hop_length=64, win_length=200, n_mel_channels=20,
+                                          sampling_rate=16000, mel_fmin=50.0, mel_fmax=7000.0), 3001)):
+            st = ref_stft.TacotronSTFT(**kw)
+            g = torch.Generator().manual_seed(31)
+            wav = (torch.rand(2, T, generator=g) * 2 - 1) * torch.tensor([[0.9], [0.05]])     # a loud and a quiet clip
+            wav[1, T // 2:] = 0.0                                                               # silence -> the clamp
+            with torch.no_grad():
+                m = st.mel_spectrogram(wav)
+            arrs[f"wav_{tag}"], arrs[f"mel_{tag}"], arrs[f"kw_{tag}"] = wav.numpy(), m.numpy(), np.array(repr(kw))
+            arrs[f"basis_{tag}"] = st.stft_fn.forward_basis[:, 0, :].numpy()[:, ::max(1, kw["filter_length"] // 64)]
+        save("mel_frontend", **arrs)
+
     T_OF = {"wnet_h128_d30": 200, "unet_d64": 200, "unet_d32_cond": 50, "unet_d128": 200, "wnet_h256_d36": 200}
     if want("full2"):
         for name, (base, _, _, melshape) in FULL.items():

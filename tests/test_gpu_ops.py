@@ -56,6 +56,49 @@ def test_cauchy_broadcast_wrapper(dwb):
     assert rel_max(torch.view_as_real(out), torch.view_as_real(ref)) < 2e-5
 
 
+def _cauchy_f64(v, z, w, symmetric):
+    """complex128 restatement of extensions/cauchy/cauchy.py:8-26 (`cauchy_mult_torch`; symmetric: half spectra)."""
+    d = v.unsqueeze(-1) / (z.view(1, 1, -1) - w.unsqueeze(-1))
+    if symmetric:
+        d = d + v.conj().unsqueeze(-1) / (z.view(1, 1, -1) - w.conj().unsqueeze(-1))
+    return d.sum(dim=-2)
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+@pytest.mark.parametrize("N,L,batch", [(1, 5, 3), (3, 33, 2), (32, 1000, 6), (64, 4097, 2), (256, 64, 3)])
+def test_cauchy_backward_vs_autograd_complex128(dwb, symmetric, N, L, batch):
+    """The four entries of the reference module `cauchy_mult` (cauchy.cpp:86-95): forward values and the (dv, dw)
+    the reference's autograd.Functions must return, i.e. PyTorch autograd through the complex128 formula - the
+    criterion of the reference's own extensions/cauchy/test_cauchy.py:69-99."""
+    g = torch.Generator().manual_seed(17 * N + L)
+    v = torch.randn(batch, N, dtype=torch.complex64, generator=g)
+    w = torch.randn(batch, N, dtype=torch.complex64, generator=g) - 1.5       # poles away from the unit circle
+    z = torch.exp(1j * torch.randn(L, generator=g)).to(torch.complex64)
+    dout = torch.randn(batch, L, dtype=torch.complex64, generator=g)
+    v64, w64 = v.cdouble().requires_grad_(), w.cdouble().requires_grad_()
+    ref = _cauchy_f64(v64, z.cdouble(), w64, symmetric)
+    ref.backward(dout.cdouble())
+    vg, wg, zg = v.cuda().requires_grad_(), w.cuda().requires_grad_(), z.cuda()
+    out = dwb.ops.cauchy_mult(vg, zg, wg, symmetric=symmetric)
+    out.backward(dout.cuda())
+    for name, got, want in (("out", out.detach(), ref.detach()), ("dv", vg.grad, v64.grad), ("dw", wg.grad, w64.grad)):
+        e = rel_max(torch.view_as_real(got.cpu().cdouble()), torch.view_as_real(want))
+        assert e < 5e-5, (name, e)
+    # the shim module the reference's cauchy.py imports: same four callables, raw (batch, N) signature
+    import importlib, sys
+    import diffwave_sashimi_b200.shims as shims
+    sys.path.insert(0, shims.PATH)
+    try:
+        cm = importlib.import_module("cauchy_mult")
+    finally:
+        sys.path.remove(shims.PATH)
+    f = cm.cauchy_mult_sym_fwd if symmetric else cm.cauchy_mult_fwd
+    b = cm.cauchy_mult_sym_bwd if symmetric else cm.cauchy_mult_bwd
+    assert torch.equal(f(v.cuda(), zg, w.cuda()), out.detach())
+    dv, dw = b(v.cuda(), zg, w.cuda(), dout.cuda())
+    assert torch.equal(dv, vg.grad) and torch.equal(dw, wg.grad)
+
+
 @pytest.mark.parametrize("H,L", [(4, 64), (3, 100), (2, 250), (2, 1000)])
 def test_s4_kernel_gen_vs_reference(dwb, H, L):
     g = load_golden(f"s4kernel_H{H}_L{L}")
@@ -185,3 +228,25 @@ def test_fftconv_variants(env):
     worst = float([ln for ln in r.stdout.splitlines() if ln.startswith("WORST")][-1].split()[1])
     print(env, "worst rel_l2", worst)
     assert worst < 2e-5
+
+
+@pytest.mark.parametrize("tag", ["lj", "small"])
+def test_mel_front_end_vs_reference_golden(dwb, tag):
+    """GPU mel front end (dwb_mel_spectrogram) against TacotronSTFT.mel_spectrogram of the reference's own stft.py."""
+    import ast
+    from diffwave_sashimi_b200 import mel as M
+    g = load_golden("mel_frontend")
+    kw = ast.literal_eval(str(g[f"kw_{tag}"]))
+    wav, ref = torch.from_numpy(g[f"wav_{tag}"]), torch.from_numpy(g[f"mel_{tag}"])
+    st = M.TacotronSTFT(**kw)
+    got = st.mel_spectrogram(wav.cuda()).cpu()
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    print(f"mel front end {tag}: max abs err of log-mel {err:.2e}")
+    assert err < 2e-4
+    # int16-valued input path of Mel2Samp.get_mel (audio / 32768) and the oracle on the same clip
+    one = M.get_mel(st, (wav[0] * 32768.0).cuda()).cpu()
+    assert (one - ref[0]).abs().max().item() < 2e-4
+    melb = torch.from_numpy(M.mel_filterbank(kw["sampling_rate"], kw["filter_length"], kw["n_mel_channels"], kw["mel_fmin"], kw["mel_fmax"]))
+    orc = O.mel_spectrogram(wav, melb, kw["filter_length"], kw["hop_length"], kw["win_length"])
+    assert (got.double() - orc).abs().max().item() < 2e-4

@@ -130,3 +130,34 @@ def test_cond_cache_is_not_fooled_by_recycled_storage(dwb):
     sd = {k: torch.as_tensor(v) for k, v in g["sd"].items()}
     ref = O.forward(g["cfg"], sd, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), mel=torch.from_numpy(mel_np * -0.5))
     assert rel_l2(outs[1].cpu(), ref) < 1e-4
+
+
+def test_generate_entry_point_vocodes_a_wav(dwb, tmp_path):
+    """`python generate.py experiment=ljspeech ...` end to end on a synthetic 1.4 s utterance: wav -> GPU mel front end
+    -> conditioning features -> T=50 sampler at audio_length = frames * hop (2.1 x the training segment: overlap-save)
+    -> float32 wav files, with the reference's directory and file naming (generate.py:117-121,188-192)."""
+    import os
+    import subprocess
+    import sys
+    from scipy.io import wavfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    wavs = tmp_path / "wavs"
+    wavs.mkdir()
+    sr, n = 22050, 33075 - 512
+    t = np.arange(n) / sr
+    wav = (0.4 * np.sin(2 * np.pi * 220 * t) * np.hanning(n) * 32767).astype(np.int16)
+    wavfile.write(str(wavs / "utt.wav"), sr, wav)
+    r = subprocess.run([sys.executable, os.path.join(root, "generate.py"), "experiment=ljspeech", "model=sashimi_small",
+                        "model.unconditional=false", "generate.random_init=true", f"dataset.data_path={wavs}",
+                        "generate.mel_name=utt", "generate.n_samples=2", "generate.seed=3"],
+                       capture_output=True, text=True, cwd=str(tmp_path), timeout=600,
+                       env=dict(os.environ, PYTHONPATH=root))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    frames = n // 256 + 1
+    assert f"begin generating audio of length {frames * 256}" in r.stdout
+    outs = sorted(p for p in tmp_path.rglob("*.wav") if "waveforms" in str(p))
+    assert [p.name for p in outs] == ["0k_0.wav", "0k_1.wav"], outs
+    assert "_T50_betaT0.05_L16000_hop256_cond" in str(outs[0])
+    for p in outs:
+        rate, data = wavfile.read(str(p))
+        assert rate == sr and data.dtype == np.float32 and data.shape == (frames * 256,) and np.isfinite(data).all()

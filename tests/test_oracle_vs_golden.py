@@ -1,5 +1,7 @@
 """Pin oracle/diffwave_oracle.py against fixtures produced by the unmodified reference
 (tests/golden/make_golden.py).  CPU only."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -145,6 +147,27 @@ def test_kernel_length_doubling(H, L):
     assert len(out) == 1 and int(sdm["blk.layer." + p + "L"]) == 4 * L and rel_max(sdm["blk.layer." + p + "C"], s4[p + "C"]) < 1e-4
     with pytest.raises(ValueError):
         list(E.rewrite_fresh_kernels([("blk.", H, 3 * L)], {"blk.layer." + k: v.clone() for k, v in s1.items()}))
+
+
+@pytest.mark.parametrize("tag", ["lj", "small"])
+def test_mel_front_end(tag):
+    """dataloaders/stft.py TacotronSTFT.mel_spectrogram as run by the reference's own code (librosa's filterbank
+    replaced by torchaudio's implementation of the same Slaney bank when the fixture was made)."""
+    import ast
+    from diffwave_sashimi_b200 import mel as M
+    g = load_golden("mel_frontend")
+    kw = ast.literal_eval(str(g[f"kw_{tag}"]))
+    wav, ref = torch.from_numpy(g[f"wav_{tag}"]), g[f"mel_{tag}"]
+    melb = torch.from_numpy(M.mel_filterbank(kw["sampling_rate"], kw["filter_length"], kw["n_mel_channels"], kw["mel_fmin"], kw["mel_fmax"]))
+    got = O.mel_spectrogram(wav, melb, kw["filter_length"], kw["hop_length"], kw["win_length"])
+    assert got.shape == ref.shape == (2, kw["n_mel_channels"], wav.shape[1] // kw["hop_length"] + 1)
+    # log-mel values: absolute tolerance (the silent half sits exactly on the clamp, log 1e-5)
+    assert (got - torch.from_numpy(ref).double()).abs().max().item() < 2e-4
+    assert float(ref.min()) == pytest.approx(math.log(1e-5), abs=1e-6)
+    # the host mirror builds the reference's float32 basis bit for bit (numpy fft of the identity x scipy window)
+    step = max(1, kw["filter_length"] // 64)
+    assert np.array_equal(M.forward_basis(kw["filter_length"], kw["win_length"]).numpy()[:, ::step], g[f"basis_{tag}"])
+    assert (O.stft_forward_basis(kw["filter_length"], kw["win_length"]).float().numpy()[:, ::step] - g[f"basis_{tag}"]).__abs__().max() < 1e-6
 
 
 def test_names():
