@@ -63,6 +63,7 @@ struct Op {
     uint4 *Wo_f[2] = {nullptr, nullptr}, *W1_f[2] = {nullptr, nullptr}, *W2_f[2] = {nullptr, nullptr};
     bool mma = false;
     bool umma = false;             // tcgen05 path (mix_umma.cu)
+    bool gemm = false;             // tcgen05 GEMM-per-contraction path (mix_gemm_umma.cu): widths mix_umma.cu has no tile for
     uint8_t *Wimg = nullptr;
     float *bimg = nullptr;
     int F = 0;
@@ -136,6 +137,7 @@ struct dwb_plan {
     int ws_B = 0, ws_L = 0;
     std::vector<float *> bufs, stat_bufs;
     float *g_buf = nullptr, *emb_buf = nullptr, *part_buf = nullptr;
+    float *hid_buf = nullptr;      // (B,F,l) hidden activations of the GEMM-per-contraction mixing path
     float *skip_acc = nullptr;     // wavenet
     std::vector<void *> ws_owned;
 
@@ -433,7 +435,14 @@ static int finalize_sashimi(dwb_plan *p, cudaStream_t st) {
                     TRY(mix_umma_pack(H, o.Wo_t, o.W1_t, o.W2_t, o.bo, o.b1, o.b2, o.Wimg, o.bimg, st));
                     p->launches += 1;
                 }
-                o.mma = !o.umma && p->use_mma && mix_mma_supported(H, o.F, l);
+                o.gemm = !o.umma && p->use_mma && p->use_umma && mix_gemm_supported(H, o.F, l);
+                if (o.gemm) {
+                    void *d;
+                    TRY(dev_alloc(p, mix_gemm_image_bytes(H, o.F), &d)); o.Wimg = (uint8_t *)d;
+                    TRY(mix_gemm_pack(H, o.F, o.Wo_t, o.W1_t, o.W2_t, o.Wimg, st));
+                    p->launches += 1;
+                }
+                o.mma = !o.umma && !o.gemm && p->use_mma && mix_mma_supported(H, o.F, l);
                 if (o.mma) {
                     auto pack = [&](const float *Wt, int M, int K, uint4 **f) -> int {
                         for (int q = 0; q < 2; ++q) {
@@ -555,6 +564,11 @@ static int ensure_workspace(dwb_plan *p, int B, int L) {
             TRY(dev_alloc(p, (size_t)B * L * 2 * sizeof(float), &d, true)); p->stat_bufs.push_back((float *)d);
         }
         TRY(dev_alloc(p, maxact, &d, true)); p->g_buf = (float *)d;
+        size_t hid = 0;
+        for (auto &o : p->ops)
+            if (o.kind == OP_BLOCK && o.gemm) hid = std::max(hid, (size_t)B * o.F * run_len(p, o.l, L) * sizeof(float));
+        p->hid_buf = nullptr;
+        if (hid) { TRY(dev_alloc(p, hid, &d, true)); p->hid_buf = (float *)d; }
     } else {
         for (int i = 0; i < 2; ++i) {
             TRY(dev_alloc(p, (size_t)B * c.res_channels * L * sizeof(float), &d, true));
@@ -705,8 +719,9 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
                 a.Wo_fh = o.Wo_f[0]; a.Wo_fl = o.Wo_f[1]; a.W1_fh = o.W1_f[0]; a.W1_fl = o.W1_f[1];
                 a.W2_fh = o.W2_f[0]; a.W2_fl = o.W2_f[1];
                 a.Wimg = o.Wimg; a.bimg = o.bimg;
-                TRY(o.umma ? mix_umma_launch(a, B, st) : (o.mma ? mix_mma_launch(a, B, st) : mix_launch(a, B, st)));
-                p->launches += (lt && r > o.l) ? 3 : 2;
+                TRY(o.umma ? mix_umma_launch(a, B, st)
+                           : (o.gemm ? mix_gemm_launch(a, p->hid_buf, B, st) : (o.mma ? mix_mma_launch(a, B, st) : mix_launch(a, B, st))));
+                p->launches += ((lt && r > o.l) ? 3 : 2) + (o.gemm ? 4 : 0);
                 PROF(DWB_PROF_MIX0 + std::min(stage_of(p, o.l), 3));
             } else {
                 PoolArgs a{};
@@ -1205,6 +1220,14 @@ int dwb_plan_mix_block(dwb_plan *p, int block, int exact, const float *g, const 
             a.Wimg = o.Wimg; a.bimg = o.bimg;
             p->launches += 1;
             if (exact) return mix_launch(a, B, (cudaStream_t)stream);
+            if (o.gemm) {
+                float *hid = nullptr;
+                DWB_CUDA(cudaMalloc(&hid, (size_t)B * o.F * o.l * sizeof(float)));
+                int rc = mix_gemm_launch(a, hid, B, (cudaStream_t)stream);
+                cudaStreamSynchronize((cudaStream_t)stream);
+                cudaFree(hid);
+                return rc;
+            }
             return o.umma ? mix_umma_launch(a, B, (cudaStream_t)stream)
                           : (o.mma ? mix_mma_launch(a, B, (cudaStream_t)stream) : mix_launch(a, B, (cudaStream_t)stream));
         }

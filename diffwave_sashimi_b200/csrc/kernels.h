@@ -86,6 +86,11 @@ size_t mix_umma_image_bytes(int H);
 int mix_umma_pack(int H, const float *Wo_t, const float *W1_t, const float *W2_t, const float *bo, const float *b1,
                   const float *b2, uint8_t *img, float *bimg, cudaStream_t st);
 int mix_umma_launch(const MixArgs &a, int B, cudaStream_t st);
+// widths without a fused tcgen05 kernel (H = 512): three tcgen05 GEMM launches + two statistics launches (mix_gemm_umma.cu)
+bool mix_gemm_supported(int H, int F, int l);
+size_t mix_gemm_image_bytes(int H, int F);
+int mix_gemm_pack(int H, int F, const float *Wo_t, const float *W1_t, const float *W2_t, uint8_t *img, cudaStream_t st);
+int mix_gemm_launch(const MixArgs &a, float *hid /* (B,F,l) workspace */, int B, cudaStream_t st);
 int frag_pack(const float *Wt, int M, int K, uint32_t *fhi, uint32_t *flo, cudaStream_t st);
 int down_pool_launch(const PoolArgs &a, int B, cudaStream_t st);
 int up_pool_launch(const PoolArgs &a, int B, cudaStream_t st);

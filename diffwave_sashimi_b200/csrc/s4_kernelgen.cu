@@ -397,7 +397,11 @@ cauchy_sym_fwd_kernel(const float2 *__restrict__ v, const float2 *__restrict__ z
                 // v/(z-w) + conj(v)/(z-conj(w)); both denominators share (z.x - w.x)
                 const float dx = zz.x - wn.x;
                 const float dy1 = zz.y - wn.y, dy2 = zz.y + wn.y;
-                const float i1 = 1.0f / (dx * dx + dy1 * dy1), i2 = 1.0f / (dx * dx + dy2 * dy2);
+                // MUFU.RCP (1 ulp) instead of the IEEE division sequence: the kernel is instruction-issue bound
+                // (ncu: issue-active 93 %), and two exact divisions were ~40 % of its instructions
+                float i1, i2;
+                asm("rcp.approx.f32 %0, %1;" : "=f"(i1) : "f"(fmaf(dx, dx, dy1 * dy1)));
+                asm("rcp.approx.f32 %0, %1;" : "=f"(i2) : "f"(fmaf(dx, dx, dy2 * dy2)));
                 // v * conj(d1) * i1 ; conj(v) * conj(d2) * i2
                 ar += (vn.x * dx + vn.y * dy1) * i1 + (vn.x * dx - vn.y * dy2) * i2;
                 ai += (vn.y * dx - vn.x * dy1) * i1 + (-vn.y * dx - vn.x * dy2) * i2;
@@ -410,6 +414,54 @@ cauchy_sym_fwd_kernel(const float2 *__restrict__ v, const float2 *__restrict__ z
         ai += __shfl_down_sync(0xffffffffu, ai, off, LPL);
     }
     if (live && lane == 0) out[(size_t)b * L + li] = make_float2(ar, ai);
+}
+
+// Many outputs: one thread owns LT outputs l (256 apart, so a warp's loads and stores stay coalesced) and walks the whole
+// state dimension; every (v, w) pair read from shared memory is used LT times and the products v.x dx, v.y dx are
+// shared by the two conjugate terms: 16 FP32 + 2 MUFU.RCP per (l, n) against ~55 instructions for the lane-split
+// kernel above (ncu round 2: that one is issue bound at 93 %).
+template <int LT>
+__global__ void __launch_bounds__(CAUCHY_THREADS)
+cauchy_sym_fwd_mt_kernel(const float2 *__restrict__ v, const float2 *__restrict__ z, const float2 *__restrict__ w,
+                         float2 *__restrict__ out, int N, int L) {
+    __shared__ float4 svw[CAUCHY_NCHUNK];
+    const int b = blockIdx.y, l0 = blockIdx.x * (CAUCHY_THREADS * LT) + threadIdx.x;
+    float2 zz[LT];
+    float ar[LT], ai[LT];
+#pragma unroll
+    for (int j = 0; j < LT; ++j) {
+        const int l = l0 + j * CAUCHY_THREADS;
+        zz[j] = l < L ? z[l] : make_float2(2.f, 0.f);
+        ar[j] = ai[j] = 0.f;
+    }
+    for (int n0 = 0; n0 < N; n0 += CAUCHY_NCHUNK) {
+        const int cnt = min(CAUCHY_NCHUNK, N - n0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += CAUCHY_THREADS) {
+            const float2 a = v[(size_t)b * N + n0 + i], c = w[(size_t)b * N + n0 + i];
+            svw[i] = make_float4(a.x, a.y, c.x, c.y);
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int i = 0; i < cnt; ++i) {
+            const float4 q = svw[i];
+#pragma unroll
+            for (int j = 0; j < LT; ++j) {
+                const float dx = zz[j].x - q.z, dy1 = zz[j].y - q.w, dy2 = zz[j].y + q.w, dx2 = dx * dx;
+                float i1, i2;
+                asm("rcp.approx.f32 %0, %1;" : "=f"(i1) : "f"(fmaf(dy1, dy1, dx2)));
+                asm("rcp.approx.f32 %0, %1;" : "=f"(i2) : "f"(fmaf(dy2, dy2, dx2)));
+                const float a = q.x * dx, c = q.y * dx;
+                ar[j] = fmaf(fmaf(q.y, dy1, a), i1, fmaf(fmaf(-q.y, dy2, a), i2, ar[j]));
+                ai[j] = fmaf(fmaf(-q.x, dy1, c), i1, fmaf(fmaf(-q.x, dy2, -c), i2, ai[j]));
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < LT; ++j) {
+        const int l = l0 + j * CAUCHY_THREADS;
+        if (l < L) out[(size_t)b * L + l] = make_float2(ar[j], ai[j]);
+    }
 }
 
 }  // namespace dwb
@@ -426,6 +478,11 @@ extern "C" int dwb_cauchy_sym_fwd(const float *v, const float *z, const float *w
     cudaStream_t st = (cudaStream_t)stream;
     const float2 *v2 = (const float2 *)v, *z2 = (const float2 *)z, *w2 = (const float2 *)w;
     float2 *o2 = (float2 *)out;
+    // many outputs: four outputs per thread, whole state dimension per thread
+    if ((int64_t)batch * L >= 262144 && L >= 2 * CAUCHY_THREADS) {
+        dim3 grid(ceil_div(L, CAUCHY_THREADS * 4), batch);
+        cauchy_sym_fwd_mt_kernel<4><<<grid, CAUCHY_THREADS, 0, st>>>(v2, z2, w2, o2, N, L);
+    } else
     // few outputs and many states: split the state dimension over a full warp; otherwise 4 lanes
     if ((int64_t)batch * L < 4096 && N >= 64) {
         dim3 grid(ceil_div(L, CAUCHY_THREADS / 32), batch);

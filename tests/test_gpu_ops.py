@@ -32,7 +32,9 @@ def test_cauchy_vs_reference_complex128(dwb, N, L):
     assert (err / ref.abs()).mean().item() < 1e-4       # the reference's own criterion is 10x KeOps + 1e-4
 
 
-@pytest.mark.parametrize("N,L,batch", [(1, 5, 3), (2, 33, 2), (32, 8001, 6), (512, 3, 4), (1024, 64, 2), (32, 2 ** 16, 2)])
+@pytest.mark.parametrize("N,L,batch", [(1, 5, 3), (2, 33, 2), (32, 8001, 6), (512, 3, 4), (1024, 64, 2), (32, 2 ** 16, 2),
+                                       # four-outputs-per-thread kernel (batch * L >= 2^18): ragged L, odd N, N > one shared chunk
+                                       (32, 16384, 32), (5, 3001, 100), (300, 1500, 180)])
 def test_cauchy_shapes(dwb, N, L, batch):
     g = torch.Generator().manual_seed(N * 1000 + L)
     v = torch.randn(batch, N, dtype=torch.complex64, generator=g)
