@@ -62,6 +62,7 @@ SIGNATURES = {
     "dwb_fftconv_size": [_I, ctypes.POINTER(_I)],
     "dwb_fftconv_prepare": [_P, _P, _I, _I, _P, _P],
     "dwb_plan_cond_features": [_P, _P, _I, _I, _I, _P, _P],
+    "dwb_debug_mix_trace": [_P, _I, _P, _P, _P, _P, _I, _P, _P],
     "dwb_debug_wave_trace": [_P, _I, _P, _P, _P, _P, _I, _I, _P, _P],
     "dwb_mel_frames": [_I, _I, _I, ctypes.POINTER(_I)],
     "dwb_mel_spectrogram": [_P, _I, _I, _F, _P, _I, _I, _P, _I, _F, _P, _P],

@@ -1235,6 +1235,25 @@ int dwb_plan_mix_block(dwb_plan *p, int block, int exact, const float *g, const 
     return DWB_ERR_INVALID;
 }
 
+/* debug (declared in dwb.h under "debug"): tcgen05 mixing of `block` with per-CTA phase timestamps */
+int dwb_debug_mix_trace(dwb_plan *p, int block, const float *g, const float *x, float *out, float *stats_out, int B,
+                        long long *trace, void *stream) {
+    DWB_REQUIRE(p && p->finalized, DWB_ERR_STATE, "plan is not finalized");
+    int n = 0;
+    for (auto &o : p->ops)
+        if (o.kind == OP_BLOCK) {
+            if (n++ != block) continue;
+            DWB_REQUIRE(o.umma, DWB_ERR_UNSUPPORTED, "block %d is not on the fused tcgen05 path", block);
+            MixArgs a{};
+            a.g = g; a.x = x; a.bo = o.bo; a.b1 = o.b1; a.b2 = o.b2;
+            a.ln2_m = o.ln2_m; a.ln2_s = o.ln2_s; a.out = out; a.stats_out = stats_out;
+            a.H = o.H; a.F = o.F; a.l = o.l; a.Wimg = o.Wimg; a.bimg = o.bimg; a.trace = trace;
+            return mix_umma_launch(a, B, (cudaStream_t)stream);
+        }
+    set_error("block %d out of range", block);
+    return DWB_ERR_INVALID;
+}
+
 /* debug (declared in dwb.h under "debug"): layer `layer` of a WaveNet plan on caller tensors with per-CTA phase timestamps */
 int dwb_debug_wave_trace(dwb_plan *p, int layer, const float *h, const float *part, float *h_out, float *skip, int B, int L,
                          long long *trace, void *stream) {

@@ -1435,7 +1435,9 @@ int mix_umma_launch(const MixArgs &a, int B, cudaStream_t st) {
         DWB_LAUNCH_CHECK();
         return DWB_OK;
     }
-    const bool pers = mode == 2 || (mode == 0 && a.H == 128);
+    // round 2, B = 64 (8000 tiles at H = 64): per-tile 370 us, persistent 337 us - the per-CTA setup (TMEM allocation
+    // against the co-resident CTA, barrier init, bias staging: 3.1 K of 21.7 K cycles per tile) stops paying for itself
+    const bool pers = mode == 2 || (mode == 0 && (a.H == 128 || (int64_t)B * ceil_div(a.l, UM_TT) >= 6000));
     if (pers) switch (a.H) {
         case 64: return launch_umma_pers<64, 2>(a, B, st);
         case 128: return launch_umma_pers<128, 2>(a, B, st);

@@ -212,6 +212,9 @@ int dwb_fftconv(const float *x, const float *stats, const float *part_t, int64_t
 /* ---- debug ---------------------------------------------------------------------------------------------------
  * One tcgen05 WaveNet layer on caller tensors, writing 16 clock64 phase timestamps per CTA to `trace`
  * ((B * ceil(L/128)) x 16 int64; tools/trace_wave.py prints the phase durations). */
+/* Fused tcgen05 mixing kernel of DiffWaveBlock `block` with 16 clock64 phase timestamps per CTA (tools/trace_umma.py). */
+int dwb_debug_mix_trace(dwb_plan *plan, int block, const float *g, const float *x, float *out, float *stats_out, int B,
+                        long long *trace, void *stream);
 int dwb_debug_wave_trace(dwb_plan *plan, int layer, const float *h, const float *part, float *h_out, float *skip, int B, int L,
                          long long *trace, void *stream);
 

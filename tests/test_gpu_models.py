@@ -338,3 +338,28 @@ def test_errors(dwb):
     sd.pop("d_layers.0.layer.D")
     with pytest.raises(RuntimeError):        # missing tensor is reported by name
         dwb.Engine(g["cfg"], {k: v.cuda() for k, v in sd.items()})
+
+
+@pytest.mark.parametrize("variant", ["tile", "pers"])
+def test_tcgen05_mixing_variants_vs_reference_golden(variant):
+    """The per-tile and the persistent form of the fused tcgen05 mixing kernel (chosen by tile count at run time,
+    forced here through DWB_UMMA, which is read once per process -> subprocess) against the reference's eps."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+        "import bench, diffwave_sashimi_b200 as dwb\n"
+        "cfg = dict(bench.CONFIGS['unet_d64']['cfg']); net = dwb.construct_model(dict(cfg))\n"
+        "net.load_state_dict(dwb.init.seeded_state_dict(cfg, seed=0)); net = net.cuda().eval()\n"
+        "g = np.load(%r)\n"
+        "x = torch.randn(1, 1, 16000, generator=torch.Generator().manual_seed(5)).cuda()\n"
+        "with torch.no_grad(): e = net((x, torch.full((1, 1), 100.0).cuda())).cpu().double()\n"
+        "r = torch.from_numpy(g['eps_t100']).double(); print('REL', float((e - r).norm() / r.norm()))\n"
+    ) % (root, os.path.join(GOLDEN, "full_unet_d64.npz"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, DWB_UMMA=variant))
+    assert r.returncode == 0, r.stderr[-2000:]
+    rel = float([l for l in r.stdout.splitlines() if l.startswith("REL")][0].split()[1])
+    print(f"DWB_UMMA={variant}: rel_l2 {rel:.2e}")
+    assert rel < 1e-4

@@ -69,8 +69,9 @@ if "fft" in args.ops:
         got = ops.fftconv(xs[0][:nb].contiguous(), kf, stats=stats[:nb].contiguous(), part_t=pt[:nb].contiguous(), ln_m=0.2, ln_s=1.3)
         err = rel(got, ref)
         us = timeit(lambda i: ops.fftconv(xs[i], kf, stats=stats, part_t=pt, ln_m=0.2, ln_s=1.3), nbuf)
+        us_ns = timeit(lambda i: ops.fftconv(xs[i], kf, stats=None, part_t=pt), nbuf)      # no LayerNorm statistics to read
         nbytes = 2 * 4.0 * B * H * l
-        print(json.dumps({"tag": args.tag, "op": "fftconv", "H": H, "l": l, "B": B, "us": round(us, 1),
+        print(json.dumps({"tag": args.tag, "op": "fftconv", "H": H, "l": l, "B": B, "us": round(us, 1), "us_without_stats": round(us_ns, 1),
                           "GBs": round(nbytes / us / 1e3, 1), "rel_l2_vs_f64": err}))
 
 if "mix" in args.ops:
