@@ -73,10 +73,25 @@ DEFAULT = "unet_d64"
 CFG = CONFIGS[DEFAULT]["cfg"]            # tools/ import these
 WORKLOAD = CONFIGS[DEFAULT]["workload"]
 BETA_0, L = 1e-4, 16000
-KERNEL_NAMES = {"fftconv_s0": "fftconv3_kernel<14> (top stage, l=16000)", "fftconv_s1": "fftconv_kernel<12> (l=4000)",
-                "fftconv_s2": "fftconv_kernel<10> (l=1000)", "mix_s0": "sashimi_mix_umma_kernel (l=16000)",
-                "mix_s1": "sashimi_mix_umma_pers_kernel (l=4000)", "mix_s2": "sashimi_mix_umma256_kernel (l=1000)",
-                "wave_block": "wave_block_umma_kernel (tcgen05 residual layer)"}
+def kernel_label(kname, cfg, B):
+    """Which kernel a profile category runs for this config (the dispatch rules of csrc/api.cu, mix_umma.cu, fftconv.cu)."""
+    if kname == "wave_block":
+        C = cfg["res_channels"]
+        return ("wave_block_umma_kernel<%d,%d> (tcgen05 residual layer)" % (C, cfg["skip_channels"])) if C in (128, 256) \
+            else "wave_block_mma_kernel (mma.sync)"
+    if kname[:-1] in ("fftconv_s", "mix_s"):
+        s_ = int(kname[-1])
+        H, l = cfg["d_model"] * cfg["expand"] ** s_, L // (4 ** s_)
+        if kname.startswith("fft"):
+            lg = max(4, (l - 1).bit_length())
+            return f"fftconv3_kernel<{lg}> (H={H}, l={l})" if lg == 14 and l % 4 == 0 else f"fftconv_kernel<{lg}> (H={H}, l={l})"
+        tiles = B * ((l + 127) // 128)
+        k = {64: "sashimi_mix_umma_pers_kernel<64,2>" if tiles >= 6000 else "sashimi_mix_umma_kernel<64,2>",
+             128: "sashimi_mix_umma_pers_kernel<128,2>", 256: "sashimi_mix_umma256_kernel"}.get(H)
+        if k is None:
+            k = "mix_gemm_umma_kernel x3 + channel_stats_kernel x2" if H % 128 == 0 else f"sashimi_mix_mma_kernel<{H}> (mma.sync)"
+        return f"{k} (H={H}, l={l})"
+    return kname
 
 
 def metric_name(T):
@@ -335,7 +350,7 @@ def roofline(name, res, eng, B, dev):
     cfg = spec["cfg"]
     kern = {}
     for kname, (kms, cnt) in prof.items():
-        ent = {"ms_per_forward": round(kms, 4), "launches": cnt, "share": round(kms / tot, 4)}
+        ent = {"kernel": kernel_label(kname, cfg, B), "ms_per_forward": round(kms, 4), "launches": cnt, "share": round(kms / tot, 4)}
         us = kms / cnt * 1e3
         if kname.startswith("fftconv_s") or kname.startswith("mix_s"):
             s = int(kname[-1])
@@ -361,7 +376,7 @@ def roofline(name, res, eng, B, dev):
         traffic = tj.get(f"{name}:{dom}", tj.get(dom, {}) if name == DEFAULT else {}).get(str(B))
     if spec["bound"] == "hbm":
         whole = res["bytes_cs"] * T * B / step_s / 1e9
-        roof = {"bound": "hbm", "kernel": KERNEL_NAMES.get(dom, dom), "achieved": d.get("achieved_GBs"), "peak": hbm, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": kernel_label(dom, cfg, B), "achieved": d.get("achieved_GBs"), "peak": hbm, "unit": "GB/s",
                 "frac": d.get("frac_of_hbm"), "traffic": traffic, "peak_source": src,
                 "algorithmic_bytes_per_launch": d.get("algorithmic_bytes_per_launch"),
                 "whole_loop": {"achieved": round(whole, 1), "frac": round(whole / hbm, 4), "unit": "GB/s",
@@ -369,7 +384,7 @@ def roofline(name, res, eng, B, dev):
                                "note": "SURVEY 8(d) bytes x T x B / step time"}}
     else:
         whole = res["flops_cs"] * T * B / step_s / 1e12
-        roof = {"bound": "tensor", "kernel": KERNEL_NAMES.get(dom, dom), "achieved": d.get("achieved_TFs"), "peak": tf,
+        roof = {"bound": "tensor", "kernel": kernel_label(dom, cfg, B), "achieved": d.get("achieved_TFs"), "peak": tf,
                 "unit": "TFLOP/s", "frac": d.get("frac_of_tensor"), "traffic": traffic, "peak_source": src,
                 "algorithmic_flops_per_launch": d.get("algorithmic_flops_per_launch"),
                 "note": "fp32-equivalent work; every product is 3 bf16 MMAs (hi*hi + lo*hi + hi*lo, the parity mode), "
@@ -398,6 +413,12 @@ def main():
 
     import torch
     import torch.distributed as dist
+
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner at communicator
+    # creation) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -456,6 +477,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if line:
         print(json.dumps(line))
 
