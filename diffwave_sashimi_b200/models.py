@@ -81,19 +81,50 @@ class _EngineBacked(nn.Module):
 
     _cfg: dict
 
+    def _fingerprint(self):
+        # (address, in-place version) of every parameter and buffer: changes under optimizer steps, submodule
+        # load_state_dict, .to()/.cuda(), in-place edits.  Writes through `p.data` do not bump the version counter:
+        # call invalidate() after those.
+        ts = self.__dict__.get("_fp_tensors")
+        if ts is None:                  # the Parameter / buffer objects themselves are stable: cache the traversal
+            ts = self.__dict__["_fp_tensors"] = list(self.parameters()) + list(self.buffers())
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
     def _engine_get(self):
         from .engine import Engine
         eng = self.__dict__.get("_engine")
+        if eng is not None and self.__dict__.get("_engine_fp") != self._fingerprint():
+            self.invalidate()           # parameters changed under the compiled plan: rebuild rather than serve stale weights
+            eng = None
         if eng is None:
             eng = Engine(self._cfg, self)
             self.__dict__["_engine"] = eng
+            self.__dict__["_engine_fp"] = self._fingerprint()     # after the build: it may rewrite fresh S4 kernels in place
         return eng
 
     def invalidate(self):
-        """Drop the compiled plan (call after changing parameters in place)."""
+        """Drop the compiled plan (needed only after writes through `p.data`; everything else is detected)."""
         eng = self.__dict__.pop("_engine", None)
+        self.__dict__.pop("_engine_fp", None)
+        self.__dict__.pop("_fp_tensors", None)
         if eng is not None:
             eng.close()
+
+    def __getstate__(self):             # the plan is a ctypes handle: never pickled or deep-copied with the module
+        st = self.__dict__.copy()
+        st.pop("_engine", None)
+        st.pop("_engine_fp", None)
+        st.pop("_fp_tensors", None)
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
 
     def load_state_dict(self, *a, **k):
         self.invalidate()

@@ -161,3 +161,27 @@ def test_generate_entry_point_vocodes_a_wav(dwb, tmp_path):
     for p in outs:
         rate, data = wavfile.read(str(p))
         assert rate == sr and data.dtype == np.float32 and data.shape == (frames * 256,) and np.isfinite(data).all()
+
+
+def test_plan_follows_parameter_changes(dwb):
+    """in-place parameter changes (optimizer step, EMA copy_, submodule load_state_dict) must not leave a
+    stale compiled plan behind; modules stay deep-copyable and picklable after they have run."""
+    import copy
+    import pickle
+    g = load_golden("tiny_wnet")
+    net = _model(dwb, g["cfg"], g["sd"])
+    x, t = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()
+    with torch.no_grad():
+        e0 = net((x, t)).clone()
+        assert rel_l2(e0.cpu(), g["eps"]) < 1e-4
+        net.final_conv[2].conv.weight.mul_(2.0)                  # in place, no load_state_dict
+        net.final_conv[2].conv.bias.mul_(2.0)
+        e1 = net((x, t)).clone()
+        assert rel_l2(e1.cpu(), 2.0 * g["eps"]) < 1e-4
+        sub = {k: v * 0.5 for k, v in net.final_conv[2].state_dict().items()}
+        net.final_conv[2].load_state_dict(sub)                   # submodule load
+        assert rel_l2(net((x, t)).cpu(), g["eps"]) < 1e-4
+        twin = copy.deepcopy(net)
+        assert torch.equal(twin((x, t)), net((x, t)))
+        again = pickle.loads(pickle.dumps(net))
+        assert torch.equal(again.cuda()((x, t)), net((x, t)))
