@@ -10,6 +10,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "common.cuh"
+
 namespace dwb {
 namespace s2 {
 
@@ -180,22 +182,19 @@ __device__ __forceinline__ void rotate_w32(C2 (&x)[16]) {
 
 
 // ---- elementwise activations, two lanes (MUFU and the final selects stay scalar) ---------------------
-// GELU (erf form): same formula as gelu_fast (common.cuh)
+// GELU (erf form): same formula as gelu_fast (common.cuh): 0.5 x + |x| (0.5 - 2^-Q(|x|)); 5 FFMA2 + FADD2 + FMUL2 +
+// FFMA2 packed, the two |x| and the two MUFU.EX2 scalar
 __device__ __forceinline__ V2 gelu_fast2(const V2 &x) {
-    float t0, t1, e0, e1;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.v.x), 1.0f)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.v.y), 1.0f)));
-    const V2 t(t0, t1);
-    V2 p = fma(t, V2(1.061405429f), V2(-1.453152027f));
-    p = fma(t, p, V2(1.421413741f));
-    p = fma(t, p, V2(-0.284496736f));
-    p = fma(t, p, V2(0.254829592f));
-    const V2 ea = (x * x) * (-0.5f * 1.4426950408889634f);
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(ea.v.x));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(ea.v.y));
-    const V2 hh = (x * 0.5f) * (V2(e0, e1) * (p * t));
-    const V2 d = x - hh;
-    return V2(x.v.x >= 0.f ? d.v.x : hh.v.x, x.v.y >= 0.f ? d.v.y : hh.v.y);
+    const V2 a(fabsf(x.v.x), fabsf(x.v.y));
+    V2 q = fma(a, V2(DWB_GELU_Q5), V2(DWB_GELU_Q4));
+    q = fma(a, q, V2(DWB_GELU_Q3));
+    q = fma(a, q, V2(DWB_GELU_Q2));
+    q = fma(a, q, V2(DWB_GELU_Q1));
+    q = fma(a, q, V2(DWB_GELU_Q0));
+    float h0, h1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(q.v.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(q.v.y));
+    return fma(a, V2(0.5f) - V2(h0, h1), x * 0.5f);
 }
 
 // 1 / (1 + exp(-x)), same approximations as __fdividef(1, 1 + __expf(-x))

@@ -22,6 +22,7 @@ struct MixArgs {
     float ln2_m, ln2_s;
     float *out, *stats_out;        // (B,H,l), (B,l,2)
     int H, F, l;
+    int rev;                       // tcgen05 kernels: walk tiles from the end of the batch (serpentine L2 reuse)
 };
 
 struct PoolArgs {
@@ -86,6 +87,7 @@ size_t mix_umma_image_bytes(int H);
 int mix_umma_pack(int H, const float *Wo_t, const float *W1_t, const float *W2_t, const float *bo, const float *b1,
                   const float *b2, uint8_t *img, float *bimg, cudaStream_t st);
 int mix_umma_launch(const MixArgs &a, int B, cudaStream_t st);
+bool mix_reverse_order();
 // widths without a fused tcgen05 kernel (H = 512): three tcgen05 GEMM launches + two statistics launches (mix_gemm_umma.cu)
 bool mix_gemm_supported(int H, int F, int l);
 size_t mix_gemm_image_bytes(int H, int F);

@@ -90,6 +90,56 @@ __device__ __forceinline__ void stat_merge16(const float (&v)[16], int n, float 
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
+// ---- epilogue helpers shared by the fused kernels --------------------------------------------
+// channel stride in floats: a compile-time constant for the shapes of the BASELINE configs (the loads
+// and stores of a thread's channels then need no address arithmetic at all: [base + immediate]),
+// the runtime l otherwise (one IMAD.WIDE per access)
+template <int LC>
+__device__ __forceinline__ const float *chan(const float *base, int i, int l) {
+    if (LC) return base + (size_t)i * LC;
+    return reinterpret_cast<const float *>(reinterpret_cast<const char *>(base) + (unsigned long long)(unsigned)(4 * l) * (unsigned)i);
+}
+template <int LC>
+__device__ __forceinline__ float *chan(float *base, int i, int l) {
+    if (LC) return base + (size_t)i * LC;
+    return reinterpret_cast<float *>(reinterpret_cast<char *>(base) + (unsigned long long)(unsigned)(4 * l) * (unsigned)i);
+}
+
+// running sums of d = v - pivot and d^2 over 16 values, two values per packed instruction.  The pivot
+// (the thread's first value) keeps the final M2 = sum d^2 - (sum d)^2 / n free of the cancellation a raw
+// sum of squares has when |mean| >> std.
+__device__ __forceinline__ void stat_acc16(const float (&v)[16], const s2::V2 &piv, s2::V2 &sd, s2::V2 &sq) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        const s2::V2 d = s2::V2(v[i], v[i + 1]) - piv;
+        sd = sd + d;
+        sq = s2::fma(d, d, sq);
+    }
+}
+__device__ __forceinline__ void stat_finish(const s2::V2 &sd, const s2::V2 &sq, float piv, int n, float &mean, float &M2) {
+    const float S = sd.v.x + sd.v.y, Q = sq.v.x + sq.v.y, inv = 1.0f / (float)n;
+    mean = fmaf(S, inv, piv);
+    M2 = fmaxf(fmaf(-S * inv, S, Q), 0.f);
+}
+
+// fp32 -> (hi, lo) bf16 split of 8 consecutive K elements with the residuals as packed subtractions
+__device__ __forceinline__ void split8p(const float *v, uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = v[2 * i], b = v[2 * i + 1];
+        uint32_t hp;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(b), "f"(a));     // low half = a, high half = b
+        const s2::V2 d = s2::V2(a, b) - s2::V2(__uint_as_float(hp << 16), __uint_as_float(hp & 0xFFFF0000u));
+        uint32_t lp;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lp) : "f"(d.v.y), "f"(d.v.x));
+        h[i] = hp;
+        l[i] = lp;
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 template <int H, int CS>
 __global__ void __launch_bounds__(UCfg<H, CS>::NTHREADS, (H == 64) ? 2 : 1)
 sashimi_mix_umma_kernel(MixArgs a) {
@@ -106,7 +156,7 @@ sashimi_mix_umma_kernel(MixArgs a) {
              *acc3_ready = acc2_ready + C::NC1;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y, t0 = blockIdx.x * UM_TT, l = a.l;
+    const int b = a.rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y, t0 = (a.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * UM_TT, l = a.l;
     long long *trace = a.trace ? a.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
 #define UM_TRACE(slot) do { if (trace && tid == 0) trace[slot] = clock64(); } while (0)
 #define UM_TRACE_MMA(slot) do { if (trace) trace[slot] = clock64(); } while (0)
@@ -486,9 +536,9 @@ struct PCfg {
     static_assert(SMEM <= 227 * 1024, "persistent tile set does not fit shared memory");
 };
 
-template <int H, int CS>
+template <int H, int CS, int LC>
 __global__ void __launch_bounds__(PCfg<H, CS>::NTHREADS, 1)
-sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
+sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
     using P = PCfg<H, CS>;
     using C = UCfg<H, CS>;
     extern __shared__ uint8_t smem_raw[];
@@ -500,7 +550,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
     uint64_t *wfull = bars + P::NG * P::NBAR_G, *wempty = wfull + P::NS;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int l = a.l, ntx = ceil_div(l, UM_TT), ntiles = B * ntx;
+    const int l = LC ? LC : a.l, ntx = ceil_div(l, UM_TT), ntiles = B * ntx;
     const int stride = gridDim.x * P::NG;
     long long *trace = a.trace ? a.trace + (size_t)blockIdx.x * 16 : nullptr;
 
@@ -518,7 +568,10 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
         }
         fence_mbar_init();
     }
-    for (int i = tid; i < 5 * H; i += P::NTHREADS) bias_s[i] = a.bimg[i];
+    // biases: bo' (2H; per 128: 64 value | 64 gate) b1 (F) b2 (H); the gate biases pre-multiplied by -log2(e)
+    // so that the sigmoid's exponent is one FFMA2 of the accumulator
+    for (int i = tid; i < 5 * H; i += P::NTHREADS)
+        bias_s[i] = a.bimg[i] * ((i < 2 * H && (i & 64)) ? -1.4426950408889634f : 1.0f);
     constexpr int EPI_WARPS = P::NG * P::GW;
     if (warp == EPI_WARPS) tmem_alloc(tptr, 512);
     tc_fence_before();
@@ -566,6 +619,18 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
                                     (acc0 || term > 0 || ks > 0) ? 1u : 0u);
                 }
             };
+            // G3 (TS form): the A operand is the hidden tile E2 left in TMEM over the accumulator columns it read:
+            // per 16 f-columns 8 packed hi columns then 8 packed lo columns = one K = 16 step each
+            auto issue_block_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t bbase, int NR) {
+                const uint32_t idesc = idesc_bf16(128, NR);
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t ao = a_tmem + (term == 1 ? 8 : 0);
+                    const uint32_t bo = bbase + (term == 2 ? NR * 128 : 0);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) mma_bf16_ts(d, ao + ks * 16, smem_desc_sw128(bo + ks * 32), idesc, 1u);
+                }
+            };
             int cnt = 0;     // weight stages consumed so far (ring position when streaming)
             uint32_t ph = 0;
 #pragma unroll 1
@@ -600,8 +665,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
                             mbar_wait(wfull + s, P::RESIDENT ? 0u : (uint32_t)((cnt / P::NS) & 1));
                             tc_fence_after();
                         }
-                        issue_block(tmem + C::R3 + nc * 128, slot0 + C::hid_slot(kc) * UM_SLOT,
-                                    w0 + s * UM_STAGE + (j % C::BPS3) * C::NR3 * 256, C::NR3, true);
+                        issue_block_ts(tmem + C::R3 + nc * 128, tmem + 64 * kc, w0 + s * UM_STAGE + (j % C::BPS3) * C::NR3 * 256, C::NR3);
                         if (j % C::BPS3 == C::BPS3 - 1) {
                             if (!P::RESIDENT) mma_commit(wempty + s);
                             ++i;
@@ -614,6 +678,10 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
         }
     } else {
         // ================= epilogue threads of group grp =========================================
+        // Software pipeline across the tiles of a group: the next tile's g is requested before this tile's
+        // last accumulator is awaited and becomes the A operand of the next G1 as soon as G3 has released
+        // the operand slots, so G1(next) runs under E3(this); the next tile's x is requested before E3 and
+        // stays in registers until E1 (no TMEM staging).  x1 likewise stays in registers from E1 to LN2.
         const int grp = warp / P::GW, cg = (warp % P::GW) >> 2, q = warp & 3;
         const int r = 32 * q + lane;
         uint64_t *gb = bars + grp * P::NBAR_G;
@@ -653,34 +721,34 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
                 M2 = m2;
             }
         };
-
-        int tile = blockIdx.x * P::NG + grp;
-        float gin[PER];
-        {
-            const int b = tile / ntx, t = (tile - b * ntx) * UM_TT + r;
-            const bool valid = tile < ntiles && t < l;
-            const size_t brow = (size_t)b * H * l + (valid ? t : 0);
-            const float *gp = a.g + brow + cg * PER * l;
+        // this thread's channels of a (B,H,l) tensor at tile `tl_`: g / skip / out use h = cg*PER + i,
+        // x uses the GLU pairing h = nc*64 + cg*PP + i (the columns E1 produces)
+        auto tile_row = [&](int tile_, bool &valid_) -> size_t {
+            const int pt_ = rev ? ntiles - 1 - tile_ : tile_;           // rev: walk the batch from its end (see mix_umma_launch)
+            const int b_ = pt_ / ntx, t_ = (pt_ - b_ * ntx) * UM_TT + r;
+            valid_ = tile_ < ntiles && t_ < l;
+            return (size_t)b_ * H * l + (valid_ ? t_ : 0);
+        };
+        auto load_g = [&](float (&gin)[PER], int tile_) {
+            bool v_;
+            const float *gp = a.g + tile_row(tile_, v_) + (size_t)cg * PER * l;
 #pragma unroll
-            for (int i = 0; i < PER; ++i, gp += l) gin[i] = valid ? __ldg(gp) : 0.f;
-        }
-        uint32_t ph = 0;
-        int it = 0;
-        if (grp > 0 && stagger_ns > 0) __nanosleep(stagger_ns);     // start the groups out of phase
-#pragma unroll 1
-        for (; tile < ntiles; tile += stride, ph ^= 1, ++it) {
-            const int b = tile / ntx, t = (tile - b * ntx) * UM_TT + r;
-            const bool valid = t < l;
-            const size_t brow = (size_t)b * H * l + (valid ? t : 0);
-            const float *xp = a.x + brow;
-            float *op = a.out + brow;
-            PT(0);
-            // ---- g: split, store as the A operand of G1
+            for (int i = 0; i < PER; ++i) gin[i] = v_ ? __ldg(chan<LC>(gp, i, l)) : 0.f;
+        };
+        auto load_x = [&](float (&xin)[PER], int tile_) {
+            bool v_;
+            const float *xp = a.x + tile_row(tile_, v_) + (size_t)cg * PP * l;
+#pragma unroll
+            for (int nc = 0; nc < C::NC1; ++nc)
+#pragma unroll
+                for (int i = 0; i < PP; ++i) xin[nc * PP + i] = v_ ? __ldg(chan<LC>(xp, nc * 64 + i, l)) : 0.f;
+        };
+        auto store_g = [&](const float (&gin)[PER]) {
 #pragma unroll
             for (int c8 = 0; c8 < PER / 8; ++c8) {
                 const int h0 = cg * PER + c8 * 8;
                 uint4 hi, lo;
-                split8(gin + 8 * c8, hi, lo);
+                split8p(gin + 8 * c8, hi, lo);
                 uint8_t *slot = slots + (h0 >> 6) * UM_SLOT;
                 const uint32_t off = sw128_off(r, (h0 & 63) >> 3);
                 *reinterpret_cast<uint4 *>(slot + off) = hi;
@@ -688,86 +756,95 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
             }
             fence_proxy_async_smem();
             mbar_arrive(g_ready);
-            PT(1);
-            // ---- x -> TMEM R3 while G1 runs
-            {
-                float xin[PER];
-#pragma unroll
-                for (int nc = 0; nc < C::NC1; ++nc) {
-                    const float *xq = xp + (nc * 64 + cg * PP) * l;
-#pragma unroll
-                    for (int i = 0; i < PP; ++i, xq += l) xin[nc * PP + i] = valid ? __ldg(xq) : 0.f;
-                }
-#pragma unroll
-                for (int nc = 0; nc < C::NC1; ++nc)
-#pragma unroll
-                    for (int sc = 0; sc < PP / 16; ++sc) {
-                        float v[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = xin[nc * PP + sc * 16 + i];
-                        tmem_st16(tl + C::R3 + nc * 64 + cg * PP + sc * 16, v);
-                    }
-                tmem_wait_st();
-            }
-            PT(2);
-            // ---- E1: GLU + residual -> x1 (TMEM R3), LN2 statistics
-            float mean = 0.f, M2 = 0.f;
-            {
-                int n = 0;
+        };
+
+        int tile = blockIdx.x * P::NG + grp;
+        float xin[PER];                               // x of this tile, then x1 (E1 -> LN2)
+        {
+            float gin[PER];
+            load_g(gin, tile);
+            load_x(xin, tile);
+            if (grp > 0 && stagger_ns > 0) __nanosleep(stagger_ns);     // start the groups out of phase
+            if (tile < ntiles) store_g(gin);
+        }
+        uint32_t ph = 0;
+        int it = 0;
 #pragma unroll 1
+        for (; tile < ntiles; tile += stride, ph ^= 1, ++it) {
+            const int ptile = rev ? ntiles - 1 - tile : tile;
+            const int b = ptile / ntx, t = (ptile - b * ntx) * UM_TT + r;
+            const bool valid = t < l;
+            const size_t brow = (size_t)b * H * l + (valid ? t : 0);
+            PT(0);
+            // ---- E1: GLU + residual -> x1 (TMEM R3 for G3's accumulation, registers for LN2), LN2 statistics
+            float mean, M2;
+            {
+                s2::V2 sd(0.f), sq(0.f);
+                float piv = 0.f;
+#pragma unroll
                 for (int nc = 0; nc < C::NC1; ++nc) {
                     mbar_wait(acc1_ready + nc, ph);
                     tc_fence_after();
-                    if (nc == 0) PT(3);
-#pragma unroll 1
+                    if (nc == 0) PT(1);
+#pragma unroll
                     for (int sc = 0; sc < PP / 16; ++sc) {
                         const int p0 = cg * PP + sc * 16, h0 = nc * 64 + p0;
-                        float xv[16], av[16], gv[16];
+                        float av[16], gv[16];
                         tmem_ld16(tl + nc * 128 + p0, av);
                         tmem_ld16(tl + nc * 128 + 64 + p0, gv);
-                        tmem_ld16(tl + C::R3 + h0, xv);
                         tmem_wait_ld();
                         const float *ba = bo_s + nc * 128 + p0;
+                        float(&xv)[16] = *reinterpret_cast<float(*)[16]>(xin + nc * PP + sc * 16);
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
-                            // two channels per packed instruction (FADD2 / FMUL2 / FFMA2)
-                            s2::V2 y = (s2::V2(av[i], av[i + 1]) + s2::V2(ba[i], ba[i + 1])) *
-                                       s2::sigmoid_fast2(s2::V2(gv[i], gv[i + 1]) + s2::V2(ba[64 + i], ba[64 + i + 1]));
-                            y = y + s2::V2(xv[i], xv[i + 1]);
+                            // two channels per packed instruction: sigmoid(gate) = 1 / (1 + 2^(-log2e gate - log2e b))
+                            const s2::V2 ea = s2::fma(s2::V2(gv[i], gv[i + 1]), s2::V2(-1.4426950408889634f), s2::V2(ba[64 + i], ba[64 + i + 1]));
+                            float e0, e1, r0, r1;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(ea.v.x));
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(ea.v.y));
+                            const s2::V2 dn = s2::V2(e0, e1) + s2::V2(1.0f);
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(dn.v.x));
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(dn.v.y));
+                            const s2::V2 y = s2::fma(s2::V2(av[i], av[i + 1]) + s2::V2(ba[i], ba[i + 1]), s2::V2(r0, r1), s2::V2(xv[i], xv[i + 1]));
                             xv[i] = y.v.x;
                             xv[i + 1] = y.v.y;
-                            if (a.cond && valid) {
-                                xv[i] += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i) * l);
-                                xv[i + 1] += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i + 1) * l);
-                            }
                         }
-                        stat_merge16(xv, n, mean, M2);
-                        n += 16;
+                        if (a.cond && valid) {
+                            const float *cp = a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (size_t)h0 * l;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) xv[i] += __ldg(chan<LC>(cp, i, l));
+                        }
+                        if (nc == 0 && sc == 0) piv = xv[0];
+                        stat_acc16(xv, s2::V2(piv), sd, sq);
                         tmem_st16(tl + C::R3 + h0, xv);
                     }
                 }
+                stat_finish(sd, sq, piv, PER, mean, M2);
                 tmem_wait_st();
             }
-            PT(4);
+            PT(2);
             exchange(mean, M2);
             // ---- z = LN2(x1), split, store as the A operand of G2
             {
                 const float rstd = valid ? rsqrtf(M2 * (1.0f / H)) : 0.f;
-                const float sc_a = a.ln2_s * rstd, sh = a.ln2_m - mean;
-#pragma unroll 1
+                const float sc_a = a.ln2_s * rstd;
+                const s2::V2 sc2(sc_a), sh2(sc_a * (a.ln2_m - mean));
+#pragma unroll
                 for (int k = 0; k < PER / 16; ++k) {
                     const int nc = k / (PP / 16), sc = k % (PP / 16);
                     const int h0 = nc * 64 + cg * PP + sc * 16;
                     float v[16];
-                    tmem_ld16(tl + C::R3 + h0, v);
-                    tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = sc_a * (v[i] + sh);
+                    for (int i = 0; i < 16; i += 2) {
+                        const s2::V2 z = s2::fma(s2::V2(xin[k * 16 + i], xin[k * 16 + i + 1]), sc2, sh2);
+                        v[i] = z.v.x;
+                        v[i + 1] = z.v.y;
+                    }
                     uint8_t *slot = slots + (h0 >> 6) * UM_SLOT;
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         uint4 hi, lo;
-                        split8(v + 8 * hh, hi, lo);
+                        split8p(v + 8 * hh, hi, lo);
                         const uint32_t off = sw128_off(r, ((h0 & 63) >> 3) + hh);
                         *reinterpret_cast<uint4 *>(slot + off) = hi;
                         *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
@@ -777,7 +854,8 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
                 tc_fence_before();
                 mbar_arrive(z_ready);
             }
-            PT(5);
+            const int nt = tile + stride;
+            PT(3);
             // ---- E2: hidden = gelu(W1 z + b1), split, store as the A operand of G3
             {
                 constexpr int PERF = 128 / CS;
@@ -785,7 +863,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
                 for (int nc = 0; nc < C::NC1; ++nc) {
                     mbar_wait(acc2_ready + nc, ph);
                     tc_fence_after();
-                    if (nc == 0) PT(6);
+                    if (nc == 0) PT(4);
 #pragma unroll 1
                     for (int sc = 0; sc < PERF / 16; ++sc) {
                         const int col = cg * PERF + sc * 16, f0 = nc * 128 + col;
@@ -795,78 +873,85 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns) {
                         const float *bb = b1_s + f0;
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
-                        const s2::V2 r = s2::gelu_fast2(s2::V2(v[i], v[i + 1]) + s2::V2(bb[i], bb[i + 1]));
-                        v[i] = r.v.x;
-                        v[i + 1] = r.v.y;
-                    }
-                        const int kc = f0 >> 6;
-                        uint8_t *slot = slots + C::hid_slot(kc) * UM_SLOT;
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            uint4 hi, lo;
-                            split8(v + 8 * hh, hi, lo);
-                            const uint32_t off = sw128_off(r, ((f0 & 63) >> 3) + hh);
-                            *reinterpret_cast<uint4 *>(slot + off) = hi;
-                            *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
+                            const s2::V2 rr = s2::gelu_fast2(s2::V2(v[i], v[i + 1]) + s2::V2(bb[i], bb[i + 1]));
+                            v[i] = rr.v.x;
+                            v[i + 1] = rr.v.y;
                         }
+                        const int kc = f0 >> 6;
+                        uint4 h0, l0, h1, l1;
+                        split8p(v, h0, l0);
+                        split8p(v + 8, h1, l1);
+                        tmem_st8(tl + f0, h0, h1);                 // in place: the 16 columns just read
+                        tmem_st8(tl + f0 + 8, l0, l1);
                         if (((f0 + 16) & 63) == 0 || sc == PERF / 16 - 1) {
-                            fence_proxy_async_smem();
+                            tmem_wait_st();
                             tc_fence_before();
                             mbar_arrive(hid_ready + kc);
                         }
                     }
                 }
             }
-            PT(7);
-            // ---- the next tile's g goes in flight now and lands while E3 runs
+            PT(5);
+            // ---- the next tile's g goes in flight now; once G3 has released the operand slots it becomes the
+            //      A operand of G1(next), which then runs under E3
             {
-                const int nt = tile + stride;
-                const int nb = nt / ntx, ntm = (nt - nb * ntx) * UM_TT + r;
-                const bool nvalid = nt < ntiles && ntm < l;
-                const size_t nrow = (size_t)nb * H * l + (nvalid ? ntm : 0);
-                const float *gp = a.g + nrow + cg * PER * l;
-#pragma unroll
-                for (int i = 0; i < PER; ++i, gp += l) gin[i] = nvalid ? __ldg(gp) : 0.f;
-            }
-            // ---- E3: x2 = acc3 (= x1 + W2 hidden) + b2 (+skip); store; statistics for the next norm
-            {
+                float gin[PER];
+                load_g(gin, nt);
                 mbar_wait(acc3_ready, ph);
                 tc_fence_after();
-                PT(8);
-                int n = 0;
-                mean = 0.f;
-                M2 = 0.f;
+                PT(6);
+                if (nt < ntiles) store_g(gin);
+            }
+            // x of the next tile: requested here, lands during E3, consumed by E1 of the next tile (a request before E2
+            // measured slower: the burst of loads blocks the issuing warps until the memory pipeline accepts it, and
+            // here the other group's E2 and this group's G1(next) fill that time)
+            load_x(xin, nt);
+            PT(7);
+            // ---- E3: x2 = acc3 (= x1 + W2 hidden) + b2 (+skip); store; statistics for the next norm
+            {
+                s2::V2 sd(0.f), sq(0.f);
+                float piv = 0.f;
+                float *op = a.out + brow + (size_t)cg * PER * l;
+                const float *sp = a.skip ? a.skip + brow + (size_t)cg * PER * l : nullptr;
 #pragma unroll 1
                 for (int sc = 0; sc < PER / 16; ++sc) {
                     const int h0 = cg * PER + sc * 16;
                     float v[16];
                     tmem_ld16(tl + C::R3 + h0, v);
-                    if (a.skip) {
-                        float sk[16];
-                        const float *sp = a.skip + brow + h0 * l;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i, sp += l) sk[i] = valid ? __ldg(sp) : 0.f;
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += sk[i];
-                    } else
-                        tmem_wait_ld();
                     const float *bb = b2_s + h0;
+                    if (sp) {
+                        float sk[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += bb[i];
-                    if (valid) {
-                        float *oq = op + h0 * l;
+                        for (int i = 0; i < 16; ++i) sk[i] = valid ? __ldg(chan<LC>(sp, sc * 16 + i, l)) : 0.f;
+                        tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i, oq += l) *oq = v[i];
+                        for (int i = 0; i < 16; i += 2) {
+                            const s2::V2 y = (s2::V2(v[i], v[i + 1]) + s2::V2(bb[i], bb[i + 1])) + s2::V2(sk[i], sk[i + 1]);
+                            v[i] = y.v.x;
+                            v[i + 1] = y.v.y;
+                        }
+                    } else {
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            const s2::V2 y = s2::V2(v[i], v[i + 1]) + s2::V2(bb[i], bb[i + 1]);
+                            v[i] = y.v.x;
+                            v[i + 1] = y.v.y;
+                        }
                     }
-                    stat_merge16(v, n, mean, M2);
-                    n += 16;
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) *chan<LC>(op, sc * 16 + i, l) = v[i];
+                    }
+                    if (sc == 0) piv = v[0];
+                    stat_acc16(v, s2::V2(piv), sd, sq);
                 }
+                stat_finish(sd, sq, piv, PER, mean, M2);
                 exchange(mean, M2);
                 if (cg == 0 && valid)
                     *reinterpret_cast<float2 *>(a.stats_out + ((size_t)b * l + t) * 2) = make_float2(mean, rsqrtf(M2 * (1.0f / H)));
             }
-            PT(9);
+            PT(8);
         }
 #undef PT
     }
@@ -934,7 +1019,7 @@ sashimi_mix_umma256_kernel(MixArgs a) {
              *acc2_ready = acc1_ready + C::NC1, *acc3_ready = acc2_ready + C::NC1;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y, t0 = blockIdx.x * UM_TT, l = a.l;
+    const int b = a.rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y, t0 = (a.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * UM_TT, l = a.l;
     if (tid == 0) {
         for (int i = 0; i < C::NS; ++i) {
             mbar_init(wfull + i, 1);
@@ -1398,26 +1483,46 @@ static int launch_umma(const MixArgs &a, int B, cudaStream_t st) {
     return DWB_OK;
 }
 
-template <int H, int CS>
+template <int H, int CS, int LC>
 static int launch_umma_pers(const MixArgs &a, int B, cudaStream_t st) {
     using P = PCfg<H, CS>;
-    auto k = sashimi_mix_umma_pers_kernel<H, CS>;
+    auto k = sashimi_mix_umma_pers_kernel<H, CS, LC>;
     static int sms[16] = {};
     int dev = 0;
     DWB_CUDA(cudaGetDevice(&dev));
     if (!sms[dev & 15]) {
-        DWB_CUDA(cudaDeviceGetAttribute(&sms[dev & 15], cudaDevAttrMultiProcessorCount, dev));
         DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+        DWB_CUDA(cudaDeviceGetAttribute(&sms[dev & 15], cudaDevAttrMultiProcessorCount, dev));
     }
     const int ntiles = B * ceil_div(a.l, UM_TT);
     const int grid = std::min(sms[dev & 15], ceil_div(ntiles, P::NG));
     static const int stagger = [] { const char *e = getenv("DWB_UMMA_STAGGER"); return e ? atoi(e) : 0; }();
-    k<<<grid, P::NTHREADS, P::SMEM, st>>>(a, B, stagger);
+    k<<<grid, P::NTHREADS, P::SMEM, st>>>(a, B, stagger, mix_reverse_order() ? 1 : 0);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
 }
+// the stage lengths of the BASELINE configs get a compile-time channel stride (LC), every other length the generic kernel
+template <int H, int CS>
+static int launch_umma_pers_l(const MixArgs &a, int B, cudaStream_t st) {
+    switch (a.l) {
+        case 16000: return launch_umma_pers<H, CS, 16000>(a, B, st);
+        case 4000: return launch_umma_pers<H, CS, 4000>(a, B, st);
+        case 1000: return launch_umma_pers<H, CS, 1000>(a, B, st);
+    }
+    return launch_umma_pers<H, CS, 0>(a, B, st);
+}
 
-int mix_umma_launch(const MixArgs &a, int B, cudaStream_t st) {
+// Serpentine order between consecutive kernels: the S4 convolution walks the batch forwards, the mixing kernel
+// that follows walks it backwards, so each kernel starts on the clips its predecessor touched last - the part of
+// the (B,H,l) tensors that is still in the 126 MB L2 (DWB_SERPENTINE=0 turns it off for the A/B).
+bool mix_reverse_order() {
+    static const bool on = [] { const char *e = getenv("DWB_SERPENTINE"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+
+int mix_umma_launch(const MixArgs &a_in, int B, cudaStream_t st) {
+    MixArgs a = a_in;
+    a.rev = mix_reverse_order() ? 1 : 0;
     DWB_REQUIRE(a.Wimg && a.bimg, DWB_ERR_STATE, "mix_umma: weights were not packed");
     DWB_REQUIRE((int64_t)a.H * a.l < (int64_t)1 << 31, DWB_ERR_UNSUPPORTED, "mix_umma: H*l = %lld needs 64-bit channel offsets",
                 (long long)a.H * a.l);
@@ -1438,9 +1543,10 @@ int mix_umma_launch(const MixArgs &a, int B, cudaStream_t st) {
     // round 2, B = 64 (8000 tiles at H = 64): per-tile 370 us, persistent 337 us - the per-CTA setup (TMEM allocation
     // against the co-resident CTA, barrier init, bias staging: 3.1 K of 21.7 K cycles per tile) stops paying for itself
     const bool pers = mode == 2 || (mode == 0 && (a.H == 128 || (int64_t)B * ceil_div(a.l, UM_TT) >= 6000));
+    static const bool cs4 = [] { const char *e = getenv("DWB_UMMA_CS"); return e && atoi(e) == 4; }();
     if (pers) switch (a.H) {
-        case 64: return launch_umma_pers<64, 2>(a, B, st);
-        case 128: return launch_umma_pers<128, 2>(a, B, st);
+        case 64: return launch_umma_pers_l<64, 2>(a, B, st);
+        case 128: return cs4 ? launch_umma_pers_l<128, 4>(a, B, st) : launch_umma_pers_l<128, 2>(a, B, st);
     }
     switch (a.H) {
         case 64: return launch_umma<64, 2>(a, B, st);

@@ -12,8 +12,9 @@ net = dwb.construct_model(dict(cfg)); net.load_state_dict(sd); net = net.cuda().
 eng = net._engine_get()
 pers_env = os.environ.get("DWB_UMMA")
 for blk, H, l in [(0, 64, 16000), (1, 128, 4000), (2, 256, 1000)]:
-    pers = (pers_env == "pers") or (pers_env is None and H == 128)
-    names = (["top", "g_arrive", "x_tmem", "acc1", "E1", "z_arrive", "acc2", "E2", "acc3", "E3end"] if pers else
+    ntile_all = B * ((l + 127) // 128)
+    pers = H != 256 and ((pers_env == "pers") or (pers_env is None and (H == 128 or ntile_all >= 6000)))
+    names = (["top", "acc1", "E1", "z_arrive+x_next", "acc2", "E2", "acc3", "g_next", "E3end"] if pers else
              ["start", "setup", "g_arrive", "x_tmem", "acc1", "E1", "z_arrive", "acc2", "skip_ld", "acc3", "E3", "endsync", "mma_g", "mma_z", "mma_end"])
     g = torch.randn(B, H, l, device="cuda"); x = torch.randn(B, H, l, device="cuda")
     out = torch.empty_like(x); st = torch.empty(B, l, 2, device="cuda")
@@ -29,6 +30,8 @@ for blk, H, l in [(0, 64, 16000), (1, 128, 4000), (2, 256, 1000)]:
     t = t[t[:, 1] > 0]
     rel = t[:, :15] - t[:, :1]
     print(f"H={H} l={l} B={B}: {B*ntile} tiles, {'persistent' if pers else 'per-tile'} kernel, {e0.elapsed_time(e1)*1e3:.0f} us; median cycles since CTA/tile start:")
+    if len(rel) == 0:
+        continue
     med = rel.median(0).values
     for i, n in enumerate(names):
         print(f"   {n:10s} {med[i]:9.0f}")
