@@ -21,7 +21,10 @@
 //
 // Roles: warps [0, 4*CS) epilogue (CS threads per time step, each a contiguous column group),
 // warp 4*CS = weight producer (one lane), warp 4*CS+1 = TMEM owner + MMA issuer (one lane).
+#include <cuda.h>
 #include <stdlib.h>
+
+#include <string.h>
 
 #include <algorithm>
 #include <string>
@@ -506,13 +509,26 @@ sashimi_mix_umma_kernel(MixArgs a) {
 }
 
 // =========================================================================================
-// Persistent variant: one CTA per SM walks a strided list of tiles.  NG independent groups of
-// epilogue warps (each with its own MMA-issuer warp, barriers, operand slots and TMEM columns)
-// keep NG tiles in flight, so the waits of one group (HBM loads, MMA round trips) are filled by
-// the other's arithmetic; barriers, TMEM and (H = 64) the whole 96 KB weight image are set up
-// once per CTA instead of once per tile, and the next tile's g is already in flight while the
-// current tile finishes.  H = 128 has room for one group only (its operands need 128 KB) and
-// keeps streaming the 384 KB weight image through the ring.
+// Persistent variant: one CTA per SM walks a strided list of tiles; NG independent groups of
+// epilogue warps (each with its own MMA-issuer warp, barriers and TMEM columns) keep NG tiles in
+// flight, so the waits of one group are filled by the other's arithmetic.  Barriers, TMEM and
+// (H = 64) the whole 96 KB weight image are set up once per CTA; H = 128 has TMEM for one group
+// only and streams its 384 KB weight image through a ring.
+//
+// No activation operand touches shared memory: the A operands of all three GEMMs live in TMEM
+// (tcgen05.mma TS form).  Per group:  ACC [0, 2H) accumulator of G1 / G2, then - written in place
+// by E2 over the columns it has just read - the split hidden tile (per 16 f-columns: 8 packed hi
+// columns, 8 packed lo columns = one K = 16 step each);  R3 [2H, 3H) x1 -> x2 (G3 accumulates onto
+// x1);  AOP [3H, 4H) the split g tile, then the split z = LN2(x1) tile, same [8 hi | 8 lo] layout.
+// Shared memory holds the weights and, per group, two fp32 [H x 128] staging buffers that a
+// producer warp fills one tile ahead with 1-D bulk copies (one 512-byte row per channel): XB with
+// the next tile's x, GB with its g.  The epilogue threads read them with plain LDS, so nothing
+// they execute waits on global memory except the optional skip tensor, and up to 4 x 32 KB of
+// input are in flight per SM at any time (register prefetch kept ~40 KB in flight and paced the
+// kernel at ~3 TB/s: Little's law).  Tiles are software-pipelined inside a group: the next tile's
+// g operand is written as soon as G3 has been awaited, so G1(next) runs under E3(this).
+// STAGE = false (sequence lengths outside the BASELINE set, unaligned tensors) takes x and g
+// through registers with plain loads instead; everything else is identical.
 // =========================================================================================
 template <int H, int CS>
 struct PCfg {
@@ -520,25 +536,29 @@ struct PCfg {
     static constexpr int NG = (H == 64) ? 2 : 1;
     static constexpr bool RESIDENT = (H == 64);
     static constexpr int GW = 4 * CS, EPI = 128 * CS;
-    static constexpr int NTHREADS = NG * EPI + NG * 32 + 32;
+    // warps: NG epilogue groups | NG MMA issuers | weight producer | (streaming weights only) input-staging producer;
+    // with resident weights the weight producer is idle after its first copies and stages the inputs itself
+    static constexpr int NTHREADS = NG * EPI + NG * 32 + 32 + (RESIDENT ? 0 : 32);
     static constexpr int NS = RESIDENT ? U::NSTG : 2;          // weight buffers (RESIDENT: one per stage)
     static constexpr int GCOLS = 512 / NG;                     // TMEM columns per group
-    static constexpr int XCOL = 3 * H;                         // spare columns: statistics exchange
-    static constexpr int NBAR_G = 2 + U::KC3 + 2 * U::NC1 + 1;
+    static constexpr int R3 = 2 * H, AOP = 3 * H;
+    static constexpr int STG = H * 512;                        // one staged fp32 [H x 128] tile
+    static constexpr int NBAR_G = 2 + U::KC3 + 2 * U::NC1 + 1 + 4;      // g z hid[] acc1[] acc2[] acc3 | xfull xempty gfull gempty
     static constexpr int NBAR = NG * NBAR_G + 2 * NS;
-    static constexpr int OFF_SLOT = 0;
-    static constexpr int OFF_W = OFF_SLOT + NG * U::NSLOT * UM_SLOT;
+    static constexpr int OFF_STG = 0;
+    static constexpr int OFF_W = OFF_STG + NG * 2 * STG;
     static constexpr int OFF_BIAS = OFF_W + NS * UM_STAGE;
     static constexpr int OFF_BAR = OFF_BIAS + 5 * H * 4;
     static constexpr int OFF_TPTR = OFF_BAR + NBAR * 8;
     static constexpr int SMEM = OFF_TPTR + 16 + 1024;
-    static_assert(XCOL + 2 * CS <= GCOLS, "no spare TMEM columns for the statistics exchange");
+    static_assert(4 * H <= GCOLS, "TMEM budget: accumulator (2H) + x1 (H) + A operand (H) columns per group");
     static_assert(SMEM <= 227 * 1024, "persistent tile set does not fit shared memory");
 };
 
-template <int H, int CS, int LC>
+template <int H, int CS, int LC, bool STAGE>
 __global__ void __launch_bounds__(PCfg<H, CS>::NTHREADS, 1)
-sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
+sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __grid_constant__ CUtensorMap tm_x,
+                             const __grid_constant__ CUtensorMap tm_g) {
     using P = PCfg<H, CS>;
     using C = UCfg<H, CS>;
     extern __shared__ uint8_t smem_raw[];
@@ -559,8 +579,13 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
             uint64_t *gb = bars + g * P::NBAR_G;
             mbar_init(gb + 0, P::EPI);                                    // g_ready
             mbar_init(gb + 1, P::EPI);                                    // z_ready
-            for (int i = 0; i < C::KC3; ++i) mbar_init(gb + 2 + i, C::HID_ARRIVE);
+            for (int i = 0; i < C::KC3; ++i) mbar_init(gb + 2 + i, P::EPI);      // every thread contributes to every K chunk
             for (int i = 0; i < 2 * C::NC1 + 1; ++i) mbar_init(gb + 2 + C::KC3 + i, 1);   // acc1[], acc2[], acc3
+            uint64_t *sb = gb + P::NBAR_G - 4;
+            mbar_init(sb + 0, 1);                                         // xfull (transaction bytes)
+            mbar_init(sb + 1, P::EPI);                                    // xempty
+            mbar_init(sb + 2, 1);                                         // gfull
+            mbar_init(sb + 3, P::EPI);                                    // gempty
         }
         for (int i = 0; i < P::NS; ++i) {
             mbar_init(wfull + i, 1);
@@ -579,25 +604,72 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
     tc_fence_after();
     const uint32_t tmem0 = *tptr;
 
-    if (warp == EPI_WARPS + P::NG) {
+    if (STAGE && tid == 0) {
+        tma_prefetch_desc(&tm_x);
+        tma_prefetch_desc(&tm_g);
+    }
+    // ---- input staging producer: stream 2g = x tiles of group g, 2g + 1 = its g tiles; transfer k of a stream is the
+    // group's k-th tile and is issued as soon as transfer k - 1 has been taken out of the buffer
+    auto stage_producer = [&]() {
+        constexpr int NSTR = 2 * P::NG;
+        int k[NSTR], total[P::NG];
+        bool more = false;
+#pragma unroll
+        for (int g = 0; g < P::NG; ++g) {
+            const int first = blockIdx.x * P::NG + g;
+            k[2 * g] = k[2 * g + 1] = 0;
+            total[g] = first < ntiles ? (ntiles - 1 - first) / stride + 1 : 0;
+            more |= total[g] > 0;
+        }
+        while (more) {
+            more = false;
+#pragma unroll
+            for (int sidx = 0; sidx < NSTR; ++sidx) {
+                const int g = sidx >> 1, isg = sidx & 1;
+                if (k[sidx] >= total[g]) continue;
+                more = true;
+                uint64_t *sb = bars + g * P::NBAR_G + P::NBAR_G - 4 + 2 * isg;       // full, empty of this stream
+                if (k[sidx] > 0) {
+                    const int ok = lane == 0 ? (int)mbar_try(sb + 1, (uint32_t)((k[sidx] - 1) & 1)) : 0;
+                    if (!__shfl_sync(0xffffffffu, ok, 0)) continue;
+                }
+                const int tile_ = blockIdx.x * P::NG + g + k[sidx] * stride;
+                const int pt_ = rev ? ntiles - 1 - tile_ : tile_;
+                const int b_ = pt_ / ntx, t0_ = (pt_ - b_ * ntx) * UM_TT;
+                if (lane == 0) {
+                    // one box = all H channel rows x 128 steps of clip b_ (columns past l arrive as zeros and count as bytes)
+                    mbar_arrive_expect_tx(sb, P::STG);
+                    tma_load_2d(sm + P::OFF_STG + (2 * g + isg) * P::STG, isg ? &tm_g : &tm_x, t0_, b_ * H, sb);
+                }
+                ++k[sidx];
+            }
+        }
+    };
+
+    if (STAGE && !P::RESIDENT && warp == EPI_WARPS + P::NG + 1) {
+        stage_producer();
+    } else if (warp == EPI_WARPS + P::NG) {
         // ================= weight producer =====================================================
-        if (lane == 0) {
-            if (P::RESIDENT) {
+        if (P::RESIDENT) {
+            if (lane == 0)
                 for (int i = 0; i < C::NSTG; ++i) {
                     mbar_arrive_expect_tx(wfull + i, UM_STAGE);
                     bulk_g2s(wbuf + (size_t)i * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + i);
                 }
-            } else {
-                int cnt = 0;
-                for (int tile = blockIdx.x * P::NG; tile < ntiles; tile += stride)
-                    for (int i = 0; i < C::NSTG; ++i, ++cnt) {
-                        const int s = cnt % P::NS;
-                        mbar_wait(wempty + s, ((cnt / P::NS) & 1) ^ 1);
-                        mbar_arrive_expect_tx(wfull + s, UM_STAGE);
-                        bulk_g2s(wbuf + (size_t)s * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + s);
-                    }
-            }
+            __syncwarp();
+            if (STAGE) stage_producer();
+        } else if (lane == 0) {
+            int cnt = 0;
+            for (int tile = blockIdx.x * P::NG; tile < ntiles; tile += stride)
+                for (int i = 0; i < C::NSTG; ++i, ++cnt) {
+                    const int s = cnt % P::NS;
+                    mbar_wait(wempty + s, ((cnt / P::NS) & 1) ^ 1);
+                    mbar_arrive_expect_tx(wfull + s, UM_STAGE);
+                    bulk_g2s(wbuf + (size_t)s * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + s);
+                }
         }
+    } else if (warp >= EPI_WARPS + P::NG) {
+        // (staging warp of an instantiation without staging: nothing to do)
     } else if (warp >= EPI_WARPS) {
         // ================= MMA issuer of group grp ==============================================
         const int grp = warp - EPI_WARPS;
@@ -605,30 +677,18 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
             uint64_t *gb = bars + grp * P::NBAR_G;
             uint64_t *g_ready = gb, *z_ready = gb + 1, *hid_ready = gb + 2, *acc1_ready = hid_ready + C::KC3,
                      *acc2_ready = acc1_ready + C::NC1, *acc3_ready = acc2_ready + C::NC1;
-            const uint32_t slot0 = smem_u32(sm + P::OFF_SLOT + grp * C::NSLOT * UM_SLOT), w0 = smem_u32(wbuf);
+            const uint32_t w0 = smem_u32(wbuf);
             const uint32_t tmem = tmem0 + grp * P::GCOLS;
-            auto issue_block = [&](uint32_t d, uint32_t abase, uint32_t bbase, int NR, bool acc0) {
-                const uint32_t idesc = idesc_bf16(128, NR);
-#pragma unroll
-                for (int term = 0; term < 3; ++term) {
-                    const uint32_t ao = abase + (term == 1 ? UM_SLOT / 2 : 0);
-                    const uint32_t bo = bbase + (term == 2 ? NR * 128 : 0);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_bf16_ss(d, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
-                                    (acc0 || term > 0 || ks > 0) ? 1u : 0u);
-                }
-            };
-            // G3 (TS form): the A operand is the hidden tile E2 left in TMEM over the accumulator columns it read:
-            // per 16 f-columns 8 packed hi columns then 8 packed lo columns = one K = 16 step each
-            auto issue_block_ts = [&](uint32_t d, uint32_t a_tmem, uint32_t bbase, int NR) {
+            // one [128 x NR] x K = 64 block, A operand in TMEM ([8 hi | 8 lo] columns per K = 16 step): 3 split terms x 4 k-steps
+            auto issue_block = [&](uint32_t d, uint32_t a_tmem, uint32_t bbase, int NR, bool acc0) {
                 const uint32_t idesc = idesc_bf16(128, NR);
 #pragma unroll
                 for (int term = 0; term < 3; ++term) {
                     const uint32_t ao = a_tmem + (term == 1 ? 8 : 0);
                     const uint32_t bo = bbase + (term == 2 ? NR * 128 : 0);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) mma_bf16_ts(d, ao + ks * 16, smem_desc_sw128(bo + ks * 32), idesc, 1u);
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_bf16_ts(d, ao + ks * 16, smem_desc_sw128(bo + ks * 32), idesc, (acc0 || term > 0 || ks > 0) ? 1u : 0u);
                 }
             };
             int cnt = 0;     // weight stages consumed so far (ring position when streaming)
@@ -647,7 +707,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
                             const int s = P::RESIDENT ? i : cnt % P::NS;
                             mbar_wait(wfull + s, P::RESIDENT ? 0u : (uint32_t)((cnt / P::NS) & 1));
                             tc_fence_after();
-                            issue_block(tmem + nc * 128, slot0 + kc * UM_SLOT, w0 + s * UM_STAGE, 128, kc > 0);
+                            issue_block(tmem + nc * 128, tmem + P::AOP + 64 * kc, w0 + s * UM_STAGE, 128, kc > 0);
                             if (!P::RESIDENT) mma_commit(wempty + s);
                         }
                         mma_commit((gemm == 0 ? acc1_ready : acc2_ready) + nc);
@@ -665,7 +725,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
                             mbar_wait(wfull + s, P::RESIDENT ? 0u : (uint32_t)((cnt / P::NS) & 1));
                             tc_fence_after();
                         }
-                        issue_block_ts(tmem + C::R3 + nc * 128, tmem + 64 * kc, w0 + s * UM_STAGE + (j % C::BPS3) * C::NR3 * 256, C::NR3);
+                        issue_block(tmem + P::R3 + nc * 128, tmem + 64 * kc, w0 + s * UM_STAGE + (j % C::BPS3) * C::NR3 * 256, C::NR3, true);
                         if (j % C::BPS3 == C::BPS3 - 1) {
                             if (!P::RESIDENT) mma_commit(wempty + s);
                             ++i;
@@ -678,16 +738,12 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
         }
     } else {
         // ================= epilogue threads of group grp =========================================
-        // Software pipeline across the tiles of a group: the next tile's g is requested before this tile's
-        // last accumulator is awaited and becomes the A operand of the next G1 as soon as G3 has released
-        // the operand slots, so G1(next) runs under E3(this); the next tile's x is requested before E3 and
-        // stays in registers until E1 (no TMEM staging).  x1 likewise stays in registers from E1 to LN2.
         const int grp = warp / P::GW, cg = (warp % P::GW) >> 2, q = warp & 3;
         const int r = 32 * q + lane;
         uint64_t *gb = bars + grp * P::NBAR_G;
         uint64_t *g_ready = gb, *z_ready = gb + 1, *hid_ready = gb + 2, *acc1_ready = hid_ready + C::KC3,
                  *acc2_ready = acc1_ready + C::NC1, *acc3_ready = acc2_ready + C::NC1;
-        uint8_t *slots = sm + P::OFF_SLOT + grp * C::NSLOT * UM_SLOT;
+        uint64_t *xfull = gb + P::NBAR_G - 4, *xempty = xfull + 1, *gfull = xfull + 2, *gempty = xfull + 3;
         const uint32_t tl = tmem0 + grp * P::GCOLS + ((uint32_t)(32 * q) << 16);
         const float *bo_s = bias_s, *b1_s = bias_s + 2 * H, *b2_s = bias_s + 4 * H;
         constexpr int PER = H / CS, PP = 64 / CS;
@@ -695,17 +751,18 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
         const bool tracer = trace && grp == 0 && etid == 0;
 #define PT(slot) do { if (tracer && it == 1) trace[slot] = clock64(); } while (0)
 
-        // statistics exchange between the CS column groups of a time step (partners share the TMEM lane)
-        auto exchange = [&](float &mean, float &M2) {
+        // statistics exchange between the CS column groups of a time step (partners share the TMEM lane) through
+        // a column of this thread's own range that it has already consumed
+        auto exchange = [&](uint32_t col, float &mean, float &M2) {
             if (CS > 1) {
-                tmem_st2(tl + P::XCOL + 2 * cg, mean, M2);
+                tmem_st2(tl + col + cg * (H / CS), mean, M2);
                 tmem_wait_st();
                 tc_fence_before();
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(P::EPI) : "memory");
                 tc_fence_after();
                 float pm[CS], p2[CS];
 #pragma unroll
-                for (int c = 0; c < CS; ++c) tmem_ld2(tl + P::XCOL + 2 * c, pm[c], p2[c]);
+                for (int c = 0; c < CS; ++c) tmem_ld2(tl + col + c * (H / CS), pm[c], p2[c]);
                 tmem_wait_ld();
                 float ms = 0.f;
 #pragma unroll
@@ -721,51 +778,73 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
                 M2 = m2;
             }
         };
-        // this thread's channels of a (B,H,l) tensor at tile `tl_`: g / skip / out use h = cg*PER + i,
-        // x uses the GLU pairing h = nc*64 + cg*PP + i (the columns E1 produces)
         auto tile_row = [&](int tile_, bool &valid_) -> size_t {
             const int pt_ = rev ? ntiles - 1 - tile_ : tile_;           // rev: walk the batch from its end (see mix_umma_launch)
             const int b_ = pt_ / ntx, t_ = (pt_ - b_ * ntx) * UM_TT + r;
             valid_ = tile_ < ntiles && t_ < l;
             return (size_t)b_ * H * l + (valid_ ? t_ : 0);
         };
-        auto load_g = [&](float (&gin)[PER], int tile_) {
+        // this thread's channels: g / skip / out use h = cg*PER + i; x uses the GLU pairing h = nc*64 + cg*PP + i
+        // (the columns E1 produces).  par = parity of the stream's transfer (the group's tile counter & 1).
+        const float *xb = reinterpret_cast<const float *>(sm + P::OFF_STG + (2 * grp) * P::STG) + r;
+        const float *gbuf = reinterpret_cast<const float *>(sm + P::OFF_STG + (2 * grp + 1) * P::STG) + r;
+        auto take_x = [&](float (&xin)[PER], int tile_, uint32_t par) {
+            bool v_;
+            const size_t row = tile_row(tile_, v_);
+            if (STAGE) {
+                mbar_wait(xfull, par);
+#pragma unroll
+                for (int nc = 0; nc < C::NC1; ++nc)
+#pragma unroll
+                    for (int i = 0; i < PP; ++i) xin[nc * PP + i] = v_ ? xb[(nc * 64 + cg * PP + i) * UM_TT] : 0.f;
+                mbar_arrive(xempty);
+            } else {
+                const float *xp = a.x + row + (size_t)cg * PP * l;
+#pragma unroll
+                for (int nc = 0; nc < C::NC1; ++nc)
+#pragma unroll
+                    for (int i = 0; i < PP; ++i) xin[nc * PP + i] = v_ ? __ldg(chan<LC>(xp, nc * 64 + i, l)) : 0.f;
+            }
+        };
+        auto load_g = [&](float (&gin)[PER], int tile_) {       // !STAGE: request only
             bool v_;
             const float *gp = a.g + tile_row(tile_, v_) + (size_t)cg * PER * l;
 #pragma unroll
             for (int i = 0; i < PER; ++i) gin[i] = v_ ? __ldg(chan<LC>(gp, i, l)) : 0.f;
         };
-        auto load_x = [&](float (&xin)[PER], int tile_) {
+        auto take_g = [&](float (&gin)[PER], int tile_, uint32_t par) {
             bool v_;
-            const float *xp = a.x + tile_row(tile_, v_) + (size_t)cg * PP * l;
+            tile_row(tile_, v_);
+            mbar_wait(gfull, par);
 #pragma unroll
-            for (int nc = 0; nc < C::NC1; ++nc)
-#pragma unroll
-                for (int i = 0; i < PP; ++i) xin[nc * PP + i] = v_ ? __ldg(chan<LC>(xp, nc * 64 + i, l)) : 0.f;
+            for (int i = 0; i < PER; ++i) gin[i] = v_ ? gbuf[(cg * PER + i) * UM_TT] : 0.f;
+            mbar_arrive(gempty);
+        };
+        // 16 channels starting at h0 -> the A operand columns of their K = 16 step: [8 packed hi | 8 packed lo]
+        auto store_aop = [&](const float *v, int h0) {
+            uint4 hi0, lo0, hi1, lo1;
+            split8p(v, hi0, lo0);
+            split8p(v + 8, hi1, lo1);
+            tmem_st8(tl + P::AOP + h0, hi0, hi1);
+            tmem_st8(tl + P::AOP + h0 + 8, lo0, lo1);
         };
         auto store_g = [&](const float (&gin)[PER]) {
 #pragma unroll
-            for (int c8 = 0; c8 < PER / 8; ++c8) {
-                const int h0 = cg * PER + c8 * 8;
-                uint4 hi, lo;
-                split8p(gin + 8 * c8, hi, lo);
-                uint8_t *slot = slots + (h0 >> 6) * UM_SLOT;
-                const uint32_t off = sw128_off(r, (h0 & 63) >> 3);
-                *reinterpret_cast<uint4 *>(slot + off) = hi;
-                *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
-            }
-            fence_proxy_async_smem();
+            for (int c = 0; c < PER / 16; ++c) store_aop(gin + 16 * c, cg * PER + 16 * c);
+            tmem_wait_st();
+            tc_fence_before();
             mbar_arrive(g_ready);
         };
 
         int tile = blockIdx.x * P::NG + grp;
         float xin[PER];                               // x of this tile, then x1 (E1 -> LN2)
-        {
+        if (tile < ntiles) {
             float gin[PER];
-            load_g(gin, tile);
-            load_x(xin, tile);
+            take_x(xin, tile, 0);
+            if (STAGE) take_g(gin, tile, 0);
+            else load_g(gin, tile);
             if (grp > 0 && stagger_ns > 0) __nanosleep(stagger_ns);     // start the groups out of phase
-            if (tile < ntiles) store_g(gin);
+            store_g(gin);
         }
         uint32_t ph = 0;
         int it = 0;
@@ -775,6 +854,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
             const int b = ptile / ntx, t = (ptile - b * ntx) * UM_TT + r;
             const bool valid = t < l;
             const size_t brow = (size_t)b * H * l + (valid ? t : 0);
+            const int nt = tile + stride;
             PT(0);
             // ---- E1: GLU + residual -> x1 (TMEM R3 for G3's accumulation, registers for LN2), LN2 statistics
             float mean, M2;
@@ -816,15 +896,15 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
                         }
                         if (nc == 0 && sc == 0) piv = xv[0];
                         stat_acc16(xv, s2::V2(piv), sd, sq);
-                        tmem_st16(tl + C::R3 + h0, xv);
+                        tmem_st16(tl + P::R3 + h0, xv);
                     }
                 }
                 stat_finish(sd, sq, piv, PER, mean, M2);
                 tmem_wait_st();
             }
             PT(2);
-            exchange(mean, M2);
-            // ---- z = LN2(x1), split, store as the A operand of G2
+            exchange(0, mean, M2);                // accumulator columns this thread has consumed (G2 has not been issued)
+            // ---- z = LN2(x1), split -> AOP: the A operand of G2 (G1 has completed: acc1 was awaited)
             {
                 const float rstd = valid ? rsqrtf(M2 * (1.0f / H)) : 0.f;
                 const float sc_a = a.ln2_s * rstd;
@@ -832,7 +912,6 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
 #pragma unroll
                 for (int k = 0; k < PER / 16; ++k) {
                     const int nc = k / (PP / 16), sc = k % (PP / 16);
-                    const int h0 = nc * 64 + cg * PP + sc * 16;
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 16; i += 2) {
@@ -840,23 +919,15 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
                         v[i] = z.v.x;
                         v[i + 1] = z.v.y;
                     }
-                    uint8_t *slot = slots + (h0 >> 6) * UM_SLOT;
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint4 hi, lo;
-                        split8p(v + 8 * hh, hi, lo);
-                        const uint32_t off = sw128_off(r, ((h0 & 63) >> 3) + hh);
-                        *reinterpret_cast<uint4 *>(slot + off) = hi;
-                        *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
-                    }
+                    store_aop(v, nc * 64 + cg * PP + sc * 16);
                 }
-                fence_proxy_async_smem();
+                tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(z_ready);
             }
-            const int nt = tile + stride;
+            if (STAGE && nt < ntiles) take_x(xin, nt, (uint32_t)((it + 1) & 1));      // x of the next tile (requested a tile ago)
             PT(3);
-            // ---- E2: hidden = gelu(W1 z + b1), split, store as the A operand of G3
+            // ---- E2: hidden = gelu(W1 z + b1), split, written in place over the accumulator columns as the A operand of G3
             {
                 constexpr int PERF = 128 / CS;
 #pragma unroll 1
@@ -866,9 +937,12 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
                     if (nc == 0) PT(4);
 #pragma unroll 1
                     for (int sc = 0; sc < PERF / 16; ++sc) {
-                        const int col = cg * PERF + sc * 16, f0 = nc * 128 + col;
+                        // a thread's columns are spread over both 64-wide K chunks of this N chunk, so the first chunk is
+                        // complete - and its part of G3 issued - when E2 is half way through the second
+                        constexpr int SPK = PERF / 32;             // 16-column steps per K chunk and thread
+                        const int col = (sc / SPK) * 64 + cg * (PERF / 2) + (sc % SPK) * 16, f0 = nc * 128 + col;
                         float v[16];
-                        tmem_ld16(tl + nc * 128 + col, v);
+                        tmem_ld16(tl + f0, v);
                         tmem_wait_ld();
                         const float *bb = b1_s + f0;
 #pragma unroll
@@ -881,9 +955,9 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
                         uint4 h0, l0, h1, l1;
                         split8p(v, h0, l0);
                         split8p(v + 8, h1, l1);
-                        tmem_st8(tl + f0, h0, h1);                 // in place: the 16 columns just read
+                        tmem_st8(tl + f0, h0, h1);
                         tmem_st8(tl + f0 + 8, l0, l1);
-                        if (((f0 + 16) & 63) == 0 || sc == PERF / 16 - 1) {
+                        if (sc % SPK == SPK - 1) {
                             tmem_wait_st();
                             tc_fence_before();
                             mbar_arrive(hid_ready + kc);
@@ -892,20 +966,25 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
                 }
             }
             PT(5);
-            // ---- the next tile's g goes in flight now; once G3 has released the operand slots it becomes the
-            //      A operand of G1(next), which then runs under E3
-            {
+            // ---- once G3 has been awaited the A operand columns are free: the next tile's g goes in and G1(next) runs under E3
+            if (STAGE) {
+                mbar_wait(acc3_ready, ph);
+                tc_fence_after();
+                PT(6);
+                if (nt < ntiles) {
+                    float gin[PER];
+                    take_g(gin, nt, (uint32_t)((it + 1) & 1));
+                    store_g(gin);
+                }
+            } else {
                 float gin[PER];
                 load_g(gin, nt);
                 mbar_wait(acc3_ready, ph);
                 tc_fence_after();
                 PT(6);
                 if (nt < ntiles) store_g(gin);
+                take_x(xin, nt, 0);               // requested here, lands during E3
             }
-            // x of the next tile: requested here, lands during E3, consumed by E1 of the next tile (a request before E2
-            // measured slower: the burst of loads blocks the issuing warps until the memory pipeline accepts it, and
-            // here the other group's E2 and this group's G1(next) fill that time)
-            load_x(xin, nt);
             PT(7);
             // ---- E3: x2 = acc3 (= x1 + W2 hidden) + b2 (+skip); store; statistics for the next norm
             {
@@ -917,7 +996,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
                 for (int sc = 0; sc < PER / 16; ++sc) {
                     const int h0 = cg * PER + sc * 16;
                     float v[16];
-                    tmem_ld16(tl + C::R3 + h0, v);
+                    tmem_ld16(tl + P::R3 + h0, v);
                     const float *bb = b2_s + h0;
                     if (sp) {
                         float sk[16];
@@ -947,7 +1026,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev) {
                     stat_acc16(v, s2::V2(piv), sd, sq);
                 }
                 stat_finish(sd, sq, piv, PER, mean, M2);
-                exchange(mean, M2);
+                exchange(P::R3, mean, M2);        // x2 columns this thread has read (the next E1 rewrites them later)
                 if (cg == 0 && valid)
                     *reinterpret_cast<float2 *>(a.stats_out + ((size_t)b * l + t) * 2) = make_float2(mean, rsqrtf(M2 * (1.0f / H)));
             }
@@ -1483,10 +1562,34 @@ static int launch_umma(const MixArgs &a, int B, cudaStream_t st) {
     return DWB_OK;
 }
 
+// tensor map of a row-major (rows, cols) fp32 matrix for boxes of [box_rows x box_cols] (dense rows in shared memory).
+// The driver entry point is resolved through the runtime, so libdwb.so does not link libcuda.
+static int make_tmap_rows(CUtensorMap *tm, const float *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return (EncodeFn)fn;
+    }();
+    DWB_REQUIRE(encode, DWB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[2] = {cols, rows}, gstride[1] = {cols * sizeof(float)};
+    const cuuint32_t box[2] = {box_cols, box_rows}, estr[2] = {1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DWB_REQUIRE(r == CUDA_SUCCESS, DWB_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows %llu, cols %llu)", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols);
+    return DWB_OK;
+}
+
 template <int H, int CS, int LC>
 static int launch_umma_pers(const MixArgs &a, int B, cudaStream_t st) {
     using P = PCfg<H, CS>;
-    auto k = sashimi_mix_umma_pers_kernel<H, CS, LC>;
+    auto k = sashimi_mix_umma_pers_kernel<H, CS, LC, (LC != 0)>;      // the BASELINE lengths take their inputs through bulk copies
     static int sms[16] = {};
     int dev = 0;
     DWB_CUDA(cudaGetDevice(&dev));
@@ -1497,13 +1600,24 @@ static int launch_umma_pers(const MixArgs &a, int B, cudaStream_t st) {
     const int ntiles = B * ceil_div(a.l, UM_TT);
     const int grid = std::min(sms[dev & 15], ceil_div(ntiles, P::NG));
     static const int stagger = [] { const char *e = getenv("DWB_UMMA_STAGGER"); return e ? atoi(e) : 0; }();
-    k<<<grid, P::NTHREADS, P::SMEM, st>>>(a, B, stagger, mix_reverse_order() ? 1 : 0);
+    CUtensorMap tm_x, tm_g;
+    memset(&tm_x, 0, sizeof(tm_x));
+    memset(&tm_g, 0, sizeof(tm_g));
+    if (LC != 0) {      // staged inputs: (B*H, l) fp32 row-major, boxes of [H rows x 128 steps]
+        int rc = make_tmap_rows(&tm_x, a.x, (uint64_t)B * H, (uint64_t)a.l, H, UM_TT);
+        if (rc == DWB_OK) rc = make_tmap_rows(&tm_g, a.g, (uint64_t)B * H, (uint64_t)a.l, H, UM_TT);
+        if (rc != DWB_OK) return rc;
+    }
+    k<<<grid, P::NTHREADS, P::SMEM, st>>>(a, B, stagger, mix_reverse_order() ? 1 : 0, tm_x, tm_g);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
 }
 // the stage lengths of the BASELINE configs get a compile-time channel stride (LC), every other length the generic kernel
 template <int H, int CS>
 static int launch_umma_pers_l(const MixArgs &a, int B, cudaStream_t st) {
+    static const bool nostage = [] { const char *e = getenv("DWB_UMMA_STAGE"); return e && atoi(e) == 0; }();
+    // bulk copies need 16-byte aligned rows: l % 4 == 0 (true for the lengths below) and aligned base pointers
+    if (nostage || ((reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.x)) & 15)) return launch_umma_pers<H, CS, 0>(a, B, st);
     switch (a.l) {
         case 16000: return launch_umma_pers<H, CS, 16000>(a, B, st);
         case 4000: return launch_umma_pers<H, CS, 4000>(a, B, st);
@@ -1526,9 +1640,9 @@ int mix_umma_launch(const MixArgs &a_in, int B, cudaStream_t st) {
     DWB_REQUIRE(a.Wimg && a.bimg, DWB_ERR_STATE, "mix_umma: weights were not packed");
     DWB_REQUIRE((int64_t)a.H * a.l < (int64_t)1 << 31, DWB_ERR_UNSUPPORTED, "mix_umma: H*l = %lld needs 64-bit channel offsets",
                 (long long)a.H * a.l);
-    // measured (B200, unet d64, B = 32): H = 64 is fastest as two per-tile CTAs per SM (2.53 ms per forward vs
-    // 2.72 persistent); H = 128 fits one tile per SM either way and gains from the persistent loop (1.65 vs 1.71).
-    // DWB_UMMA=tile / pers forces one variant for both widths.
+    // The persistent kernel is the default for H = 64 and H = 128 at every batch size (round 2, B = 64: 243 / 167 us per
+    // launch against 370 / 229 us for the per-tile kernel); DWB_UMMA=tile forces the per-tile form, which keeps its
+    // operands in shared memory and serves as the second implementation in the variant tests.
     static const int mode = [] {
         const char *e = getenv("DWB_UMMA");
         return !e ? 0 : (std::string(e) == "tile" ? 1 : (std::string(e) == "pers" ? 2 : 0));
@@ -1540,13 +1654,10 @@ int mix_umma_launch(const MixArgs &a_in, int B, cudaStream_t st) {
         DWB_LAUNCH_CHECK();
         return DWB_OK;
     }
-    // round 2, B = 64 (8000 tiles at H = 64): per-tile 370 us, persistent 337 us - the per-CTA setup (TMEM allocation
-    // against the co-resident CTA, barrier init, bias staging: 3.1 K of 21.7 K cycles per tile) stops paying for itself
-    const bool pers = mode == 2 || (mode == 0 && (a.H == 128 || (int64_t)B * ceil_div(a.l, UM_TT) >= 6000));
-    static const bool cs4 = [] { const char *e = getenv("DWB_UMMA_CS"); return e && atoi(e) == 4; }();
+    const bool pers = mode != 1;
     if (pers) switch (a.H) {
         case 64: return launch_umma_pers_l<64, 2>(a, B, st);
-        case 128: return cs4 ? launch_umma_pers_l<128, 4>(a, B, st) : launch_umma_pers_l<128, 2>(a, B, st);
+        case 128: return launch_umma_pers_l<128, 2>(a, B, st);
     }
     switch (a.H) {
         case 64: return launch_umma<64, 2>(a, B, st);
