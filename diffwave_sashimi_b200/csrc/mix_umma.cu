@@ -812,14 +812,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
 #pragma unroll
             for (int i = 0; i < PER; ++i) gin[i] = v_ ? __ldg(chan<LC>(gp, i, l)) : 0.f;
         };
-        auto take_g = [&](float (&gin)[PER], int tile_, uint32_t par) {
-            bool v_;
-            tile_row(tile_, v_);
-            mbar_wait(gfull, par);
-#pragma unroll
-            for (int i = 0; i < PER; ++i) gin[i] = v_ ? gbuf[(cg * PER + i) * UM_TT] : 0.f;
-            mbar_arrive(gempty);
-        };
+
         // 16 channels starting at h0 -> the A operand columns of their K = 16 step: [8 packed hi | 8 packed lo]
         auto store_aop = [&](const float *v, int h0) {
             uint4 hi0, lo0, hi1, lo1;
@@ -827,6 +820,23 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
             split8p(v + 8, hi1, lo1);
             tmem_st8(tl + P::AOP + h0, hi0, hi1);
             tmem_st8(tl + P::AOP + h0 + 8, lo0, lo1);
+        };
+        // staged g tile -> A operand of G1, 16 channels at a time (keeps the live registers low next to the skip prefetch)
+        auto take_store_g = [&](int tile_, uint32_t par) {
+            bool v_;
+            tile_row(tile_, v_);
+            mbar_wait(gfull, par);
+#pragma unroll
+            for (int c = 0; c < PER / 16; ++c) {
+                float gin[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) gin[i] = v_ ? gbuf[(cg * PER + 16 * c + i) * UM_TT] : 0.f;
+                store_aop(gin, cg * PER + 16 * c);
+            }
+            mbar_arrive(gempty);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(g_ready);
         };
         auto store_g = [&](const float (&gin)[PER]) {
 #pragma unroll
@@ -839,12 +849,15 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
         int tile = blockIdx.x * P::NG + grp;
         float xin[PER];                               // x of this tile, then x1 (E1 -> LN2)
         if (tile < ntiles) {
-            float gin[PER];
-            take_x(xin, tile, 0);
-            if (STAGE) take_g(gin, tile, 0);
-            else load_g(gin, tile);
             if (grp > 0 && stagger_ns > 0) __nanosleep(stagger_ns);     // start the groups out of phase
-            store_g(gin);
+            if (STAGE) {
+                take_store_g(tile, 0);
+            } else {
+                float gin[PER];
+                take_x(xin, tile, 0);
+                load_g(gin, tile);
+                store_g(gin);
+            }
         }
         uint32_t ph = 0;
         int it = 0;
@@ -855,6 +868,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
             const bool valid = t < l;
             const size_t brow = (size_t)b * H * l + (valid ? t : 0);
             const int nt = tile + stride;
+            if (STAGE) take_x(xin, tile, (uint32_t)(it & 1));      // staged a tile ago; x is not live across E2 / E3
             PT(0);
             // ---- E1: GLU + residual -> x1 (TMEM R3 for G3's accumulation, registers for LN2), LN2 statistics
             float mean, M2;
@@ -925,7 +939,6 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
                 tc_fence_before();
                 mbar_arrive(z_ready);
             }
-            if (STAGE && nt < ntiles) take_x(xin, nt, (uint32_t)((it + 1) & 1));      // x of the next tile (requested a tile ago)
             PT(3);
             // ---- E2: hidden = gelu(W1 z + b1), split, written in place over the accumulator columns as the A operand of G3
             {
@@ -967,15 +980,17 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
             }
             PT(5);
             // ---- once G3 has been awaited the A operand columns are free: the next tile's g goes in and G1(next) runs under E3
+            float sk[STAGE ? PER : 1];            // the UNet skip of this tile: requested before the wait for G3, added in E3
+            const float *sp = a.skip ? a.skip + brow + (size_t)cg * PER * l : nullptr;
             if (STAGE) {
+                if (sp) {
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) sk[i] = valid ? __ldg(chan<LC>(sp, i, l)) : 0.f;
+                }
                 mbar_wait(acc3_ready, ph);
                 tc_fence_after();
                 PT(6);
-                if (nt < ntiles) {
-                    float gin[PER];
-                    take_g(gin, nt, (uint32_t)((it + 1) & 1));
-                    store_g(gin);
-                }
+                if (nt < ntiles) take_store_g(nt, (uint32_t)((it + 1) & 1));
             } else {
                 float gin[PER];
                 load_g(gin, nt);
@@ -991,21 +1006,23 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
                 s2::V2 sd(0.f), sq(0.f);
                 float piv = 0.f;
                 float *op = a.out + brow + (size_t)cg * PER * l;
-                const float *sp = a.skip ? a.skip + brow + (size_t)cg * PER * l : nullptr;
-#pragma unroll 1
+#pragma unroll
                 for (int sc = 0; sc < PER / 16; ++sc) {
                     const int h0 = cg * PER + sc * 16;
                     float v[16];
                     tmem_ld16(tl + P::R3 + h0, v);
                     const float *bb = b2_s + h0;
                     if (sp) {
-                        float sk[16];
+                        float skl[16];
+                        if (!STAGE) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) sk[i] = valid ? __ldg(chan<LC>(sp, sc * 16 + i, l)) : 0.f;
+                            for (int i = 0; i < 16; ++i) skl[i] = valid ? __ldg(chan<LC>(sp, sc * 16 + i, l)) : 0.f;
+                        }
                         tmem_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
-                            const s2::V2 y = (s2::V2(v[i], v[i + 1]) + s2::V2(bb[i], bb[i + 1])) + s2::V2(sk[i], sk[i + 1]);
+                            const s2::V2 kk = STAGE ? s2::V2(sk[(sc * 16 + i) % (STAGE ? PER : 1)], sk[(sc * 16 + i + 1) % (STAGE ? PER : 1)]) : s2::V2(skl[i], skl[i + 1]);
+                            const s2::V2 y = (s2::V2(v[i], v[i + 1]) + s2::V2(bb[i], bb[i + 1])) + kk;
                             v[i] = y.v.x;
                             v[i + 1] = y.v.y;
                         }
