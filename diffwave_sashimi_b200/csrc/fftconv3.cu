@@ -13,6 +13,10 @@
 // models/sashimi.py:148-152 (norm1 + fc_t).  Requires l % 4 == 0 and 16-byte aligned rows.
 #include <stdint.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "fft_plan.cuh"
 #include "fft_radix.cuh"
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(Fft3Cfg<LOG2M>::NT, Fft3Cfg<LOG2M>::MINB)
 fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
                 long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
                 const float2 *__restrict__ tw /* W_n^i, i < M */, const float2 *__restrict__ tw2, float *g, float *scratch, int B, int H,
-                int l, int resident) {
+                int l, int resident, int stagger_ns) {
     using Cfg = Fft3Cfg<LOG2M>;
     constexpr int LH = Cfg::LH, Mh = Cfg::Mh, NT = Cfg::NT, NP = Cfg::NP, RL = Cfg::RL;
     constexpr int log2sub0 = LH - 4, sub0 = 1 << log2sub0;         // outer pass: radix 16, span Mh
@@ -220,18 +224,10 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
     float *twBr = twAi + Cfg::NTW0, *twBi = twBr + Cfg::NTW0;      // W_M^j
     float *midr = twBi + Cfg::NTW0, *midi = midr + Cfg::NMID;
     const int tid = threadIdx.x;
-    const int row = blockIdx.x;
-    const int h = row / B, b = row - h * B;
-    const size_t off = ((size_t)b * H + h) * (size_t)l;
-    const float4 *xr4 = reinterpret_cast<const float4 *>(x + off);
-    float *gr = g + off;
-    float *ys = scratch ? scratch + off : nullptr;               // parks the LN-applied input for the odd half
-    const float pt = part_t ? part_t[(size_t)b * part_stride_b + h] : 0.f;
-    const float4 *st4 = stats ? reinterpret_cast<const float4 *>(stats + (size_t)b * l * 2) : nullptr;
-    const float4 *kcr = kc + (size_t)h * (2 * Mh + 2);             // (Mh + 1) entries of two float4
-    const float lns = st4 ? ln_s : 1.f, lnm = st4 ? ln_m : 0.f;
+    const float lns = stats ? ln_s : 1.f, lnm = stats ? ln_m : 0.f;
     const int half = l >> 1;                                       // complex entries of the packed row (even)
 
+    // twiddle tables: once per CTA (the grid is persistent: a CTA walks rows blockIdx.x, + gridDim.x, ...)
     for (int j = tid; j < Cfg::NTW0; j += NT) {
         const float2 a = tw[4 * j], bb = tw[2 * j];
         twAr[j] = a.x;
@@ -257,11 +253,25 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
     const int j0 = 2 * tid;                                         // outer-pass butterflies j0, j0 + 1
     const int pb0 = padf(j0);
 
+    // persistent grid: the second CTA of an SM starts half a row period late, so that the memory phases of one
+    // (prologue, parked rows, epilogue) fall into the arithmetic phases of the other
+    if (stagger_ns > 0 && blockIdx.x >= gridDim.x / 2)
+        for (int t = 0; t < stagger_ns; t += 1000) __nanosleep(1000);
+#pragma unroll 1
+    for (int row = blockIdx.x; row < B * H; row += gridDim.x) {
+    const int h = row / B, b = row - h * B;
+    const size_t off = ((size_t)b * H + h) * (size_t)l;
+    const float4 *xr4 = reinterpret_cast<const float4 *>(x + off);
+    float *gr = g + off;
+    float *ys = scratch ? scratch + off : nullptr;               // parks the LN-applied input for the odd half
+    const float pt = part_t ? part_t[(size_t)b * part_stride_b + h] : 0.f;
+    const float4 *st4 = stats ? reinterpret_cast<const float4 *>(stats + (size_t)b * l * 2) : nullptr;
+    const float4 *kcr = kc + (size_t)h * (2 * Mh + 2);             // (Mh + 1) entries of two float4
 #pragma unroll 1
     for (int odd = 0; odd < 2; ++odd) {
         if (odd) {
-            // warm L2 with the input row of the CTA that will run two waves from now (rows are dispatched in
-            // order, two per SM): its outer pass then waits for L2 instead of HBM
+            // warm L2 with the row this CTA (persistent grid) or the CTA two waves from now (one row per CTA) takes next:
+            // its outer pass then waits for L2 instead of HBM
             const int nrow = row + resident;
             if (nrow < B * H) {
                 const int nh = nrow / B, nb = nrow - nh * B;
@@ -440,6 +450,7 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
             }
         }
         __syncthreads();          // the next half overwrites the planes
+    }
     }
 }
 
@@ -666,8 +677,15 @@ static int launch_fftconv3(const float *x, const float *stats, const float *part
     }
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    fftconv3_kernel<LOG2M, COMPACT><<<dim3(B * H, 1, 1), Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw,
-                                                                                 tw2, g, scratch, B, H, l, nsm * Cfg::MINB);
+    // One CTA per row by default.  DWB_FFT_PERS=1 launches a persistent grid instead (one CTA per resident slot walks rows
+    // slot, slot + grid, ...; twiddle tables built once per CTA): measured SLOWER on B200 at B = 64, 549 us against 504 us,
+    // with or without a half-period start offset between the two CTAs of an SM (DWB_FFT_STAGGER, ns) - the hardware's
+    // dynamic CTA dispatch keeps the rows in flight a contiguous window of one or two channels' tables.
+    static const bool pers = [] { const char *e = getenv("DWB_FFT_PERS"); return e && atoi(e) == 1; }();
+    static const int stagger = [] { const char *e = getenv("DWB_FFT_STAGGER"); return e ? atoi(e) : 0; }();
+    const int resident = nsm * Cfg::MINB, grid = pers ? std::min(B * H, resident) : B * H;
+    fftconv3_kernel<LOG2M, COMPACT><<<dim3(grid, 1, 1), Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw,
+                                                                               tw2, g, scratch, B, H, l, resident, pers ? stagger : 0);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
 }
