@@ -209,5 +209,17 @@ __device__ __forceinline__ V2 sigmoid_fast2(const V2 &x) {
     return V2(r0, r1);
 }
 
+// sigmoid of a gate whose bias arrives pre-multiplied by -log2(e):  1 / (1 + 2^(-log2e x + bs))
+__device__ __forceinline__ V2 sigmoid_scaled2(const V2 &x, const V2 &bs) {
+    const V2 ea = fma(x, V2(-1.4426950408889634f), bs);
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(ea.v.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(ea.v.y));
+    const V2 d = V2(e0, e1) + V2(1.0f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.v.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.v.y));
+    return V2(r0, r1);
+}
+
 }  // namespace s2
 }  // namespace dwb

@@ -338,7 +338,7 @@ sashimi_mix_umma_kernel(MixArgs a) {
                     for (int i = 0; i < 16; i += 2) {
                         // two channels per packed instruction (FADD2 / FMUL2 / FFMA2)
                         s2::V2 y = (s2::V2(av[i], av[i + 1]) + s2::V2(ba[i], ba[i + 1])) *
-                                   s2::sigmoid_fast2(s2::V2(gv[i], gv[i + 1]) + s2::V2(ba[64 + i], ba[64 + i + 1]));
+                                   s2::sigmoid_scaled2(s2::V2(gv[i], gv[i + 1]), s2::V2(ba[64 + i], ba[64 + i + 1]));
                         y = y + s2::V2(xv[i], xv[i + 1]);
                         xv[i] = y.v.x;
                         xv[i + 1] = y.v.y;
@@ -540,6 +540,9 @@ struct PCfg {
     // with resident weights the weight producer is idle after its first copies and stages the inputs itself
     static constexpr int NTHREADS = NG * EPI + NG * 32 + 32 + (RESIDENT ? 0 : 32);
     static constexpr int NS = RESIDENT ? U::NSTG : 2;          // weight buffers (RESIDENT: one per stage)
+    // biases in shared memory.  (H = 128 measured with a third ring stage in their place and the biases through L1:
+    // 191 us against 167 us - the uniform bias loads sit on the epilogues' critical path.)
+    static constexpr bool BIAS_SMEM = true;
     static constexpr int GCOLS = 512 / NG;                     // TMEM columns per group
     static constexpr int R3 = 2 * H, AOP = 3 * H;
     static constexpr int STG = H * 512;                        // one staged fp32 [H x 128] tile
@@ -548,7 +551,7 @@ struct PCfg {
     static constexpr int OFF_STG = 0;
     static constexpr int OFF_W = OFF_STG + NG * 2 * STG;
     static constexpr int OFF_BIAS = OFF_W + NS * UM_STAGE;
-    static constexpr int OFF_BAR = OFF_BIAS + 5 * H * 4;
+    static constexpr int OFF_BAR = OFF_BIAS + (BIAS_SMEM ? 5 * H * 4 : 0);
     static constexpr int OFF_TPTR = OFF_BAR + NBAR * 8;
     static constexpr int SMEM = OFF_TPTR + 16 + 1024;
     static_assert(4 * H <= GCOLS, "TMEM budget: accumulator (2H) + x1 (H) + A operand (H) columns per group");
@@ -593,10 +596,10 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
         }
         fence_mbar_init();
     }
-    // biases: bo' (2H; per 128: 64 value | 64 gate) b1 (F) b2 (H); the gate biases pre-multiplied by -log2(e)
-    // so that the sigmoid's exponent is one FFMA2 of the accumulator
-    for (int i = tid; i < 5 * H; i += P::NTHREADS)
-        bias_s[i] = a.bimg[i] * ((i < 2 * H && (i & 64)) ? -1.4426950408889634f : 1.0f);
+    // biases: bo' (2H; per 128: 64 value | 64 gate pre-multiplied by -log2 e) b1 (F) b2 (H): in shared memory next to resident
+    // weights; with streamed weights the space goes to a third ring stage and the biases come through L1
+    if (P::BIAS_SMEM)
+        for (int i = tid; i < 5 * H; i += P::NTHREADS) bias_s[i] = a.bimg[i];
     constexpr int EPI_WARPS = P::NG * P::GW;
     if (warp == EPI_WARPS) tmem_alloc(tptr, 512);
     tc_fence_before();
@@ -745,7 +748,8 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
                  *acc2_ready = acc1_ready + C::NC1, *acc3_ready = acc2_ready + C::NC1;
         uint64_t *xfull = gb + P::NBAR_G - 4, *xempty = xfull + 1, *gfull = xfull + 2, *gempty = xfull + 3;
         const uint32_t tl = tmem0 + grp * P::GCOLS + ((uint32_t)(32 * q) << 16);
-        const float *bo_s = bias_s, *b1_s = bias_s + 2 * H, *b2_s = bias_s + 4 * H;
+        const float *bsrc = P::BIAS_SMEM ? bias_s : a.bimg;
+        const float *bo_s = bsrc, *b1_s = bsrc + 2 * H, *b2_s = bsrc + 4 * H;
         constexpr int PER = H / CS, PP = 64 / CS;
         const int etid = tid - grp * P::EPI;         // thread index inside the group
         const bool tracer = trace && grp == 0 && etid == 0;
@@ -892,14 +896,8 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
                             // two channels per packed instruction: sigmoid(gate) = 1 / (1 + 2^(-log2e gate - log2e b))
-                            const s2::V2 ea = s2::fma(s2::V2(gv[i], gv[i + 1]), s2::V2(-1.4426950408889634f), s2::V2(ba[64 + i], ba[64 + i + 1]));
-                            float e0, e1, r0, r1;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(ea.v.x));
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(ea.v.y));
-                            const s2::V2 dn = s2::V2(e0, e1) + s2::V2(1.0f);
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(dn.v.x));
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(dn.v.y));
-                            const s2::V2 y = s2::fma(s2::V2(av[i], av[i + 1]) + s2::V2(ba[i], ba[i + 1]), s2::V2(r0, r1), s2::V2(xv[i], xv[i + 1]));
+                            const s2::V2 sg = s2::sigmoid_scaled2(s2::V2(gv[i], gv[i + 1]), s2::V2(ba[64 + i], ba[64 + i + 1]));
+                            const s2::V2 y = s2::fma(s2::V2(av[i], av[i + 1]) + s2::V2(ba[i], ba[i + 1]), sg, s2::V2(xv[i], xv[i + 1]));
                             xv[i] = y.v.x;
                             xv[i + 1] = y.v.y;
                         }
@@ -1062,25 +1060,27 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
 // =========================================================================================
 // H = 256 (F = 512): the operands of one 128-step tile no longer fit the per-tile scheme
 // (z alone is 128 KB, the weights 1.5 MB).  Same orientation and epilogues, but
-//   * G1/G2 run in N chunks of 128 columns through ONE accumulator region R1 (the MMA issuer waits
-//     for the epilogue to drain it: r1a/r1b barriers),
-//   * the hidden activations never touch shared memory: the epilogue writes them (split bf16,
-//     packed pairs) straight into TMEM and G3 takes its A operand from there (tcgen05.mma TS form),
-//     double-buffered per 64-wide K chunk (HBUF 0/1, released by tcgen05.commit),
-//   * biases come through L1 (uniform __ldg), the column-group statistics exchange through idle
-//     HBUF columns, so shared memory holds only z (4 slots) and a 3-stage weight ring.
-// TMEM: [0,256) x1 / acc3 | [256,384) R1 | [384,448) HBUF0 | [448,512) HBUF1.
+//   * G1/G2 run in N chunks of 128 columns through TWO accumulator regions R1a / R1b used alternately, so the
+//     epilogue of chunk n (GLU, or GELU + split) runs under the MMAs of chunk n + 1,
+//   * the hidden activations never touch shared memory: E2 writes them (split bf16, per 16 f-columns 8 packed
+//     hi columns then 8 packed lo columns) in place over the accumulator columns it has just read, and G3
+//     takes its A operand from there (tcgen05.mma TS form).  The tensor pipe executes in issue order, so the
+//     G2 chunk that next overwrites a region is simply issued after the G3 blocks that read it,
+//   * biases come through L1 (uniform __ldg), the column-group statistics exchange through idle R1a columns,
+//     so shared memory holds only g / z (4 slots) and a 3-stage weight ring.
+// TMEM: [0,256) x1 / acc3 | [256,384) R1a | [384,512) R1b.
 // Weight image = 48 stages of 32 KB in consumption order:
 //   G1 (nc, kc) x16 | G2(0) x4 | for nc = 0..3: { G2(nc+1) x4 (nc < 3) | G3(2nc) x2 | G3(2nc+1) x2 }.
 // =========================================================================================
 struct U256 {
-    static constexpr int H = 256, F = 512, CS = 2, EPI = 256, NTHREADS = EPI + 64;
+    static constexpr int H = 256, F = 512;
     static constexpr int NC1 = 4, KC1 = 4, KC3 = 8, NB3 = 2, NSTG = 48, NS = 3, NSLOT = 4;
-    static constexpr int R3 = 0, R1 = 256, HBUF = 384;
+    static constexpr int R3 = 0, R1 = 256;
+    __host__ __device__ static constexpr int r1(int nc) { return R1 + 128 * (nc & 1); }
     static constexpr int OFF_SLOT = 0;
     static constexpr int OFF_RING = NSLOT * UM_SLOT;
     static constexpr int OFF_BAR = OFF_RING + NS * UM_STAGE;
-    static constexpr int NBAR = 2 * NS + 2 + 2 + KC3 + 2 + 2 * NC1 + 1;
+    static constexpr int NBAR = 2 * NS + 2 + 2 + KC3 + 2 * NC1 + 1;
     static constexpr int OFF_TPTR = OFF_BAR + NBAR * 8;
     static constexpr int SMEM = OFF_TPTR + 16 + 1024;
     static constexpr size_t IMG_BYTES = (size_t)NSTG * UM_STAGE;
@@ -1101,18 +1101,21 @@ struct U256 {
     }
 };
 
-__global__ void __launch_bounds__(U256::NTHREADS, 1)
+// CS = epilogue threads per time step (2 or 4): each owns 64 / CS GLU pairs of every 64-channel block
+template <int CS>
+__global__ void __launch_bounds__(128 * CS + 64, 1)
 sashimi_mix_umma256_kernel(MixArgs a) {
     using C = U256;
-    constexpr int H = C::H;
+    constexpr int H = C::H, EPI = 128 * CS, PP = 64 / CS, PER = H / CS, PERF = 128 / CS;
+    constexpr int PW = 4 * CS, MW = 4 * CS + 1;             // producer / MMA issuer warps
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *slots = sm + C::OFF_SLOT, *ring = sm + C::OFF_RING;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + C::OFF_BAR);
     uint32_t *tptr = reinterpret_cast<uint32_t *>(sm + C::OFF_TPTR);
-    uint64_t *wfull = bars, *wempty = wfull + C::NS, *g_ready = wempty + C::NS, *z_ready = g_ready + 1, *r1a = z_ready + 1,
-             *r1b = r1a + 1, *hid_ready = r1b + 1, *hfree = hid_ready + C::KC3, *acc1_ready = hfree + 2,
-             *acc2_ready = acc1_ready + C::NC1, *acc3_ready = acc2_ready + C::NC1;
+    uint64_t *wfull = bars, *wempty = wfull + C::NS, *g_ready = wempty + C::NS, *z_ready = g_ready + 1, *r1free = z_ready + 1,
+             *hid_ready = r1free + 2, *acc1_ready = hid_ready + C::KC3, *acc2_ready = acc1_ready + C::NC1,
+             *acc3_ready = acc2_ready + C::NC1;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = a.rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y, t0 = (a.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * UM_TT, l = a.l;
@@ -1121,23 +1124,21 @@ sashimi_mix_umma256_kernel(MixArgs a) {
             mbar_init(wfull + i, 1);
             mbar_init(wempty + i, 1);
         }
-        mbar_init(g_ready, C::EPI);
-        mbar_init(z_ready, C::EPI);
-        mbar_init(r1a, C::EPI);
-        mbar_init(r1b, C::EPI);
-        for (int i = 0; i < C::KC3; ++i) mbar_init(hid_ready + i, 128);
-        mbar_init(hfree, 1);
-        mbar_init(hfree + 1, 1);
+        mbar_init(g_ready, EPI);
+        mbar_init(z_ready, EPI);
+        mbar_init(r1free, EPI);
+        mbar_init(r1free + 1, EPI);
+        for (int i = 0; i < C::KC3; ++i) mbar_init(hid_ready + i, 64 * CS);
         for (int i = 0; i < 2 * C::NC1 + 1; ++i) mbar_init(acc1_ready + i, 1);
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc(tptr, 512);
+    if (warp == MW) tmem_alloc(tptr, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tptr;
 
-    if (warp == 8) {
+    if (warp == PW) {
         // ================= weight producer =====================================================
         if (lane == 0) {
             for (int i = 0; i < C::NSTG; ++i) {
@@ -1147,7 +1148,7 @@ sashimi_mix_umma256_kernel(MixArgs a) {
                 bulk_g2s(ring + (size_t)s * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + s);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == MW) {
         // ================= MMA issuer ==========================================================
         if (lane == 0) {
             const uint32_t slot0 = smem_u32(slots), ring0 = smem_u32(ring);
@@ -1163,8 +1164,8 @@ sashimi_mix_umma256_kernel(MixArgs a) {
                 mma_commit(wempty + (i % C::NS));
                 ++i;
             };
-            // D[R1] = A[slots, all K] x stage blocks (SS form)
-            auto gemm_ss = [&](uint64_t *ready) {
+            // D[R1(nc)] = A[slots, all K] x stage blocks (SS form)
+            auto gemm_ss = [&](int nc, uint64_t *ready) {
 #pragma unroll 1
                 for (int kc = 0; kc < C::KC1; ++kc) {
                     const uint32_t bbase = next_stage(), abase = slot0 + kc * UM_SLOT;
@@ -1173,49 +1174,45 @@ sashimi_mix_umma256_kernel(MixArgs a) {
                         const uint32_t ao = abase + (term == 1 ? UM_SLOT / 2 : 0), bo = bbase + (term == 2 ? UM_STAGE / 2 : 0);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            mma_bf16_ss(tmem + C::R1, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
+                            mma_bf16_ss(tmem + C::r1(nc), smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
                                         (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
                     }
                     done_stage();
                 }
                 mma_commit(ready);
             };
-            // R3[nb] += HBUF[kc & 1] x stage (TS form: A from TMEM)
+            // R3[nb] += hidden K chunk kc (in place in R1(kc / 2), columns 64 (kc & 1) ..) x stage (TS form: A from TMEM)
             auto gemm_ts = [&](int kc) {
 #pragma unroll 1
                 for (int nb = 0; nb < C::NB3; ++nb) {
-                    const uint32_t bbase = next_stage(), abase = tmem + C::HBUF + 64 * (kc & 1);
+                    const uint32_t bbase = next_stage(), abase = tmem + C::r1(kc >> 1) + 64 * (kc & 1);
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {
-                        const uint32_t ao = abase + (term == 1 ? 32 : 0), bo = bbase + (term == 2 ? UM_STAGE / 2 : 0);
+                        const uint32_t ao = abase + (term == 1 ? 8 : 0), bo = bbase + (term == 2 ? UM_STAGE / 2 : 0);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            mma_bf16_ts(tmem + C::R3 + nb * 128, ao + ks * 8, smem_desc_sw128(bo + ks * 32), idesc, 1u);
+                            mma_bf16_ts(tmem + C::R3 + nb * 128, ao + ks * 16, smem_desc_sw128(bo + ks * 32), idesc, 1u);
                     }
                     done_stage();
                 }
-                mma_commit(hfree + (kc & 1));
             };
             mbar_wait(g_ready, 0);
             tc_fence_after();
 #pragma unroll 1
             for (int nc = 0; nc < C::NC1; ++nc) {
-                if (nc > 0) {
-                    mbar_wait(r1a, (nc - 1) & 1);
+                if (nc >= 2) {                            // E1 has drained this accumulator region (chunk nc - 2)
+                    mbar_wait(r1free + (nc & 1), 0);
                     tc_fence_after();
                 }
-                gemm_ss(acc1_ready + nc);
+                gemm_ss(nc, acc1_ready + nc);
             }
-            mbar_wait(z_ready, 0);
+            mbar_wait(z_ready, 0);                        // (every E1 chunk has been read: both regions are free)
             tc_fence_after();
-            gemm_ss(acc2_ready + 0);
+            gemm_ss(0, acc2_ready + 0);
 #pragma unroll 1
             for (int nc = 0; nc < C::NC1; ++nc) {
-                if (nc + 1 < C::NC1) {
-                    mbar_wait(r1b, nc & 1);
-                    tc_fence_after();
-                    gemm_ss(acc2_ready + nc + 1);
-                }
+                // region (nc + 1) & 1 held hidden chunk nc - 1: its G3 blocks were issued in the previous iteration
+                if (nc + 1 < C::NC1) gemm_ss(nc + 1, acc2_ready + nc + 1);
 #pragma unroll 1
                 for (int cg = 0; cg < 2; ++cg) {
                     mbar_wait(hid_ready + 2 * nc + cg, 0);
@@ -1233,26 +1230,27 @@ sashimi_mix_umma256_kernel(MixArgs a) {
         const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
         const size_t brow = (size_t)b * H * l + (valid ? t : 0);
         const float *bo_g = a.bimg, *b1_g = a.bimg + 2 * H, *b2_g = a.bimg + 4 * H;
-        // this thread's channels: h = nc * 64 + cg * 32 + i, nc < 4, i < 32 (the same set in every phase)
+        // this thread's channels: h = nc * 64 + cg * PP + i, nc < 4, i < PP (the same set in every phase)
+        constexpr int NCR = 64 / PP, NRD = PER / 64;        // 64-channel blocks per round of 64 loads, rounds
 
-        // ---- g -> slots (A operand of G1), two rounds of 64 loads in flight
+        // ---- g -> slots (A operand of G1), rounds of 64 loads in flight
 #pragma unroll 1
-        for (int rd = 0; rd < 2; ++rd) {
+        for (int rd = 0; rd < NRD; ++rd) {
             float v[64];
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const float *gp = a.g + brow + ((2 * rd + kk) * 64 + cg * 32) * l;
+            for (int kk = 0; kk < NCR; ++kk) {
+                const float *gp = a.g + brow + (size_t)((NCR * rd + kk) * 64 + cg * PP) * l;
 #pragma unroll
-                for (int i = 0; i < 32; ++i, gp += l) v[kk * 32 + i] = valid ? __ldg(gp) : 0.f;
+                for (int i = 0; i < PP; ++i) v[kk * PP + i] = valid ? __ldg(chan<0>(gp, i, l)) : 0.f;
             }
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                uint8_t *slot = slots + (2 * rd + kk) * UM_SLOT;
+            for (int kk = 0; kk < NCR; ++kk) {
+                uint8_t *slot = slots + (NCR * rd + kk) * UM_SLOT;
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
+                for (int c8 = 0; c8 < PP / 8; ++c8) {
                     uint4 hi, lo;
-                    split8(v + kk * 32 + 8 * c8, hi, lo);
-                    const uint32_t off = sw128_off(r, cg * 4 + c8);
+                    split8p(v + kk * PP + 8 * c8, hi, lo);
+                    const uint32_t off = sw128_off(r, cg * (PP / 8) + c8);
                     *reinterpret_cast<uint4 *>(slot + off) = hi;
                     *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
                 }
@@ -1262,97 +1260,115 @@ sashimi_mix_umma256_kernel(MixArgs a) {
         mbar_arrive(g_ready);
         // ---- x -> TMEM R3 while G1 runs
 #pragma unroll 1
-        for (int rd = 0; rd < 2; ++rd) {
+        for (int rd = 0; rd < NRD; ++rd) {
             float v[64];
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const float *xp = a.x + brow + ((2 * rd + kk) * 64 + cg * 32) * l;
+            for (int kk = 0; kk < NCR; ++kk) {
+                const float *xp = a.x + brow + (size_t)((NCR * rd + kk) * 64 + cg * PP) * l;
 #pragma unroll
-                for (int i = 0; i < 32; ++i, xp += l) v[kk * 32 + i] = valid ? __ldg(xp) : 0.f;
+                for (int i = 0; i < PP; ++i) v[kk * PP + i] = valid ? __ldg(chan<0>(xp, i, l)) : 0.f;
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float w[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) w[i] = v[c * 16 + i];
-                tmem_st16(tl + C::R3 + (2 * rd + c / 2) * 64 + cg * 32 + (c & 1) * 16, w);
+                tmem_st16(tl + C::R3 + (NCR * rd + (c * 16) / PP) * 64 + cg * PP + (c * 16) % PP, w);
             }
         }
         tmem_wait_st();
 
-        auto exchange = [&](float &mean, float &M2) {       // through HBUF columns (idle outside E2 / G3)
-            tmem_st2(tl + C::HBUF + 2 * cg, mean, M2);
+        auto exchange = [&](float &mean, float &M2) {       // through R1a columns (idle at both exchange points)
+            tmem_st2(tl + C::R1 + 2 * cg, mean, M2);
             tmem_wait_st();
             tc_fence_before();
-            asm volatile("bar.sync 1, %0;" ::"n"(C::EPI) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
             tc_fence_after();
-            float m0, s0, m1, s1;
-            tmem_ld2(tl + C::HBUF, m0, s0);
-            tmem_ld2(tl + C::HBUF + 2, m1, s1);
+            float pm[CS], p2[CS];
+#pragma unroll
+            for (int c = 0; c < CS; ++c) tmem_ld2(tl + C::R1 + 2 * c, pm[c], p2[c]);
             tmem_wait_ld();
-            const float mt = 0.5f * (m0 + m1), d0 = m0 - mt, d1 = m1 - mt;
+            float ms = 0.f;
+#pragma unroll
+            for (int c = 0; c < CS; ++c) ms += pm[c];
+            const float mt = ms * (1.0f / CS);
+            float m2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CS; ++c) {
+                const float d = pm[c] - mt;
+                m2 += p2[c] + d * d * (float)PER;
+            }
             mean = mt;
-            M2 = s0 + s1 + (d0 * d0 + d1 * d1) * (float)(H / 2);
+            M2 = m2;
         };
 
         // ---- E1: GLU + residual -> x1 (R3), LN2 statistics
-        float mean = 0.f, M2 = 0.f;
+        float mean, M2;
         {
-            int n = 0;
+            s2::V2 sd(0.f), sq(0.f);
+            float piv = 0.f;
 #pragma unroll 1
             for (int nc = 0; nc < C::NC1; ++nc) {
                 mbar_wait(acc1_ready + nc, 0);
                 tc_fence_after();
+                const uint32_t r1 = tl + C::r1(nc);
 #pragma unroll 1
-                for (int sc = 0; sc < 2; ++sc) {
-                    const int p0 = cg * 32 + sc * 16, h0 = nc * 64 + p0;
+                for (int sc = 0; sc < PP / 16; ++sc) {
+                    const int p0 = cg * PP + sc * 16, h0 = nc * 64 + p0;
                     float xv[16], av[16], gv[16];
-                    tmem_ld16(tl + C::R1 + p0, av);
-                    tmem_ld16(tl + C::R1 + 64 + p0, gv);
+                    tmem_ld16(r1 + p0, av);
+                    tmem_ld16(r1 + 64 + p0, gv);
                     tmem_ld16(tl + C::R3 + h0, xv);
                     tmem_wait_ld();
                     const float *ba = bo_g + nc * 128 + p0;
 #pragma unroll
                     for (int i = 0; i < 16; i += 2) {
                         // two channels per packed instruction (FADD2 / FMUL2 / FFMA2)
-                        s2::V2 y = (s2::V2(av[i], av[i + 1]) + s2::V2(__ldg(ba + i), __ldg(ba + i + 1))) *
-                                   s2::sigmoid_fast2(s2::V2(gv[i], gv[i + 1]) + s2::V2(__ldg(ba + 64 + i), __ldg(ba + 64 + i + 1)));
-                        y = y + s2::V2(xv[i], xv[i + 1]);
+                        const s2::V2 y = s2::fma(s2::V2(av[i], av[i + 1]) + s2::V2(__ldg(ba + i), __ldg(ba + i + 1)),
+                                                 s2::sigmoid_scaled2(s2::V2(gv[i], gv[i + 1]), s2::V2(__ldg(ba + 64 + i), __ldg(ba + 64 + i + 1))),
+                                                 s2::V2(xv[i], xv[i + 1]));
                         xv[i] = y.v.x;
                         xv[i + 1] = y.v.y;
-                        if (a.cond && valid) {
-                            xv[i] += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i) * l);
-                            xv[i + 1] += __ldg(a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (h0 + i + 1) * l);
-                        }
                     }
-                    stat_merge16(xv, n, mean, M2);
-                    n += 16;
+                    if (a.cond && valid) {
+                        const float *cp = a.cond + (size_t)(a.cond_stride_b ? b : 0) * H * l + t + (size_t)h0 * l;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) xv[i] += __ldg(chan<0>(cp, i, l));
+                    }
+                    if (nc == 0 && sc == 0) piv = xv[0];
+                    stat_acc16(xv, s2::V2(piv), sd, sq);
                     tmem_st16(tl + C::R3 + h0, xv);
                 }
                 tc_fence_before();
-                mbar_arrive(r1a);                       // R1 drained: the next N chunk may be issued
+                mbar_arrive(r1free + (nc & 1));         // this accumulator region is drained: chunk nc + 2 may be issued
             }
+            stat_finish(sd, sq, piv, PER, mean, M2);
             tmem_wait_st();
         }
         exchange(mean, M2);
         // ---- z = LN2(x1) -> slots (A operand of G2)
         {
             const float rstd = valid ? rsqrtf(M2 * (1.0f / H)) : 0.f;
-            const float sc_a = a.ln2_s * rstd, sh = a.ln2_m - mean;
+            const float sc_a = a.ln2_s * rstd;
+            const s2::V2 sc2(sc_a), sh2(sc_a * (a.ln2_m - mean));
 #pragma unroll 1
-            for (int k = 0; k < 8; ++k) {
-                const int nc = k >> 1, sc = k & 1;
-                const int h0 = nc * 64 + cg * 32 + sc * 16;
+            for (int k = 0; k < PER / 16; ++k) {
+                const int nc = k / (PP / 16), sc = k % (PP / 16);
+                const int h0 = nc * 64 + cg * PP + sc * 16;
                 float v[16];
                 tmem_ld16(tl + C::R3 + h0, v);
                 tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = sc_a * (v[i] + sh);
+                for (int i = 0; i < 16; i += 2) {
+                    const s2::V2 z = s2::fma(s2::V2(v[i], v[i + 1]), sc2, sh2);
+                    v[i] = z.v.x;
+                    v[i + 1] = z.v.y;
+                }
                 uint8_t *slot = slots + nc * UM_SLOT;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     uint4 hi, lo;
-                    split8(v + 8 * hh, hi, lo);
+                    split8p(v + 8 * hh, hi, lo);
                     const uint32_t off = sw128_off(r, ((h0 & 63) >> 3) + hh);
                     *reinterpret_cast<uint4 *>(slot + off) = hi;
                     *reinterpret_cast<uint4 *>(slot + UM_SLOT / 2 + off) = lo;
@@ -1362,71 +1378,78 @@ sashimi_mix_umma256_kernel(MixArgs a) {
             tc_fence_before();
             mbar_arrive(z_ready);
         }
-        // ---- E2: hidden = gelu(W1 z + b1) -> TMEM HBUF[cg] (A operand of G3, K chunk 2 nc + cg)
+        // ---- E2: hidden = gelu(W1 z + b1), split, in place over the accumulator columns (A operand of G3, K chunk 2 nc + cg)
 #pragma unroll 1
         for (int nc = 0; nc < C::NC1; ++nc) {
             mbar_wait(acc2_ready + nc, 0);
-            if (nc > 0) mbar_wait(hfree + cg, (nc - 1) & 1);       // G3 has consumed the previous contents
             tc_fence_after();
-            const uint32_t hb = tl + C::HBUF + 64 * cg;
+            const uint32_t r1 = tl + C::r1(nc);
 #pragma unroll 1
-            for (int sc = 0; sc < 4; ++sc) {
-                const int col = cg * 64 + sc * 16, f0 = nc * 128 + col;
+            for (int sc = 0; sc < PERF / 16; ++sc) {
+                const int col = cg * PERF + sc * 16, f0 = nc * 128 + col;
                 float v[16];
-                tmem_ld16(tl + C::R1 + col, v);
+                tmem_ld16(r1 + col, v);
                 tmem_wait_ld();
                 const float *bb = b1_g + f0;
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                        const s2::V2 r = s2::gelu_fast2(s2::V2(v[i], v[i + 1]) + s2::V2(__ldg(bb + i), __ldg(bb + i + 1)));
-                        v[i] = r.v.x;
-                        v[i + 1] = r.v.y;
-                    }
+                    const s2::V2 rr = s2::gelu_fast2(s2::V2(v[i], v[i + 1]) + s2::V2(__ldg(bb + i), __ldg(bb + i + 1)));
+                    v[i] = rr.v.x;
+                    v[i + 1] = rr.v.y;
+                }
                 uint4 h0, l0, h1, l1;
-                split8(v, h0, l0);
-                split8(v + 8, h1, l1);
-                tmem_st8(hb + sc * 8, h0, h1);
-                tmem_st8(hb + 32 + sc * 8, l0, l1);
+                split8p(v, h0, l0);
+                split8p(v + 8, h1, l1);
+                tmem_st8(r1 + col, h0, h1);
+                tmem_st8(r1 + col + 8, l0, l1);
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(hid_ready + 2 * nc + cg);
-            mbar_arrive(r1b);
+            mbar_arrive(hid_ready + 2 * nc + (cg * PERF) / 64);
         }
         // ---- E3: x2 = acc3 (= x1 + W2 hidden) + b2 (+skip); store; statistics for the next norm
         {
             mbar_wait(acc3_ready, 0);
             tc_fence_after();
-            int n = 0;
-            mean = 0.f;
-            M2 = 0.f;
+            s2::V2 sd(0.f), sq(0.f);
+            float piv = 0.f;
             float *op = a.out + brow;
 #pragma unroll 1
-            for (int k = 0; k < 8; ++k) {
-                const int h0 = (k >> 1) * 64 + cg * 32 + (k & 1) * 16;
+            for (int k = 0; k < PER / 16; ++k) {
+                const int h0 = (k / (PP / 16)) * 64 + cg * PP + (k % (PP / 16)) * 16;
                 float v[16];
                 tmem_ld16(tl + C::R3 + h0, v);
+                const float *bb = b2_g + h0;
                 if (a.skip) {
                     float sk[16];
-                    const float *sp = a.skip + brow + h0 * l;
+                    const float *sp = a.skip + brow + (size_t)h0 * l;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i, sp += l) sk[i] = valid ? __ldg(sp) : 0.f;
+                    for (int i = 0; i < 16; ++i) sk[i] = valid ? __ldg(chan<0>(sp, i, l)) : 0.f;
                     tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += sk[i];
-                } else
+                    for (int i = 0; i < 16; i += 2) {
+                        const s2::V2 y = (s2::V2(v[i], v[i + 1]) + s2::V2(__ldg(bb + i), __ldg(bb + i + 1))) + s2::V2(sk[i], sk[i + 1]);
+                        v[i] = y.v.x;
+                        v[i + 1] = y.v.y;
+                    }
+                } else {
                     tmem_wait_ld();
-                const float *bb = b2_g + h0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += __ldg(bb + i);
-                if (valid) {
-                    float *oq = op + h0 * l;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i, oq += l) *oq = v[i];
+                    for (int i = 0; i < 16; i += 2) {
+                        const s2::V2 y = s2::V2(v[i], v[i + 1]) + s2::V2(__ldg(bb + i), __ldg(bb + i + 1));
+                        v[i] = y.v.x;
+                        v[i + 1] = y.v.y;
+                    }
                 }
-                stat_merge16(v, n, mean, M2);
-                n += 16;
+                if (valid) {
+                    float *oq = op + (size_t)h0 * l;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) *chan<0>(oq, i, l) = v[i];
+                }
+                if (k == 0) piv = v[0];
+                stat_acc16(v, s2::V2(piv), sd, sq);
             }
+            stat_finish(sd, sq, piv, PER, mean, M2);
             exchange(mean, M2);
             if (cg == 0 && valid)
                 *reinterpret_cast<float2 *>(a.stats_out + ((size_t)b * l + t) * 2) = make_float2(mean, rsqrtf(M2 * (1.0f / H)));
@@ -1434,7 +1457,7 @@ sashimi_mix_umma256_kernel(MixArgs a) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == MW) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
@@ -1450,7 +1473,8 @@ __global__ void umma_pack256_kernel(const float *__restrict__ Wo_t, const float 
         float v;
         if (idx < (size_t)2 * H) {
             const int nc = idx / 128, i = idx % 128;
-            v = bo[i < 64 ? nc * 64 + i : H + nc * 64 + (i - 64)];
+            // value half as is; gate half pre-multiplied by -log2(e): the sigmoid exponent is one FFMA2 of the accumulator
+            v = i < 64 ? bo[nc * 64 + i] : -1.4426950408889634f * bo[H + nc * 64 + (i - 64)];
         } else if (idx < (size_t)4 * H)
             v = b1[idx - 2 * H];
         else
@@ -1493,7 +1517,8 @@ __global__ void umma_pack_kernel(const float *__restrict__ Wo_t, const float *__
         float v;
         if (idx < (size_t)2 * H) {
             const int nc = idx / 128, i = idx % 128;
-            v = bo[i < 64 ? nc * 64 + i : H + nc * 64 + (i - 64)];
+            // value half as is; gate half pre-multiplied by -log2(e): the sigmoid exponent is one FFMA2 of the accumulator
+            v = i < 64 ? bo[nc * 64 + i] : -1.4426950408889634f * bo[H + nc * 64 + (i - 64)];
         } else if (idx < (size_t)4 * H)
             v = b1[idx - 2 * H];
         else
@@ -1665,9 +1690,10 @@ int mix_umma_launch(const MixArgs &a_in, int B, cudaStream_t st) {
         return !e ? 0 : (std::string(e) == "tile" ? 1 : (std::string(e) == "pers" ? 2 : 0));
     }();
     if (a.H == 256) {
-        auto k = sashimi_mix_umma256_kernel;
+        static const int cs = [] { const char *e = getenv("DWB_UMMA256_CS"); return e ? atoi(e) : 4; }();
+        auto k = cs == 2 ? sashimi_mix_umma256_kernel<2> : sashimi_mix_umma256_kernel<4>;
         DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U256::SMEM));
-        k<<<dim3(ceil_div(a.l, UM_TT), B), U256::NTHREADS, U256::SMEM, st>>>(a);
+        k<<<dim3(ceil_div(a.l, UM_TT), B), 128 * (cs == 2 ? 2 : 4) + 64, U256::SMEM, st>>>(a);
         DWB_LAUNCH_CHECK();
         return DWB_OK;
     }
