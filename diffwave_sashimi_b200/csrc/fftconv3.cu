@@ -22,6 +22,7 @@
 #include "fft_radix.cuh"
 #include "fft_simd2.cuh"
 #include "kernels.h"
+#include "umma.cuh"
 
 namespace dwb {
 using s2::C2;
@@ -209,7 +210,12 @@ __device__ __forceinline__ void centre_wide(float *re, float *im, const float4 *
     __syncthreads();
 }
 
-template <int LOG2M, bool COMPACT>
+// TPARK (n = 32768 only): the two rows a CTA parks between its halves - the LayerNorm-applied input for the odd half and
+// the even half's result a[i] - live in TENSOR MEMORY instead of global memory.  The kernel issues no MMA, so the SM's
+// 256 KB of TMEM are idle; each of the two resident CTAs allocates 256 columns, a thread owns 128 words of its lane
+// (64 for y, 64 for a), writes them with tcgen05.st and reads them back itself with tcgen05.ld.  That removes
+// 4 x 64 KB per row of global stores and loads (and their L2 / DRAM traffic: 1.69x -> ~1.0x the algorithmic bytes).
+template <int LOG2M, bool COMPACT, bool TPARK>
 __global__ void __launch_bounds__(Fft3Cfg<LOG2M>::NT, Fft3Cfg<LOG2M>::MINB)
 fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
                 long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
@@ -224,6 +230,17 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
     float *twBr = twAi + Cfg::NTW0, *twBi = twBr + Cfg::NTW0;      // W_M^j
     float *midr = twBi + Cfg::NTW0, *midi = midr + Cfg::NMID;
     const int tid = threadIdx.x;
+    uint32_t tpark = 0;                                            // this thread's 128 TMEM words
+    if constexpr (TPARK) {
+        static_assert(!TPARK || (NT == 256 && Cfg::MINB == 2), "TMEM parking: 8 warps x 128 columns, two CTAs per SM");
+        uint32_t *tptr = reinterpret_cast<uint32_t *>(sm + Cfg::SMEM / sizeof(float));
+        if (tid < 32) umma::tmem_alloc(tptr, 256);
+        umma::tc_fence_before();
+        __syncthreads();
+        umma::tc_fence_after();
+        const int warp = tid >> 5;
+        tpark = *tptr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * 128u;
+    }
     const float lns = stats ? ln_s : 1.f, lnm = stats ? ln_m : 0.f;
     const int half = l >> 1;                                       // complex entries of the packed row (even)
 
@@ -282,7 +299,20 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
         // ---- outer forward pass, fused with the prologue: packed inputs i = j + p sub0 (+1 in lane 1), p < 16
         {
             C2 xx[16];
-            if (odd && ys) {
+            if (TPARK && odd) {
+                // the even half parked y in tensor memory, in register order
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[16];
+                    umma::tmem_ld16(tpark + 16 * c, v);
+                    umma::tmem_wait_ld();
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        xx[4 * c + p].x = V2(v[4 * p], v[4 * p + 1]);
+                        xx[4 * c + p].y = V2(v[4 * p + 2], v[4 * p + 3]);
+                    }
+                }
+            } else if (odd && ys) {
                 // the even half parked y as (re_i, re_i+1, im_i, im_i+1): one round trip, no statistics, no LN
 #pragma unroll
                 for (int p = 0; p < 16; ++p) {
@@ -321,9 +351,21 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
                         const float y3 = (lns * sb[p].w) * (xv[p].w - sb[p].z + lnm) + add;
                         xx[4 * hb + p].x = V2(in ? y0 : 0.f, in ? y2 : 0.f);
                         xx[4 * hb + p].y = V2(in ? y1 : 0.f, in ? y3 : 0.f);
-                        if (!odd && ys && in) *reinterpret_cast<float4 *>(ys + 2 * i) = make_float4(y0, y2, y1, y3);
+                        if (!TPARK && !odd && ys && in) *reinterpret_cast<float4 *>(ys + 2 * i) = make_float4(y0, y2, y1, y3);
+                    }
+                    if (TPARK && !odd) {
+                        float v[16];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            v[4 * p] = xx[4 * hb + p].x.v.x;
+                            v[4 * p + 1] = xx[4 * hb + p].x.v.y;
+                            v[4 * p + 2] = xx[4 * hb + p].y.v.x;
+                            v[4 * p + 3] = xx[4 * hb + p].y.v.y;
+                        }
+                        umma::tmem_st16(tpark + 16 * hb, v);
                     }
                 }
+                if (TPARK && !odd) umma::tmem_wait_st();
             }
             if (odd) s2::rotate_w32<false>(xx);
             s2::RadixS<16, false>::run(xx);
@@ -427,7 +469,35 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
             u0.y = odd ? -ld2(twBi + j0) : V2(0.f);
             s2::apply_twiddles16<true>(xx, u0, v);
             s2::RadixS<16, true>::run(xx);
-            if (odd) {
+            if (TPARK && odd) {
+                s2::rotate_w32<true>(xx);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[16];
+                    umma::tmem_ld16(tpark + 64 + 16 * c, v);
+                    umma::tmem_wait_ld();
+#pragma unroll
+                    for (int pp = 0; pp < 4; ++pp) {
+                        const int p = 4 * c + pp, i = j0 + (p << log2sub0);
+                        const V2 r = s2::gelu_fast2(xx[p].x + V2(v[4 * pp], v[4 * pp + 1])), q = s2::gelu_fast2(xx[p].y + V2(v[4 * pp + 2], v[4 * pp + 3]));
+                        if (i < half) *reinterpret_cast<float4 *>(gr + 2 * i) = make_float4(r.v.x, q.v.x, r.v.y, q.v.y);
+                    }
+                }
+            } else if (TPARK) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[16];
+#pragma unroll
+                    for (int pp = 0; pp < 4; ++pp) {
+                        v[4 * pp] = xx[4 * c + pp].x.v.x;
+                        v[4 * pp + 1] = xx[4 * c + pp].x.v.y;
+                        v[4 * pp + 2] = xx[4 * c + pp].y.v.x;
+                        v[4 * pp + 3] = xx[4 * c + pp].y.v.y;
+                    }
+                    umma::tmem_st16(tpark + 64 + 16 * c, v);
+                }
+                umma::tmem_wait_st();
+            } else if (odd) {
                 s2::rotate_w32<true>(xx);
 #pragma unroll
                 for (int p = 0; p < 16; ++p) {
@@ -451,6 +521,14 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
         }
         __syncthreads();          // the next half overwrites the planes
     }
+    }
+    if constexpr (TPARK) {
+        umma::tc_fence_before();
+        __syncthreads();
+        if (tid < 32) {
+            umma::tc_fence_after();
+            umma::tmem_dealloc(tpark, 256);             // warp 0: lane field 0, column offset 0 = the allocation base
+        }
     }
 }
 
@@ -663,16 +741,17 @@ int fftconv5_launch(int lg, const float *x, const float *stats, const float *par
     return DWB_ERR_UNSUPPORTED;
 }
 
-template <int LOG2M, bool COMPACT>
-static int launch_fftconv3(const float *x, const float *stats, const float *part_t, long long psb, float ln_m,
-                           float ln_s, const float *kc, const float2 *tw, const float2 *tw2, float *g, float *scratch, int B, int H,
-                           int l, cudaStream_t st) {
+template <int LOG2M, bool COMPACT, bool TPARK>
+static int launch_fftconv3_t(const float *x, const float *stats, const float *part_t, long long psb, float ln_m,
+                             float ln_s, const float *kc, const float2 *tw, const float2 *tw2, float *g, float *scratch, int B, int H,
+                             int l, cudaStream_t st) {
     using Cfg = Fft3Cfg<LOG2M>;
+    constexpr int SMEM = Cfg::SMEM + (TPARK ? 16 : 0);          // + the TMEM base address word
     static bool attr_set[16] = {};
     int dev = 0;
     DWB_CUDA(cudaGetDevice(&dev));
-    if (Cfg::SMEM > 48 * 1024 && !attr_set[dev & 15]) {
-        DWB_CUDA(cudaFuncSetAttribute((fftconv3_kernel<LOG2M, COMPACT>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    if (SMEM > 48 * 1024 && !attr_set[dev & 15]) {
+        DWB_CUDA(cudaFuncSetAttribute((fftconv3_kernel<LOG2M, COMPACT, TPARK>), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set[dev & 15] = true;
     }
     int nsm = 148;
@@ -684,10 +763,22 @@ static int launch_fftconv3(const float *x, const float *stats, const float *part
     static const bool pers = [] { const char *e = getenv("DWB_FFT_PERS"); return e && atoi(e) == 1; }();
     static const int stagger = [] { const char *e = getenv("DWB_FFT_STAGGER"); return e ? atoi(e) : 0; }();
     const int resident = nsm * Cfg::MINB, grid = pers ? std::min(B * H, resident) : B * H;
-    fftconv3_kernel<LOG2M, COMPACT><<<dim3(grid, 1, 1), Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw,
-                                                                               tw2, g, scratch, B, H, l, resident, pers ? stagger : 0);
+    fftconv3_kernel<LOG2M, COMPACT, TPARK><<<dim3(grid, 1, 1), Cfg::NT, SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw,
+                                                                                  tw2, g, scratch, B, H, l, resident, pers ? stagger : 0);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
+}
+
+template <int LOG2M, bool COMPACT>
+static int launch_fftconv3(const float *x, const float *stats, const float *part_t, long long psb, float ln_m,
+                           float ln_s, const float *kc, const float2 *tw, const float2 *tw2, float *g, float *scratch, int B, int H,
+                           int l, cudaStream_t st) {
+    if constexpr (LOG2M == 14) {
+        // rows parked in tensor memory (DWB_FFT_TPARK=0: in global memory, as in round 1)
+        static const bool tpark = [] { const char *e = getenv("DWB_FFT_TPARK"); return !(e && atoi(e) == 0); }();
+        if (tpark) return launch_fftconv3_t<LOG2M, COMPACT, true>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, tw2, g, scratch, B, H, l, st);
+    }
+    return launch_fftconv3_t<LOG2M, COMPACT, false>(x, stats, part_t, psb, ln_m, ln_s, kc, tw, tw2, g, scratch, B, H, l, st);
 }
 
 bool fftconv3_supported(int lg, const float *x, const float *stats, const float *g, int l) {
