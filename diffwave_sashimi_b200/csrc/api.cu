@@ -72,6 +72,8 @@ struct Op {
     // pool weights
     float *Wp_t = nullptr, *bp = nullptr;
     uint4 *Wp_f[2] = {nullptr, nullptr};
+    bool pumma = false;            // tcgen05 pool (pool_umma.cu)
+    uint8_t *Wp_img = nullptr;
 };
 
 struct WaveLayer {
@@ -465,6 +467,15 @@ static int finalize_sashimi(dwb_plan *p, cudaStream_t st) {
                 const bool up = o.kind == OP_UP;
                 const int M = up ? o.Ho * o.s : o.Ho, K = up ? o.H : o.H * o.s;
                 TRY(folded(p, o.prefix + "linear.conv", M, K, 1, true, &o.Wp_t, &o.bp, st));
+                // DWB_POOL=mma keeps the pools on the mma.sync kernels
+                static const bool pool_mma_only = [] { const char *e = getenv("DWB_POOL"); return e && std::string(e) == "mma"; }();
+                o.pumma = p->use_mma && p->use_umma && !pool_mma_only && pool_umma_supported(o.H, o.Ho, o.s, up, o.l);
+                if (o.pumma) {
+                    void *d;
+                    TRY(dev_alloc(p, pool_umma_image_bytes(o.H, o.Ho, o.s, up), &d)); o.Wp_img = (uint8_t *)d;
+                    TRY(pool_umma_pack(o.H, o.Ho, o.s, up, o.Wp_t, o.Wp_img, st));
+                    p->launches += 1;
+                }
                 o.mma = p->use_mma && pool_mma_supported(o.H, o.Ho, o.s, up);
                 if (o.mma) {
                     for (int q = 0; q < 2; ++q) {
@@ -731,7 +742,8 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
                 a.out = p->bufs[o.out_buf]; a.stats_out = p->stat_bufs[o.out_buf];
                 a.Hi = o.H; a.Ho = o.Ho; a.s = o.s; a.li = r;
                 a.W_fh = o.Wp_f[0]; a.W_fl = o.Wp_f[1];
-                if (o.mma) TRY(o.kind == OP_DOWN ? down_pool_mma_launch(a, B, st) : up_pool_mma_launch(a, B, st));
+                if (o.pumma && pool_umma_supported(o.H, o.Ho, o.s, o.kind == OP_UP, r)) TRY(pool_umma_launch(a, o.Wp_img, o.kind == OP_UP, B, st));
+                else if (o.mma) TRY(o.kind == OP_DOWN ? down_pool_mma_launch(a, B, st) : up_pool_mma_launch(a, B, st));
                 else TRY(o.kind == OP_DOWN ? down_pool_launch(a, B, st) : up_pool_launch(a, B, st));
                 p->launches += 1;
                 PROF(DWB_PROF_POOL);

@@ -46,10 +46,43 @@ struct Fft3Cfg {
         return o;
     }
     static constexpr int NMID = mid_off(NP - 1);
-    static constexpr int SMEM = (2 * PLANE + 4 * NTW0 + 2 * NMID) * (int)sizeof(float);
+    static constexpr int TWBYTES = (4 * NTW0 + 2 * NMID) * (int)sizeof(float);     // the six twiddle tables, contiguous after the planes
+    static constexpr int SMEM = 2 * PLANE * (int)sizeof(float) + TWBYTES;
+    static_assert(TWBYTES % 16 == 0, "bulk-copied twiddle image");
     static constexpr int MINB = (512 / NT > 8) ? 8 : 512 / NT;
     static_assert(RL >= 1 && RL <= 3 && NP >= 3 && NT >= 32, "v3 plan");
 };
+
+// the twiddle region in its shared-memory layout: W_Mh^j (re | im), W_M^j (re | im), j < Mh/16, then per middle pass
+// W_{S_P}^j (all re | all im); dst = shared memory (per CTA) or the global image built once per (device, log2M)
+template <int LOG2M>
+__device__ __forceinline__ void fft3_fill_twiddles(const float2 *__restrict__ tw, float *dst, int tid0, int nthreads = Fft3Cfg<LOG2M>::NT) {
+    using Cfg = Fft3Cfg<LOG2M>;
+    float *twAr = dst, *twAi = twAr + Cfg::NTW0, *twBr = twAi + Cfg::NTW0, *twBi = twBr + Cfg::NTW0;
+    float *midr = twBi + Cfg::NTW0, *midi = midr + Cfg::NMID;
+    for (int j = tid0; j < Cfg::NTW0; j += nthreads) {
+        const float2 a = tw[4 * j], bb = tw[2 * j];
+        twAr[j] = a.x;
+        twAi[j] = a.y;
+        twBr[j] = bb.x;
+        twBi[j] = bb.y;
+    }
+    int o = 0;
+#pragma unroll
+    for (int P = 1; P <= Cfg::NP - 2; ++P) {                        // W_{S_P}^j = W_n^{j 2^(2 + 4P)}
+        const int subP = Cfg::Mh >> (4 * P + 4);
+        for (int j = tid0; j < subP; j += nthreads) {
+            const float2 a = tw[j << (2 + 4 * P)];
+            midr[o + j] = a.x;
+            midi[o + j] = a.y;
+        }
+        o += subP;
+    }
+}
+template <int LOG2M>
+__global__ void fft3_twimg_kernel(const float2 *__restrict__ tw, float *img) {
+    fft3_fill_twiddles<LOG2M>(tw, img, threadIdx.x, blockDim.x);
+}
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ V2 ld2(const float *p) { return V2(*reinterpret_cast<const float2 *>(p)); }
@@ -220,7 +253,7 @@ __global__ void __launch_bounds__(Fft3Cfg<LOG2M>::NT, Fft3Cfg<LOG2M>::MINB)
 fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
                 long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
                 const float2 *__restrict__ tw /* W_n^i, i < M */, const float2 *__restrict__ tw2, float *g, float *scratch, int B, int H,
-                int l, int resident, int stagger_ns) {
+                int l, int resident, int stagger_ns, const float *__restrict__ twimg) {
     using Cfg = Fft3Cfg<LOG2M>;
     constexpr int LH = Cfg::LH, Mh = Cfg::Mh, NT = Cfg::NT, NP = Cfg::NP, RL = Cfg::RL;
     constexpr int log2sub0 = LH - 4, sub0 = 1 << log2sub0;         // outer pass: radix 16, span Mh
@@ -244,28 +277,22 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
     const float lns = stats ? ln_s : 1.f, lnm = stats ? ln_m : 0.f;
     const int half = l >> 1;                                       // complex entries of the packed row (even)
 
-    // twiddle tables: once per CTA (the grid is persistent: a CTA walks rows blockIdx.x, + gridDim.x, ...)
-    for (int j = tid; j < Cfg::NTW0; j += NT) {
-        const float2 a = tw[4 * j], bb = tw[2 * j];
-        twAr[j] = a.x;
-        twAi[j] = a.y;
-        twBr[j] = bb.x;
-        twBi[j] = bb.y;
-    }
-    {
-        int o = 0;
-#pragma unroll
-        for (int P = 1; P <= NP - 2; ++P) {                        // W_{S_P}^j = W_n^{j 2^(2 + 4P)}
-            const int subP = Mh >> (4 * P + 4);
-            for (int j = tid; j < subP; j += NT) {
-                const float2 a = tw[j << (2 + 4 * P)];
-                midr[o + j] = a.x;
-                midi[o + j] = a.y;
-            }
-            o += subP;
+    // twiddle tables, once per CTA: with a prebuilt image (twimg: the six tables in their shared-memory layout) one bulk
+    // copy that lands under the prologue's loads and is awaited just before the first twiddle is read; otherwise
+    // gathered from the W_n^i table
+    uint64_t *twbar = reinterpret_cast<uint64_t *>(sm + Cfg::SMEM / sizeof(float) + 4);
+    if (twimg) {
+        if (tid == 0) {
+            umma::mbar_init(twbar, 1);
+            umma::fence_mbar_init();
+            umma::mbar_arrive_expect_tx(twbar, Cfg::TWBYTES);
+            umma::bulk_g2s(twAr, twimg, Cfg::TWBYTES, twbar);
         }
+    } else {
+        fft3_fill_twiddles<LOG2M>(tw, twAr, tid);
     }
     __syncthreads();
+    bool tw_pending = twimg != nullptr;
 
     const int j0 = 2 * tid;                                         // outer-pass butterflies j0, j0 + 1
     const int pb0 = padf(j0);
@@ -369,6 +396,10 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
             }
             if (odd) s2::rotate_w32<false>(xx);
             s2::RadixS<16, false>::run(xx);
+            if (tw_pending) {
+                umma::mbar_wait(twbar, 0);
+                tw_pending = false;
+            }
             C2 v, u0;
             v.x = ld2(twAr + j0);
             v.y = ld2(twAi + j0);
@@ -746,7 +777,24 @@ static int launch_fftconv3_t(const float *x, const float *stats, const float *pa
                              float ln_s, const float *kc, const float2 *tw, const float2 *tw2, float *g, float *scratch, int B, int H,
                              int l, cudaStream_t st) {
     using Cfg = Fft3Cfg<LOG2M>;
-    constexpr int SMEM = Cfg::SMEM + (TPARK ? 16 : 0);          // + the TMEM base address word
+    constexpr int SMEM = Cfg::SMEM + 32;                        // + the TMEM base address word, the twiddle-copy barrier
+    // image of the shared-memory twiddle tables: immutable, per (device, log2M), built on first use (outside stream capture)
+    static float *twimg[16] = {};
+    {
+        int dev0 = 0;
+        DWB_CUDA(cudaGetDevice(&dev0));
+        if (!twimg[dev0 & 15]) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(st, &cs);
+            if (cs == cudaStreamCaptureStatusNone) {
+                float *d = nullptr;
+                DWB_CUDA(cudaMalloc(&d, Cfg::TWBYTES));
+                fft3_twimg_kernel<LOG2M><<<1, 256, 0, st>>>(tw, d);
+                DWB_LAUNCH_CHECK();
+                twimg[dev0 & 15] = d;
+            }
+        }
+    }
     static bool attr_set[16] = {};
     int dev = 0;
     DWB_CUDA(cudaGetDevice(&dev));
@@ -764,7 +812,7 @@ static int launch_fftconv3_t(const float *x, const float *stats, const float *pa
     static const int stagger = [] { const char *e = getenv("DWB_FFT_STAGGER"); return e ? atoi(e) : 0; }();
     const int resident = nsm * Cfg::MINB, grid = pers ? std::min(B * H, resident) : B * H;
     fftconv3_kernel<LOG2M, COMPACT, TPARK><<<dim3(grid, 1, 1), Cfg::NT, SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw,
-                                                                                  tw2, g, scratch, B, H, l, resident, pers ? stagger : 0);
+                                                                                  tw2, g, scratch, B, H, l, resident, pers ? stagger : 0, twimg[dev & 15]);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
 }

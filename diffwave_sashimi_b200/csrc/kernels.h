@@ -82,6 +82,11 @@ int mix_mma_launch(const MixArgs &a, int B, cudaStream_t st);
 bool pool_mma_supported(int Hi, int Ho, int s, bool up);
 int down_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st);
 int up_pool_mma_launch(const PoolArgs &a, int B, cudaStream_t st);
+// tcgen05 pools (pool_umma.cu): all output columns of a 128-step tile in one CTA's TMEM
+bool pool_umma_supported(int Hi, int Ho, int s, bool up, int li);
+size_t pool_umma_image_bytes(int Hi, int Ho, int s, bool up);
+int pool_umma_pack(int Hi, int Ho, int s, bool up, const float *W_t, uint8_t *img, cudaStream_t st);
+int pool_umma_launch(const PoolArgs &a, const uint8_t *Wimg, bool up, int B, cudaStream_t st);
 bool mix_umma_supported(int H, int F, int l);
 size_t mix_umma_image_bytes(int H);
 int mix_umma_pack(int H, const float *Wo_t, const float *W1_t, const float *W2_t, const float *bo, const float *b1,

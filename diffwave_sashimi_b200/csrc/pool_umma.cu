@@ -1,0 +1,332 @@
+// SaShiMi DownPool / UpPool on the 5th-generation tensor cores.                    models/sashimi.py:23-58
+//
+//   down(s): x'[h*s+j][c] = x[b, h, c*s + j];  out = W x' + bias                     (K = Hi*s -> M = Ho), + stats
+//   up(s):   y = W x + bias (K = Hi -> M = Ho*s);  out[b, h, c*s + j] = y[h*s+j][c] (+ skip),          + stats
+//
+// Same orientation as the mixing kernels: one CTA = 128 steps c (the MMA M dimension = the TMEM lanes) x ALL M
+// output columns (M / 128 accumulators of 128 TMEM columns), K streamed in chunks of 64: eight loader warps read
+// the A chunk from global memory with the einops rearrange folded into the addressing (down: one float4 / float2 =
+// the s samples of a channel per thread, up: one sample per channel, coalesced along time either way), split it
+// into bf16 hi / lo and store it K-major / SW128 into a two-slot ring; the weights come pre-packed (split,
+// swizzled, consumption order (kc, n-tile)) through a three-stage bulk-copy ring; three MMAs per product
+// (hi*hi + lo*hi + hi*lo).  Because a CTA holds every output channel of its steps, the epilogue thread that owns a
+// step computes the next block's TransposedLN statistics itself (up: s statistics per thread, one per sub-step).
+#include "common.cuh"
+#include "fft_simd2.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace dwb {
+using namespace umma;
+
+constexpr int PU_STAGE = 32768, PU_SLAB = 32768, PU_NSW = 3, PU_NSU = 2, PU_THREADS = 320;
+constexpr int PU_OFF_RING = PU_NSU * PU_SLAB;
+constexpr int PU_OFF_EX = PU_OFF_RING + PU_NSW * PU_STAGE;          // statistics exchange: [2 halves][128 steps][4] float2
+constexpr int PU_OFF_BAR = PU_OFF_EX + 2 * 128 * 4 * 8;
+constexpr int PU_NBAR = 2 * PU_NSW + 2 * PU_NSU + 1;
+constexpr int PU_SMEM = PU_OFF_BAR + PU_NBAR * 8 + 16 + 1024;
+
+struct PoolUmmaArgs {
+    const float *x;                // down: (B,Hi,li)          up: (B,Hi,li)
+    const float *skip;             // up only: (B,Ho,li*s) or null
+    const uint8_t *Wimg;           // stages (kc, n-tile), 32 KB each
+    const float *bias;             // (M)
+    float *out, *stats_out;        // down: (B,Ho,li/s), (B,li/s,2)   up: (B,Ho,li*s), (B,li*s,2)
+    int Hi, Ho, li, K, M;
+};
+
+template <bool UP, int S>
+__global__ void __launch_bounds__(PU_THREADS, 1)
+pool_umma_kernel(PoolUmmaArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *slabs = sm, *ring = sm + PU_OFF_RING;
+    float2 *ex = reinterpret_cast<float2 *>(sm + PU_OFF_EX);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + PU_OFF_BAR);
+    uint32_t *tptr = reinterpret_cast<uint32_t *>(bars + PU_NBAR);
+    uint64_t *wfull = bars, *wempty = wfull + PU_NSW, *ufull = wempty + PU_NSW, *uempty = ufull + PU_NSU, *acc_ready = uempty + PU_NSU;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, t0 = blockIdx.x * 128;
+    const int li = a.li, lo = UP ? li * S : li / S, lc = UP ? li : lo;      // lc: steps of the GEMM's M dimension
+    const int KC = a.K / 64, NC = a.M / 128;
+    if (tid == 0) {
+        for (int i = 0; i < PU_NSW; ++i) {
+            mbar_init(wfull + i, 1);
+            mbar_init(wempty + i, 1);
+        }
+        for (int i = 0; i < PU_NSU; ++i) {
+            mbar_init(ufull + i, 128);
+            mbar_init(uempty + i, 1);
+        }
+        mbar_init(acc_ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc(tptr, (uint32_t)a.M);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tptr;
+
+    if (warp == 8) {
+        // ================= weight producer =====================================================
+        if (lane == 0) {
+            const int n = KC * NC;
+            for (int i = 0; i < n; ++i) {
+                const int s = i % PU_NSW, ph = i / PU_NSW;
+                mbar_wait(wempty + s, (ph & 1) ^ 1);
+                mbar_arrive_expect_tx(wfull + s, PU_STAGE);
+                bulk_g2s(ring + (size_t)s * PU_STAGE, a.Wimg + (size_t)i * PU_STAGE, PU_STAGE, wfull + s);
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer ==========================================================
+        if (lane == 0) {
+            const uint32_t slab0 = smem_u32(slabs), ring0 = smem_u32(ring);
+            constexpr uint32_t idesc = idesc_bf16(128, 128);
+            int i = 0;
+#pragma unroll 1
+            for (int kc = 0; kc < KC; ++kc) {
+                const int us = kc % PU_NSU;
+                mbar_wait(ufull + us, (kc / PU_NSU) & 1);
+                tc_fence_after();
+                const uint32_t abase = slab0 + us * PU_SLAB;
+#pragma unroll 1
+                for (int nt = 0; nt < NC; ++nt, ++i) {
+                    const int s = i % PU_NSW;
+                    mbar_wait(wfull + s, (i / PU_NSW) & 1);
+                    tc_fence_after();
+                    const uint32_t bbase = ring0 + s * PU_STAGE;
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t ao = abase + (term == 1 ? PU_SLAB / 2 : 0), bo = bbase + (term == 2 ? PU_STAGE / 2 : 0);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_bf16_ss(tmem + nt * 128, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
+                                        (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    mma_commit(wempty + s);
+                }
+                mma_commit(uempty + us);
+            }
+            mma_commit(acc_ready);
+        }
+    } else {
+        // ================= loaders, then epilogue: one step per thread ===========================
+        const int q = warp & 3, cg = warp >> 2;
+        const int r = 32 * q + lane, c = t0 + r;
+        const bool valid = c < lc;
+        const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
+        const size_t cc = valid ? c : 0;
+#pragma unroll 1
+        for (int kc = cg; kc < KC; kc += PU_NSU) {
+            float v[64];
+            if (UP) {
+                const float *ap = a.x + ((size_t)b * a.Hi + (size_t)kc * 64) * li + cc;
+#pragma unroll
+                for (int i = 0; i < 64; ++i, ap += li) v[i] = valid ? __ldg(ap) : 0.f;
+            } else {
+                // k = h*S + j: the S consecutive samples of input channel h that feed output step c
+                constexpr int CH = 64 / S;
+                const float *ap = a.x + ((size_t)b * a.Hi + (size_t)kc * CH) * li + cc * S;
+#pragma unroll
+                for (int hh = 0; hh < CH; ++hh, ap += li) {
+                    if (S == 4) {
+                        const float4 w = valid ? __ldg(reinterpret_cast<const float4 *>(ap)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[4 * hh] = w.x; v[4 * hh + 1] = w.y; v[4 * hh + 2] = w.z; v[4 * hh + 3] = w.w;
+                    } else {
+                        const float2 w = valid ? __ldg(reinterpret_cast<const float2 *>(ap)) : make_float2(0.f, 0.f);
+                        v[2 * hh] = w.x; v[2 * hh + 1] = w.y;
+                    }
+                }
+            }
+            mbar_wait(uempty + cg, ((kc / PU_NSU) & 1) ^ 1);
+            uint8_t *slab = slabs + cg * PU_SLAB;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                uint4 hi, lo;
+                split8(v + 8 * c8, hi, lo);
+                const uint32_t off = sw128_off(r, c8);
+                *reinterpret_cast<uint4 *>(slab + off) = hi;
+                *reinterpret_cast<uint4 *>(slab + PU_SLAB / 2 + off) = lo;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(ufull + cg);
+        }
+
+        mbar_wait(acc_ready, 0);
+        tc_fence_after();
+        const int MH = a.M / 2, n0 = cg * MH;                  // this thread's output columns [n0, n0 + MH)
+        if (!UP) {
+            float *op = a.out + ((size_t)b * a.Ho + n0) * lo + cc;
+            float sd = 0.f, sq = 0.f, piv = 0.f;
+#pragma unroll 1
+            for (int sc = 0; sc < MH / 16; ++sc) {
+                float v[16];
+                tmem_ld16(tl + n0 + sc * 16, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + n0 + sc * 16 + i);
+                if (sc == 0) piv = v[0];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float d = v[i] - piv;
+                    sd += d;
+                    sq = fmaf(d, d, sq);
+                }
+                if (valid) {
+                    float *oq = op + (size_t)(sc * 16) * lo;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i, oq += lo) *oq = v[i];
+                }
+            }
+            const float inv = 1.0f / (float)MH;
+            const float mean = fmaf(sd, inv, piv), M2 = fmaxf(fmaf(-sd * inv, sd, sq), 0.f);
+            ex[cg * 128 + r] = make_float2(mean, M2);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (cg == 0 && valid) {
+                const float2 e0 = ex[r], e1 = ex[128 + r];
+                const float mt = 0.5f * (e0.x + e1.x), d0 = e0.x - mt, d1 = e1.x - mt;
+                const float m2 = e0.y + e1.y + (d0 * d0 + d1 * d1) * (float)MH;
+                *reinterpret_cast<float2 *>(a.stats_out + ((size_t)b * lo + c) * 2) = make_float2(mt, rsqrtf(m2 / (float)a.M));
+            }
+        } else {
+            // columns n = h*S + j: 16 columns = 16/S output channels x the S sub-steps of this thread's step
+            constexpr int HPC = 16 / S;
+            const int h0 = n0 / S, nh = MH / S;                 // this thread's output channels [h0, h0 + nh)
+            float *op = a.out + ((size_t)b * a.Ho + h0) * lo + cc * S;
+            const float *sp = a.skip ? a.skip + ((size_t)b * a.Ho + h0) * lo + cc * S : nullptr;
+            float sd[S], sq[S], piv[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) sd[j] = sq[j] = piv[j] = 0.f;
+#pragma unroll 1
+            for (int sc = 0; sc < MH / 16; ++sc) {
+                float v[16], sk[16];
+                tmem_ld16(tl + n0 + sc * 16, v);
+                if (sp) {
+#pragma unroll
+                    for (int hh = 0; hh < HPC; ++hh) {
+                        const float *sq_ = sp + (size_t)(sc * HPC + hh) * lo;
+                        if (S == 4) {
+                            const float4 w = valid ? __ldg(reinterpret_cast<const float4 *>(sq_)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            sk[4 * hh] = w.x; sk[4 * hh + 1] = w.y; sk[4 * hh + 2] = w.z; sk[4 * hh + 3] = w.w;
+                        } else {
+                            const float2 w = valid ? __ldg(reinterpret_cast<const float2 *>(sq_)) : make_float2(0.f, 0.f);
+                            sk[2 * hh] = w.x; sk[2 * hh + 1] = w.y;
+                        }
+                    }
+                }
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + n0 + sc * 16 + i) + (sp ? sk[i] : 0.f);
+                if (sc == 0) {
+#pragma unroll
+                    for (int j = 0; j < S; ++j) piv[j] = v[j];
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float d = v[i] - piv[i % S];
+                    sd[i % S] += d;
+                    sq[i % S] = fmaf(d, d, sq[i % S]);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int hh = 0; hh < HPC; ++hh) {
+                        float *oq = op + (size_t)(sc * HPC + hh) * lo;
+                        if (S == 4) *reinterpret_cast<float4 *>(oq) = make_float4(v[4 * hh], v[4 * hh + 1], v[4 * hh + 2], v[4 * hh + 3]);
+                        else *reinterpret_cast<float2 *>(oq) = make_float2(v[2 * hh], v[2 * hh + 1]);
+                    }
+                }
+            }
+            const float inv = 1.0f / (float)nh;
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                ex[(cg * 128 + r) * 4 + j] = make_float2(fmaf(sd[j], inv, piv[j]), fmaxf(fmaf(-sd[j] * inv, sd[j], sq[j]), 0.f));
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (cg == 0 && valid) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const float2 e0 = ex[r * 4 + j], e1 = ex[(128 + r) * 4 + j];
+                    const float mt = 0.5f * (e0.x + e1.x), d0 = e0.x - mt, d1 = e1.x - mt;
+                    const float m2 = e0.y + e1.y + (d0 * d0 + d1 * d1) * (float)nh;
+                    *reinterpret_cast<float2 *>(a.stats_out + ((size_t)b * lo + (size_t)c * S + j) * 2) = make_float2(mt, rsqrtf(m2 / (float)a.Ho));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc(tmem, (uint32_t)a.M);
+    }
+}
+
+// image of a transposed weight Wt [K][M]: stages (kc, n-tile) = [128 rows x 64 k] hi block, then lo block (K-major SW128)
+__global__ void pool_umma_pack_kernel(const float *__restrict__ Wt, int K, int M, uint8_t *__restrict__ img) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one (stage, row, 16-byte chunk)
+    const int NC = M / 128;
+    if (idx >= (size_t)(K / 64) * NC * 128 * 8) return;
+    const size_t stage = idx / (128 * 8);
+    const int rem = idx % (128 * 8), row = rem / 8, j8 = rem % 8;
+    const int kc = (int)(stage / NC), nt = (int)(stage % NC);
+    const int n = nt * 128 + row, k0 = kc * 64 + j8 * 8;
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float w0 = Wt[(size_t)(k0 + 2 * e) * M + n], w1 = Wt[(size_t)(k0 + 2 * e + 1) * M + n];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(w0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(w1 - __bfloat162float(h1));
+        hp[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lp[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const size_t off = stage * PU_STAGE + (size_t)row * 128 + ((j8 ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4 *>(img + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4 *>(img + off + PU_STAGE / 2) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+}
+
+// M = all output columns of a step in one CTA's TMEM (a power of two <= 512), K in 64-wide chunks, float4 / float2 rows
+bool pool_umma_supported(int Hi, int Ho, int s, bool up, int li) {
+    const int M = up ? Ho * s : Ho, K = up ? Hi : Hi * s;
+    if (!(s == 2 || s == 4)) return false;
+    if (!(M == 128 || M == 256 || M == 512) || K % 64 != 0) return false;
+    return up ? true : (li % s == 0 && (li % 4) == 0);
+}
+
+size_t pool_umma_image_bytes(int Hi, int Ho, int s, bool up) {
+    const size_t M = up ? (size_t)Ho * s : Ho, K = up ? Hi : (size_t)Hi * s;
+    return (K / 64) * (M / 128) * PU_STAGE;
+}
+
+int pool_umma_pack(int Hi, int Ho, int s, bool up, const float *W_t, uint8_t *img, cudaStream_t st) {
+    const int M = up ? Ho * s : Ho, K = up ? Hi : Hi * s;
+    const size_t total = (size_t)(K / 64) * (M / 128) * 128 * 8;
+    pool_umma_pack_kernel<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(W_t, K, M, img);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+template <bool UP, int S>
+static int launch_pool_umma(const PoolUmmaArgs &g, int B, cudaStream_t st) {
+    auto k = pool_umma_kernel<UP, S>;
+    DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PU_SMEM));
+    const int lc = UP ? g.li : g.li / S;
+    k<<<dim3(ceil_div(lc, 128), B), PU_THREADS, PU_SMEM, st>>>(g);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
+int pool_umma_launch(const PoolArgs &a, const uint8_t *Wimg, bool up, int B, cudaStream_t st) {
+    DWB_REQUIRE(Wimg, DWB_ERR_STATE, "pool_umma: weights were not packed");
+    const uintptr_t al = (uintptr_t)a.x | (uintptr_t)a.out | (uintptr_t)(a.skip ? a.skip : a.x);
+    DWB_REQUIRE((al & 15) == 0 && B <= 65535, DWB_ERR_UNSUPPORTED, "pool_umma: unaligned tensors");
+    PoolUmmaArgs g{};
+    g.x = a.x; g.skip = a.skip; g.Wimg = Wimg; g.bias = a.bias; g.out = a.out; g.stats_out = a.stats_out;
+    g.Hi = a.Hi; g.Ho = a.Ho; g.li = a.li;
+    g.M = up ? a.Ho * a.s : a.Ho;
+    g.K = up ? a.Hi : a.Hi * a.s;
+    if (up) return a.s == 4 ? launch_pool_umma<true, 4>(g, B, st) : launch_pool_umma<true, 2>(g, B, st);
+    return a.s == 4 ? launch_pool_umma<false, 4>(g, B, st) : launch_pool_umma<false, 2>(g, B, st);
+}
+
+}  // namespace dwb

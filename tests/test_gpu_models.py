@@ -340,10 +340,15 @@ def test_errors(dwb):
         dwb.Engine(g["cfg"], {k: v.cuda() for k, v in sd.items()})
 
 
-@pytest.mark.parametrize("variant", ["tile", "pers"])
+@pytest.mark.parametrize("variant", [{"DWB_UMMA": "tile"}, {"DWB_UMMA": "pers"}, {"DWB_UMMA_STAGE": "0"}, {"DWB_UMMA256_CS": "2"},
+                                     {"DWB_POOL": "mma"}, {"DWB_FFT_TPARK": "0"}, {"DWB_SERPENTINE": "0"}, {"DWB_FFT_PERS": "1"}])
 def test_tcgen05_mixing_variants_vs_reference_golden(variant):
-    """The per-tile and the persistent form of the fused tcgen05 mixing kernel (chosen by tile count at run time,
-    forced here through DWB_UMMA, which is read once per process -> subprocess) against the reference's eps."""
+    """Every implementation behind an environment switch on the unet d64 path (switches are read once per process ->
+    subprocess) against the reference's eps: the per-tile (operands in shared memory) and the persistent (operands in
+    TMEM, TMA-staged inputs) mixing kernel, the persistent kernel with register-loaded inputs (the path of sequence
+    lengths outside the BASELINE set), the H = 256 kernel with two epilogue threads per step, the mma.sync pools
+    (default: tcgen05), the S4 convolution with its parked rows in global memory (default: tensor memory), forward
+    tile order, persistent S4-convolution grid."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -358,8 +363,8 @@ def test_tcgen05_mixing_variants_vs_reference_golden(variant):
         "r = torch.from_numpy(g['eps_t100']).double(); print('REL', float((e - r).norm() / r.norm()))\n"
     ) % (root, os.path.join(GOLDEN, "full_unet_d64.npz"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, DWB_UMMA=variant))
+                       env=dict(os.environ, **variant))
     assert r.returncode == 0, r.stderr[-2000:]
     rel = float([l for l in r.stdout.splitlines() if l.startswith("REL")][0].split()[1])
-    print(f"DWB_UMMA={variant}: rel_l2 {rel:.2e}")
+    print(f"{variant}: rel_l2 {rel:.2e}")
     assert rel < 1e-4
