@@ -539,7 +539,7 @@ struct PCfg {
     // warps: NG epilogue groups | NG MMA issuers | weight producer | (streaming weights only) input-staging producer;
     // with resident weights the weight producer is idle after its first copies and stages the inputs itself
     static constexpr int NTHREADS = NG * EPI + NG * 32 + 32 + (RESIDENT ? 0 : 32);
-    static constexpr int NS = RESIDENT ? U::NSTG : 2;          // weight buffers (RESIDENT: one per stage)
+    static constexpr int NS = RESIDENT ? U::NSTG : 2;          // weight buffers (RESIDENT: one per stage; a third streaming stage measured no gain)
     // biases in shared memory.  (H = 128 measured with a third ring stage in their place and the biases through L1:
     // 191 us against 167 us - the uniform bias loads sit on the epilogues' critical path.)
     static constexpr bool BIAS_SMEM = true;
@@ -553,7 +553,7 @@ struct PCfg {
     static constexpr int OFF_BIAS = OFF_W + NS * UM_STAGE;
     static constexpr int OFF_BAR = OFF_BIAS + (BIAS_SMEM ? 5 * H * 4 : 0);
     static constexpr int OFF_TPTR = OFF_BAR + NBAR * 8;
-    static constexpr int SMEM = OFF_TPTR + 16 + 1024;
+    static constexpr int SMEM = OFF_TPTR + 16 + 1024;          // + alignment slack
     static_assert(4 * H <= GCOLS, "TMEM budget: accumulator (2H) + x1 (H) + A operand (H) columns per group");
     static_assert(SMEM <= 227 * 1024, "persistent tile set does not fit shared memory");
 };
@@ -938,23 +938,26 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
                 mbar_arrive(z_ready);
             }
             PT(3);
-            // ---- E2: hidden = gelu(W1 z + b1), split, written in place over the accumulator columns as the A operand of G3
+            // ---- E2: hidden = gelu(W1 z + b1), split, written in place over the accumulator columns as the A operand of G3.
+            //      The TMEM load of the next 16 columns is issued before the arithmetic of the current ones.
             {
-                constexpr int PERF = 128 / CS;
+                constexpr int PERF = 128 / CS, NSC = PERF / 16, SPK = PERF / 32;      // SPK: 16-column steps per K chunk and thread
+                // a thread's columns are spread over both 64-wide K chunks of an N chunk, so the first chunk is complete -
+                // and its part of G3 issued - when E2 is half way through the second
+                auto e2col = [&](int sc) { return (sc / SPK) * 64 + cg * (PERF / 2) + (sc % SPK) * 16; };
 #pragma unroll 1
                 for (int nc = 0; nc < C::NC1; ++nc) {
                     mbar_wait(acc2_ready + nc, ph);
                     tc_fence_after();
                     if (nc == 0) PT(4);
-#pragma unroll 1
-                    for (int sc = 0; sc < PERF / 16; ++sc) {
-                        // a thread's columns are spread over both 64-wide K chunks of this N chunk, so the first chunk is
-                        // complete - and its part of G3 issued - when E2 is half way through the second
-                        constexpr int SPK = PERF / 32;             // 16-column steps per K chunk and thread
-                        const int col = (sc / SPK) * 64 + cg * (PERF / 2) + (sc % SPK) * 16, f0 = nc * 128 + col;
-                        float v[16];
-                        tmem_ld16(tl + f0, v);
+                    float vbuf[2][16];
+                    tmem_ld16(tl + nc * 128 + e2col(0), vbuf[0]);
+#pragma unroll
+                    for (int sc = 0; sc < NSC; ++sc) {
+                        float(&v)[16] = vbuf[sc & 1];
+                        const int f0 = nc * 128 + e2col(sc);
                         tmem_wait_ld();
+                        if (sc + 1 < NSC) tmem_ld16(tl + nc * 128 + e2col(sc + 1), vbuf[(sc + 1) & 1]);
                         const float *bb = b1_s + f0;
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
@@ -1697,6 +1700,8 @@ int mix_umma_launch(const MixArgs &a_in, int B, cudaStream_t st) {
         DWB_LAUNCH_CHECK();
         return DWB_OK;
     }
+    // (H = 128 with four epilogue threads per step or a third weight-ring stage measured no gain: 173 / 172 us against
+    // 167-174 us - its tile time is set by the MMAs waiting for the 384 KB weight image that every tile re-streams from L2)
     const bool pers = mode != 1;
     if (pers) switch (a.H) {
         case 64: return launch_umma_pers_l<64, 2>(a, B, st);
