@@ -85,9 +85,8 @@ def kernel_label(kname, cfg, B):
         if kname.startswith("fft"):
             lg = max(4, (l - 1).bit_length())
             return f"fftconv3_kernel<{lg}> (H={H}, l={l})" if lg == 14 and l % 4 == 0 else f"fftconv_kernel<{lg}> (H={H}, l={l})"
-        tiles = B * ((l + 127) // 128)
-        k = {64: "sashimi_mix_umma_pers_kernel<64,2>" if tiles >= 6000 else "sashimi_mix_umma_kernel<64,2>",
-             128: "sashimi_mix_umma_pers_kernel<128,2>", 256: "sashimi_mix_umma256_kernel"}.get(H)
+        k = {64: "sashimi_mix_umma_pers_kernel<64,2>", 128: "sashimi_mix_umma_pers_kernel<128,2>",
+             256: "sashimi_mix_umma256_kernel"}.get(H)
         if k is None:
             k = "mix_gemm_umma_kernel x3 + channel_stats_kernel x2" if H % 128 == 0 else f"sashimi_mix_mma_kernel<{H}> (mma.sync)"
         return f"{k} (H={H}, l={l})"
