@@ -755,19 +755,26 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
         const bool tracer = trace && grp == 0 && etid == 0;
 #define PT(slot) do { if (tracer && it == 1) trace[slot] = clock64(); } while (0)
 
-        // statistics exchange between the CS column groups of a time step (partners share the TMEM lane) through
-        // a column of this thread's own range that it has already consumed
-        auto exchange = [&](uint32_t col, float &mean, float &M2) {
+        // statistics exchange between the CS column groups of a time step (partners share the TMEM lane) through two
+        // columns of this thread's OWN range that it has already consumed (col + cg * stride: a partner may still be
+        // reading its own columns of the same region).  `release`: a second barrier after the partners' values have been
+        // read, needed when the next writer of those columns is another epilogue thread rather than an MMA behind an mbarrier.
+        auto exchange = [&](uint32_t col, int stride, bool release, float &mean, float &M2) {
             if (CS > 1) {
-                tmem_st2(tl + col + cg * (H / CS), mean, M2);
+                tmem_st2(tl + col + cg * stride, mean, M2);
                 tmem_wait_st();
                 tc_fence_before();
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(P::EPI) : "memory");
                 tc_fence_after();
                 float pm[CS], p2[CS];
 #pragma unroll
-                for (int c = 0; c < CS; ++c) tmem_ld2(tl + col + c * (H / CS), pm[c], p2[c]);
+                for (int c = 0; c < CS; ++c) tmem_ld2(tl + col + c * stride, pm[c], p2[c]);
                 tmem_wait_ld();
+                if (release) {
+                    tc_fence_before();
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(P::EPI) : "memory");
+                    tc_fence_after();
+                }
                 float ms = 0.f;
 #pragma unroll
                 for (int c = 0; c < CS; ++c) ms += pm[c];
@@ -915,7 +922,9 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
                 tmem_wait_st();
             }
             PT(2);
-            exchange(0, mean, M2);                // accumulator columns this thread has consumed (G2 has not been issued)
+            // through accumulator columns this thread has consumed (its first value columns); their next writer is G2, issued
+            // only after every thread has arrived on z_ready, i.e. after its exchange reads
+            exchange(0, PP, false, mean, M2);
             // ---- z = LN2(x1), split -> AOP: the A operand of G2 (G1 has completed: acc1 was awaited)
             {
                 const float rstd = valid ? rsqrtf(M2 * (1.0f / H)) : 0.f;
@@ -1044,7 +1053,8 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
                     stat_acc16(v, s2::V2(piv), sd, sq);
                 }
                 stat_finish(sd, sq, piv, PER, mean, M2);
-                exchange(P::R3, mean, M2);        // x2 columns this thread has read (the next E1 rewrites them later)
+                // through x2 columns this thread has read; their next writer is a partner's E1 of the next tile: second barrier
+                exchange(P::R3, PER, true, mean, M2);
                 if (cg == 0 && valid)
                     *reinterpret_cast<float2 *>(a.stats_out + ((size_t)b * l + t) * 2) = make_float2(mean, rsqrtf(M2 * (1.0f / H)));
             }
@@ -1281,15 +1291,17 @@ sashimi_mix_umma256_kernel(MixArgs a) {
         }
         tmem_wait_st();
 
-        auto exchange = [&](float &mean, float &M2) {       // through R1a columns (idle at both exchange points)
-            tmem_st2(tl + C::R1 + 2 * cg, mean, M2);
+        // through R1a columns of this thread's OWN value range (all of its E1 reads are done; a partner may still be reading
+        // its own columns of R1a); the next writer of R1a is G2(0), issued after every thread has arrived on z_ready
+        auto exchange = [&](float &mean, float &M2) {
+            tmem_st2(tl + C::R1 + cg * PP, mean, M2);
             tmem_wait_st();
             tc_fence_before();
             asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
             tc_fence_after();
             float pm[CS], p2[CS];
 #pragma unroll
-            for (int c = 0; c < CS; ++c) tmem_ld2(tl + C::R1 + 2 * c, pm[c], p2[c]);
+            for (int c = 0; c < CS; ++c) tmem_ld2(tl + C::R1 + c * PP, pm[c], p2[c]);
             tmem_wait_ld();
             float ms = 0.f;
 #pragma unroll
