@@ -23,6 +23,9 @@ struct MixArgs {
     float *out, *stats_out;        // (B,H,l), (B,l,2)
     int H, F, l;
     int rev;                       // tcgen05 kernels: walk tiles from the end of the batch (serpentine L2 reuse)
+    int jitter;                    // debug (DWB_DEBUG_JITTER, ns): pseudo-random per-thread sleeps at the phase boundaries of the
+                                   // tcgen05 mixing kernels - opens the windows of timing-dependent races (TMEM columns are
+                                   // reused across phases and no tool tracks them); 0 = off
 };
 
 struct PoolArgs {

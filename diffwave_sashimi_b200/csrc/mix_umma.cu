@@ -93,6 +93,17 @@ __device__ __forceinline__ void stat_merge16(const float (&v)[16], int n, float 
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
+// debug: a per-thread pseudo-random sleep of up to `ns` nanoseconds (MixArgs::jitter), keyed on (thread, point)
+__device__ __forceinline__ void jitter_sleep(int ns, unsigned key) {
+    if (ns > 0) {
+        unsigned h = (threadIdx.x * 2654435761u) ^ (key * 40503u + blockIdx.x * 9973u);
+        h ^= h >> 13;
+        h *= 0x5bd1e995u;
+        h ^= h >> 15;
+        __nanosleep(h % (unsigned)ns);
+    }
+}
+
 // ---- epilogue helpers shared by the fused kernels --------------------------------------------
 // channel stride in floats: a compile-time constant for the shapes of the BASELINE configs (the loads
 // and stores of a thread's channels then need no address arithmetic at all: [base + immediate]),
@@ -761,11 +772,13 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
         // read, needed when the next writer of those columns is another epilogue thread rather than an MMA behind an mbarrier.
         auto exchange = [&](uint32_t col, int stride, bool release, float &mean, float &M2) {
             if (CS > 1) {
+                jitter_sleep(a.jitter, col + 1);
                 tmem_st2(tl + col + cg * stride, mean, M2);
                 tmem_wait_st();
                 tc_fence_before();
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(P::EPI) : "memory");
                 tc_fence_after();
+                jitter_sleep(a.jitter, col + 2);
                 float pm[CS], p2[CS];
 #pragma unroll
                 for (int c = 0; c < CS; ++c) tmem_ld2(tl + col + c * stride, pm[c], p2[c]);
@@ -879,6 +892,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
             const bool valid = t < l;
             const size_t brow = (size_t)b * H * l + (valid ? t : 0);
             const int nt = tile + stride;
+            jitter_sleep(a.jitter, 16 * it + 3);
             if (STAGE) take_x(xin, tile, (uint32_t)(it & 1));      // staged a tile ago; x is not live across E2 / E3
             PT(0);
             // ---- E1: GLU + residual -> x1 (TMEM R3 for G3's accumulation, registers for LN2), LN2 statistics
@@ -946,6 +960,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
                 tc_fence_before();
                 mbar_arrive(z_ready);
             }
+            jitter_sleep(a.jitter, 16 * it + 4);
             PT(3);
             // ---- E2: hidden = gelu(W1 z + b1), split, written in place over the accumulator columns as the A operand of G3.
             //      The TMEM load of the next 16 columns is issued before the arithmetic of the current ones.
@@ -1010,6 +1025,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
                 if (nt < ntiles) store_g(gin);
                 take_x(xin, nt, 0);               // requested here, lands during E3
             }
+            jitter_sleep(a.jitter, 16 * it + 5);
             PT(7);
             // ---- E3: x2 = acc3 (= x1 + W2 hidden) + b2 (+skip); store; statistics for the next norm
             {
@@ -1294,11 +1310,13 @@ sashimi_mix_umma256_kernel(MixArgs a) {
         // through R1a columns of this thread's OWN value range (all of its E1 reads are done; a partner may still be reading
         // its own columns of R1a); the next writer of R1a is G2(0), issued after every thread has arrived on z_ready
         auto exchange = [&](float &mean, float &M2) {
+            jitter_sleep(a.jitter, 1);
             tmem_st2(tl + C::R1 + cg * PP, mean, M2);
             tmem_wait_st();
             tc_fence_before();
             asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
             tc_fence_after();
+            jitter_sleep(a.jitter, 2);
             float pm[CS], p2[CS];
 #pragma unroll
             for (int c = 0; c < CS; ++c) tmem_ld2(tl + C::R1 + c * PP, pm[c], p2[c]);
@@ -1324,6 +1342,7 @@ sashimi_mix_umma256_kernel(MixArgs a) {
             float piv = 0.f;
 #pragma unroll 1
             for (int nc = 0; nc < C::NC1; ++nc) {
+                jitter_sleep(a.jitter, 4 + nc);
                 mbar_wait(acc1_ready + nc, 0);
                 tc_fence_after();
                 const uint32_t r1 = tl + C::r1(nc);
@@ -1396,6 +1415,7 @@ sashimi_mix_umma256_kernel(MixArgs a) {
         // ---- E2: hidden = gelu(W1 z + b1), split, in place over the accumulator columns (A operand of G3, K chunk 2 nc + cg)
 #pragma unroll 1
         for (int nc = 0; nc < C::NC1; ++nc) {
+            jitter_sleep(a.jitter, 8 + nc);
             mbar_wait(acc2_ready + nc, 0);
             tc_fence_after();
             const uint32_t r1 = tl + C::r1(nc);
@@ -1694,6 +1714,8 @@ bool mix_reverse_order() {
 int mix_umma_launch(const MixArgs &a_in, int B, cudaStream_t st) {
     MixArgs a = a_in;
     a.rev = mix_reverse_order() ? 1 : 0;
+    static const int jitter = [] { const char *e = getenv("DWB_DEBUG_JITTER"); return e ? atoi(e) : 0; }();
+    a.jitter = jitter;
     DWB_REQUIRE(a.Wimg && a.bimg, DWB_ERR_STATE, "mix_umma: weights were not packed");
     DWB_REQUIRE((int64_t)a.H * a.l < (int64_t)1 << 31, DWB_ERR_UNSUPPORTED, "mix_umma: H*l = %lld needs 64-bit channel offsets",
                 (long long)a.H * a.l);
