@@ -1663,10 +1663,10 @@ static int make_tmap_rows(CUtensorMap *tm, const float *base, uint64_t rows, uin
     return DWB_OK;
 }
 
-template <int H, int CS, int LC>
+template <int H, int CS, int LC, bool STAGE>
 static int launch_umma_pers(const MixArgs &a, int B, cudaStream_t st) {
     using P = PCfg<H, CS>;
-    auto k = sashimi_mix_umma_pers_kernel<H, CS, LC, (LC != 0)>;      // the BASELINE lengths take their inputs through bulk copies
+    auto k = sashimi_mix_umma_pers_kernel<H, CS, LC, STAGE>;
     static int sms[16] = {};
     int dev = 0;
     DWB_CUDA(cudaGetDevice(&dev));
@@ -1680,7 +1680,7 @@ static int launch_umma_pers(const MixArgs &a, int B, cudaStream_t st) {
     CUtensorMap tm_x, tm_g;
     memset(&tm_x, 0, sizeof(tm_x));
     memset(&tm_g, 0, sizeof(tm_g));
-    if (LC != 0) {      // staged inputs: (B*H, l) fp32 row-major, boxes of [H rows x 128 steps]
+    if (STAGE) {        // staged inputs: (B*H, l) fp32 row-major, boxes of [H rows x 128 steps]
         int rc = make_tmap_rows(&tm_x, a.x, (uint64_t)B * H, (uint64_t)a.l, H, UM_TT);
         if (rc == DWB_OK) rc = make_tmap_rows(&tm_g, a.g, (uint64_t)B * H, (uint64_t)a.l, H, UM_TT);
         if (rc != DWB_OK) return rc;
@@ -1689,18 +1689,19 @@ static int launch_umma_pers(const MixArgs &a, int B, cudaStream_t st) {
     DWB_LAUNCH_CHECK();
     return DWB_OK;
 }
-// the stage lengths of the BASELINE configs get a compile-time channel stride (LC), every other length the generic kernel
+// Inputs are staged by TMA whenever the rows are 16-byte aligned (l % 4 == 0, aligned base pointers); the stage lengths of the
+// BASELINE configs additionally get a compile-time channel stride (LC) for the remaining strided accesses (skip, output).
 template <int H, int CS>
 static int launch_umma_pers_l(const MixArgs &a, int B, cudaStream_t st) {
     static const bool nostage = [] { const char *e = getenv("DWB_UMMA_STAGE"); return e && atoi(e) == 0; }();
-    // bulk copies need 16-byte aligned rows: l % 4 == 0 (true for the lengths below) and aligned base pointers
-    if (nostage || ((reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.x)) & 15)) return launch_umma_pers<H, CS, 0>(a, B, st);
+    if (nostage || (a.l & 3) || a.l < UM_TT || ((reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.x)) & 15))
+        return launch_umma_pers<H, CS, 0, false>(a, B, st);
     switch (a.l) {
-        case 16000: return launch_umma_pers<H, CS, 16000>(a, B, st);
-        case 4000: return launch_umma_pers<H, CS, 4000>(a, B, st);
-        case 1000: return launch_umma_pers<H, CS, 1000>(a, B, st);
+        case 16000: return launch_umma_pers<H, CS, 16000, true>(a, B, st);
+        case 4000: return launch_umma_pers<H, CS, 4000, true>(a, B, st);
+        case 1000: return launch_umma_pers<H, CS, 1000, true>(a, B, st);
     }
-    return launch_umma_pers<H, CS, 0>(a, B, st);
+    return launch_umma_pers<H, CS, 0, true>(a, B, st);
 }
 
 // Serpentine order between consecutive kernels: the S4 convolution walks the batch forwards, the mixing kernel
