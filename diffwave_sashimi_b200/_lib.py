@@ -5,7 +5,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdwb.so")
+LIB_PATH = os.environ.get("DWB_LIB") or os.path.join(HERE, "libdwb.so")      # DWB_LIB: an alternative build of the same ABI (A/B runs)
 
 DWB_MAX_POOL = 4
 MODEL_WAVENET, MODEL_SASHIMI = 0, 1

@@ -1005,13 +1005,11 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
             }
             PT(5);
             // ---- once G3 has been awaited the A operand columns are free: the next tile's g goes in and G1(next) runs under E3
-            float sk[STAGE ? PER : 1];            // the UNet skip of this tile: requested before the wait for G3, added in E3
+            // (the UNet skip is loaded 16 channels at a time inside E3: requesting the whole thread's share before the wait for G3
+            //  hides its latency but costs ~23 spilled registers under the 96-register cap of this 608-thread CTA - measured on one
+            //  box with tools/ab_lib.py: 19.44 clips/s with the prefetch, 20.10 without)
             const float *sp = a.skip ? a.skip + brow + (size_t)cg * PER * l : nullptr;
             if (STAGE) {
-                if (sp) {
-#pragma unroll
-                    for (int i = 0; i < PER; ++i) sk[i] = valid ? __ldg(chan<LC>(sp, i, l)) : 0.f;
-                }
                 mbar_wait(acc3_ready, ph);
                 tc_fence_after();
                 PT(6);
@@ -1039,16 +1037,13 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
                     tmem_ld16(tl + P::R3 + h0, v);
                     const float *bb = b2_s + h0;
                     if (sp) {
-                        float skl[16];
-                        if (!STAGE) {
+                        float sk[16];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) skl[i] = valid ? __ldg(chan<LC>(sp, sc * 16 + i, l)) : 0.f;
-                        }
+                        for (int i = 0; i < 16; ++i) sk[i] = valid ? __ldg(chan<LC>(sp, sc * 16 + i, l)) : 0.f;
                         tmem_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
-                            const s2::V2 kk = STAGE ? s2::V2(sk[(sc * 16 + i) % (STAGE ? PER : 1)], sk[(sc * 16 + i + 1) % (STAGE ? PER : 1)]) : s2::V2(skl[i], skl[i + 1]);
-                            const s2::V2 y = (s2::V2(v[i], v[i + 1]) + s2::V2(bb[i], bb[i + 1])) + kk;
+                            const s2::V2 y = (s2::V2(v[i], v[i + 1]) + s2::V2(bb[i], bb[i + 1])) + s2::V2(sk[i], sk[i + 1]);
                             v[i] = y.v.x;
                             v[i + 1] = y.v.y;
                         }
