@@ -124,12 +124,13 @@ mix_gemm_umma_kernel(MixGemmArgs a) {
             lsh = a.ln_m - ms.x;
         }
         const float *Ab = a.A + (size_t)b * a.K * l + tcl;
+        const unsigned rowb = 4u * (unsigned)l;           // channel stride in bytes: one IMAD.WIDE per access instead of a live pointer each
 #pragma unroll 1
         for (int kc = cg; kc < KC; kc += MG_NSU) {
             float v[64];
-            const float *ap = Ab + (size_t)kc * 64 * l;
+            const char *ap = reinterpret_cast<const char *>(Ab + (size_t)kc * 64 * l);
 #pragma unroll
-            for (int i = 0; i < 64; ++i, ap += l) v[i] = valid ? __ldg(ap) : 0.f;
+            for (int i = 0; i < 64; ++i) v[i] = valid ? __ldg(reinterpret_cast<const float *>(ap + (unsigned long long)rowb * (unsigned)i)) : 0.f;
             if (a.stats) {
 #pragma unroll
                 for (int i = 0; i < 64; ++i) v[i] = valid ? lsc * (v[i] + lsh) : 0.f;
@@ -152,9 +153,9 @@ mix_gemm_umma_kernel(MixGemmArgs a) {
             // columns [0,64): a-rows of channels 64 nt + .., [64,128): their gate rows; this thread: 32 channels
             const int h0 = nt * 64 + cg * 32;
             float xin[32];
-            const float *xp = a.x + ((size_t)b * a.H + h0) * l + tcl;
+            const char *xp = reinterpret_cast<const char *>(a.x + ((size_t)b * a.H + h0) * l + tcl);
 #pragma unroll
-            for (int i = 0; i < 32; ++i, xp += l) xin[i] = valid ? __ldg(xp) : 0.f;
+            for (int i = 0; i < 32; ++i) xin[i] = valid ? __ldg(reinterpret_cast<const float *>(xp + (unsigned long long)rowb * (unsigned)i)) : 0.f;
             mbar_wait(acc_ready, 0);
             tc_fence_after();
             float *op = a.out + ((size_t)b * a.H + h0) * l + tcl;
@@ -178,13 +179,13 @@ mix_gemm_umma_kernel(MixGemmArgs a) {
             const int n0 = nt * 128 + cg * 64;
             float pre[64];
             if (EPI == MG_RES) {
-                const float *xp = a.x + ((size_t)b * a.H + n0) * l + tcl;
+                const char *xp = reinterpret_cast<const char *>(a.x + ((size_t)b * a.H + n0) * l + tcl);
 #pragma unroll
-                for (int i = 0; i < 64; ++i, xp += l) pre[i] = valid ? *xp : 0.f;       // x1 (written by G1: plain loads)
+                for (int i = 0; i < 64; ++i) pre[i] = valid ? *reinterpret_cast<const float *>(xp + (unsigned long long)rowb * (unsigned)i) : 0.f;   // x1 (written by G1: plain loads)
                 if (a.skip) {
-                    const float *sp = a.skip + ((size_t)b * a.H + n0) * l + tcl;
+                    const char *sp = reinterpret_cast<const char *>(a.skip + ((size_t)b * a.H + n0) * l + tcl);
 #pragma unroll
-                    for (int i = 0; i < 64; ++i, sp += l) pre[i] += valid ? __ldg(sp) : 0.f;
+                    for (int i = 0; i < 64; ++i) pre[i] += valid ? __ldg(reinterpret_cast<const float *>(sp + (unsigned long long)rowb * (unsigned)i)) : 0.f;
                 }
             }
             mbar_wait(acc_ready, 0);

@@ -122,9 +122,11 @@ pool_umma_kernel(PoolUmmaArgs a) {
         for (int kc = cg; kc < KC; kc += PU_NSU) {
             float v[64];
             if (UP) {
-                const float *ap = a.x + ((size_t)b * a.Hi + (size_t)kc * 64) * li + cc;
+                const char *ap = reinterpret_cast<const char *>(a.x + ((size_t)b * a.Hi + (size_t)kc * 64) * li + cc);
+                const unsigned rowb = 4u * (unsigned)li;                     // one IMAD.WIDE per load instead of a live pointer each
 #pragma unroll
-                for (int i = 0; i < 64; ++i, ap += li) v[i] = valid ? __ldg(ap) : 0.f;
+                for (int i = 0; i < 64; ++i)
+                    v[i] = valid ? __ldg(reinterpret_cast<const float *>(ap + (unsigned long long)rowb * (unsigned)i)) : 0.f;
             } else {
                 // k = h*S + j: the S consecutive samples of input channel h that feed output step c
                 constexpr int CH = 64 / S;
