@@ -114,6 +114,7 @@ struct dwb_plan {
     float *init_w = nullptr, *init_b = nullptr;
     float *Wf_t = nullptr, *bf = nullptr, *wz = nullptr;
     uint4 *Wf_f[2] = {nullptr, nullptr};      // split-bf16 A fragments of the head's C -> C weight
+    uint8_t *Wf_img = nullptr;                // tcgen05 head (pool_umma.cu)
     float bz = 0.f, norm_m = 0.f, norm_s = 1.f;
     int headC = 0;
 
@@ -325,6 +326,14 @@ static int finalize_head(dwb_plan *p, int C, cudaStream_t st) {
             p->Wf_f[q] = (uint4 *)d;
         }
         TRY(frag_pack(p->Wf_t, C, C, (uint32_t *)p->Wf_f[0], (uint32_t *)p->Wf_f[1], st));
+        p->launches += 1;
+    }
+    // DWB_HEAD=mma keeps the mma.sync head
+    static const bool head_mma_only = [] { const char *e = getenv("DWB_HEAD"); return e && std::string(e) == "mma"; }();
+    if (p->use_mma && p->use_umma && !head_mma_only && head_umma_supported(C)) {
+        void *d;
+        TRY(dev_alloc(p, head_umma_image_bytes(C), &d)); p->Wf_img = (uint8_t *)d;
+        TRY(head_umma_pack(C, p->Wf_t, p->Wf_img, st));
         p->launches += 1;
     }
     return DWB_OK;
@@ -791,7 +800,8 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
     h.out = out; h.l = L;
     if (upd) { h.upd_x = upd->x; h.ctl = upd->ctl; h.noise_base = upd->noise_base; }
     h.Wf_fh = p->Wf_f[0]; h.Wf_fl = p->Wf_f[1];
-    if (h.Wf_fh) TRY(head_mma_launch(h, B, st));
+    if (p->Wf_img) TRY(head_umma_launch(h, p->Wf_img, B, st));
+    else if (h.Wf_fh) TRY(head_mma_launch(h, B, st));
     else TRY(head_launch(h, B, st));
     p->launches += 1;
     PROF(DWB_PROF_HEAD);

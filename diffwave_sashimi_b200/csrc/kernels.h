@@ -90,6 +90,10 @@ bool pool_umma_supported(int Hi, int Ho, int s, bool up, int li);
 size_t pool_umma_image_bytes(int Hi, int Ho, int s, bool up);
 int pool_umma_pack(int Hi, int Ho, int s, bool up, const float *W_t, uint8_t *img, cudaStream_t st);
 int pool_umma_launch(const PoolArgs &a, const uint8_t *Wimg, bool up, int B, cudaStream_t st);
+bool head_umma_supported(int C);
+size_t head_umma_image_bytes(int C);
+int head_umma_pack(int C, const float *Wf_t, uint8_t *img, cudaStream_t st);
+int head_umma_launch(const HeadArgs &h, const uint8_t *Wimg, int B, cudaStream_t st);
 bool mix_umma_supported(int H, int F, int l);
 size_t mix_umma_image_bytes(int H);
 int mix_umma_pack(int H, const float *Wo_t, const float *W1_t, const float *W2_t, const float *bo, const float *b1,

@@ -11,6 +11,10 @@
 // swizzled, consumption order (kc, n-tile)) through a three-stage bulk-copy ring; three MMAs per product
 // (hi*hi + lo*hi + hi*lo).  Because a CTA holds every output channel of its steps, the epilogue thread that owns a
 // step computes the next block's TransposedLN statistics itself (up: s statistics per thread, one per sub-step).
+//
+// The output head (models/sashimi.py:310-312, wavenet.py:205-209) is the third mode of the same kernel:
+//   eps = wz . relu(Wf LN(x) prescale + bf) + bz,  then the DDPM update  x <- (x - c1 eps)/sqrt(alpha) (+ sigma z)
+// (generate.py:52-54): the loader applies the final LayerNorm, the epilogue thread reduces its columns against wz.
 #include "common.cuh"
 #include "fft_simd2.cuh"
 #include "kernels.h"
@@ -27,17 +31,27 @@ constexpr int PU_NBAR = 2 * PU_NSW + 2 * PU_NSU + 1;
 constexpr int PU_SMEM = PU_OFF_BAR + PU_NBAR * 8 + 16 + 1024;
 
 struct PoolUmmaArgs {
-    const float *x;                // down: (B,Hi,li)          up: (B,Hi,li)
+    const float *x;                // down: (B,Hi,li)          up / head: (B,Hi,li)
     const float *skip;             // up only: (B,Ho,li*s) or null
     const uint8_t *Wimg;           // stages (kc, n-tile), 32 KB each
     const float *bias;             // (M)
-    float *out, *stats_out;        // down: (B,Ho,li/s), (B,li/s,2)   up: (B,Ho,li*s), (B,li*s,2)
+    float *out, *stats_out;        // down: (B,Ho,li/s), (B,li/s,2)   up: (B,Ho,li*s), (B,li*s,2)   head: (B,li), unused
     int Hi, Ho, li, K, M;
+    // head only
+    const float *stats;            // (B,li,2) final LayerNorm statistics or null
+    float ln_m, ln_s, prescale;
+    const float *wz;               // (M)
+    float bz;
+    const float *upd_x, *ctl;      // fused DDPM update (HeadArgs)
+    const float *const *noise_base;
 };
 
-template <bool UP, int S>
+enum { PU_DOWN = 0, PU_UP = 1, PU_HEAD = 2 };
+
+template <int MODE, int S>
 __global__ void __launch_bounds__(PU_THREADS, 1)
 pool_umma_kernel(PoolUmmaArgs a) {
+    constexpr bool UP = MODE != PU_DOWN;          // A operand = one sample per input channel (up pool, head)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *slabs = sm, *ring = sm + PU_OFF_RING;
@@ -49,7 +63,8 @@ pool_umma_kernel(PoolUmmaArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, t0 = blockIdx.x * 128;
     const int li = a.li, lo = UP ? li * S : li / S, lc = UP ? li : lo;      // lc: steps of the GEMM's M dimension
-    const int KC = a.K / 64, NC = a.M / 128;
+    const int KC = a.K / 64, NC = (a.M + 127) / 128;
+    const int ncols = a.M < 128 ? a.M : 128;        // columns of one accumulator (head with C = 64: one 64-wide tile)
     if (tid == 0) {
         for (int i = 0; i < PU_NSW; ++i) {
             mbar_init(wfull + i, 1);
@@ -62,7 +77,8 @@ pool_umma_kernel(PoolUmmaArgs a) {
         mbar_init(acc_ready, 1);
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc(tptr, (uint32_t)a.M);
+    const uint32_t tcols = (uint32_t)(NC * 128 > 64 ? NC * 128 : 64);       // a power of two >= 32
+    if (warp == 9) tmem_alloc(tptr, tcols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -83,7 +99,7 @@ pool_umma_kernel(PoolUmmaArgs a) {
         // ================= MMA issuer ==========================================================
         if (lane == 0) {
             const uint32_t slab0 = smem_u32(slabs), ring0 = smem_u32(ring);
-            constexpr uint32_t idesc = idesc_bf16(128, 128);
+            const uint32_t idesc = idesc_bf16(128, ncols);
             int i = 0;
 #pragma unroll 1
             for (int kc = 0; kc < KC; ++kc) {
@@ -118,6 +134,12 @@ pool_umma_kernel(PoolUmmaArgs a) {
         const bool valid = c < lc;
         const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
         const size_t cc = valid ? c : 0;
+        float hsc = a.prescale, hsh = 0.f;
+        if (MODE == PU_HEAD && a.stats && valid) {
+            const float2 ms = *reinterpret_cast<const float2 *>(a.stats + ((size_t)b * li + c) * 2);
+            hsc = a.ln_s * ms.y * a.prescale;
+            hsh = (a.ln_m - ms.x) * hsc;
+        }
 #pragma unroll 1
         for (int kc = cg; kc < KC; kc += PU_NSU) {
             float v[64];
@@ -127,6 +149,10 @@ pool_umma_kernel(PoolUmmaArgs a) {
 #pragma unroll
                 for (int i = 0; i < 64; ++i)
                     v[i] = valid ? __ldg(reinterpret_cast<const float *>(ap + (unsigned long long)rowb * (unsigned)i)) : 0.f;
+                if (MODE == PU_HEAD) {           // v = (ln_s rstd)(x - mean + ln_m) prescale
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) v[i] = valid ? fmaf(v[i], hsc, hsh) : 0.f;
+                }
             } else {
                 // k = h*S + j: the S consecutive samples of input channel h that feed output step c
                 constexpr int CH = 64 / S;
@@ -159,7 +185,34 @@ pool_umma_kernel(PoolUmmaArgs a) {
         mbar_wait(acc_ready, 0);
         tc_fence_after();
         const int MH = a.M / 2, n0 = cg * MH;                  // this thread's output columns [n0, n0 + MH)
-        if (!UP) {
+        if (MODE == PU_HEAD) {
+            float part = 0.f;
+#pragma unroll 1
+            for (int sc = 0; sc < MH / 16; ++sc) {
+                float v[16];
+                tmem_ld16(tl + n0 + sc * 16, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    part = fmaf(__ldg(a.wz + n0 + sc * 16 + i), fmaxf(v[i] + __ldg(a.bias + n0 + sc * 16 + i), 0.f), part);
+            }
+            reinterpret_cast<float *>(ex)[cg * 128 + r] = part;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (cg == 0 && valid) {
+                const float e = a.bz + (reinterpret_cast<float *>(ex)[r] + reinterpret_cast<float *>(ex)[128 + r]);
+                const size_t o = (size_t)b * li + c;
+                if (a.upd_x) {
+                    // x <- (x - c1 eps) / sqrt(alpha) (+ sigma z)           generate.py:52-54
+                    const float c1 = __ldg(a.ctl), sqrt_alpha = __ldg(a.ctl + 1), sigma = __ldg(a.ctl + 2);
+                    const int slot = __float_as_int(__ldg(a.ctl + 3));
+                    float xn = (a.upd_x[o] - c1 * e) / sqrt_alpha;
+                    if (slot >= 0) xn += sigma * (*a.noise_base)[(size_t)slot * gridDim.y * li + o];
+                    a.out[o] = xn;
+                } else {
+                    a.out[o] = e;
+                }
+            }
+        } else if (!UP) {
             float *op = a.out + ((size_t)b * a.Ho + n0) * lo + cc;
             float sd = 0.f, sq = 0.f, piv = 0.f;
 #pragma unroll 1
@@ -260,14 +313,14 @@ pool_umma_kernel(PoolUmmaArgs a) {
     __syncthreads();
     if (warp == 9) {
         tc_fence_after();
-        tmem_dealloc(tmem, (uint32_t)a.M);
+        tmem_dealloc(tmem, tcols);
     }
 }
 
 // image of a transposed weight Wt [K][M]: stages (kc, n-tile) = [128 rows x 64 k] hi block, then lo block (K-major SW128)
 __global__ void pool_umma_pack_kernel(const float *__restrict__ Wt, int K, int M, uint8_t *__restrict__ img) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one (stage, row, 16-byte chunk)
-    const int NC = M / 128;
+    const int NC = (M + 127) / 128;
     if (idx >= (size_t)(K / 64) * NC * 128 * 8) return;
     const size_t stage = idx / (128 * 8);
     const int rem = idx % (128 * 8), row = rem / 8, j8 = rem % 8;
@@ -276,7 +329,7 @@ __global__ void pool_umma_pack_kernel(const float *__restrict__ Wt, int K, int M
     uint32_t hp[4], lp[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float w0 = Wt[(size_t)(k0 + 2 * e) * M + n], w1 = Wt[(size_t)(k0 + 2 * e + 1) * M + n];
+        const float w0 = n < M ? Wt[(size_t)(k0 + 2 * e) * M + n] : 0.f, w1 = n < M ? Wt[(size_t)(k0 + 2 * e + 1) * M + n] : 0.f;
         const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
         const __nv_bfloat16 l0 = __float2bfloat16_rn(w0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(w1 - __bfloat162float(h1));
         hp[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
@@ -308,11 +361,11 @@ int pool_umma_pack(int Hi, int Ho, int s, bool up, const float *W_t, uint8_t *im
     return DWB_OK;
 }
 
-template <bool UP, int S>
+template <int MODE, int S>
 static int launch_pool_umma(const PoolUmmaArgs &g, int B, cudaStream_t st) {
-    auto k = pool_umma_kernel<UP, S>;
+    auto k = pool_umma_kernel<MODE, S>;
     DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PU_SMEM));
-    const int lc = UP ? g.li : g.li / S;
+    const int lc = MODE != PU_DOWN ? g.li : g.li / S;
     k<<<dim3(ceil_div(lc, 128), B), PU_THREADS, PU_SMEM, st>>>(g);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
@@ -327,8 +380,27 @@ int pool_umma_launch(const PoolArgs &a, const uint8_t *Wimg, bool up, int B, cud
     g.Hi = a.Hi; g.Ho = a.Ho; g.li = a.li;
     g.M = up ? a.Ho * a.s : a.Ho;
     g.K = up ? a.Hi : a.Hi * a.s;
-    if (up) return a.s == 4 ? launch_pool_umma<true, 4>(g, B, st) : launch_pool_umma<true, 2>(g, B, st);
-    return a.s == 4 ? launch_pool_umma<false, 4>(g, B, st) : launch_pool_umma<false, 2>(g, B, st);
+    if (up) return a.s == 4 ? launch_pool_umma<PU_UP, 4>(g, B, st) : launch_pool_umma<PU_UP, 2>(g, B, st);
+    return a.s == 4 ? launch_pool_umma<PU_DOWN, 4>(g, B, st) : launch_pool_umma<PU_DOWN, 2>(g, B, st);
+}
+
+// ---- output head: C -> C (+ReLU) -> 1 (+ DDPM update); C in {64, 128, 256, 512}
+bool head_umma_supported(int C) { return C == 64 || C == 128 || C == 256 || C == 512; }
+size_t head_umma_image_bytes(int C) { return (size_t)(C / 64) * ((C + 127) / 128) * PU_STAGE; }
+int head_umma_pack(int C, const float *Wf_t, uint8_t *img, cudaStream_t st) {
+    const size_t total = (size_t)(C / 64) * ((C + 127) / 128) * 128 * 8;
+    pool_umma_pack_kernel<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(Wf_t, C, C, img);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+int head_umma_launch(const HeadArgs &h, const uint8_t *Wimg, int B, cudaStream_t st) {
+    DWB_REQUIRE(Wimg && B <= 65535, DWB_ERR_STATE, "head_umma: weights were not packed");
+    PoolUmmaArgs g{};
+    g.x = h.x; g.Wimg = Wimg; g.bias = h.bf; g.out = h.out;
+    g.Hi = h.C; g.Ho = h.C; g.li = h.l; g.K = h.C; g.M = h.C;
+    g.stats = h.stats; g.ln_m = h.ln_m; g.ln_s = h.ln_s; g.prescale = h.prescale; g.wz = h.wz; g.bz = h.bz;
+    g.upd_x = h.upd_x; g.ctl = h.ctl; g.noise_base = h.noise_base;
+    return launch_pool_umma<PU_HEAD, 1>(g, B, st);
 }
 
 }  // namespace dwb
