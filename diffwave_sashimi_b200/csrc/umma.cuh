@@ -10,6 +10,10 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#ifndef DWB_MBAR_HINT
+#define DWB_MBAR_HINT 20000u      // mbarrier.try_wait suspend-time hint (ns)
+#endif
+
 namespace dwb {
 namespace umma {
 
@@ -36,7 +40,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(20000u)
+        "r"(parity), "r"(DWB_MBAR_HINT)
         : "memory");
 }
 

@@ -342,13 +342,13 @@ def test_errors(dwb):
 
 @pytest.mark.parametrize("variant", [{"DWB_UMMA": "tile"}, {"DWB_UMMA": "pers"}, {"DWB_UMMA_STAGE": "0"}, {"DWB_UMMA256_CS": "2"},
                                      {"DWB_POOL": "mma"}, {"DWB_FFT_TPARK": "0"}, {"DWB_SERPENTINE": "0"}, {"DWB_FFT_PERS": "1"},
-                                     {"DWB_DEBUG_JITTER": "20000"}, {"DWB_DEBUG_JITTER": "3000", "DWB_UMMA256_CS": "2"}])
+                                     {"DWB_HEAD": "mma"}, {"DWB_DEBUG_JITTER": "20000"}, {"DWB_DEBUG_JITTER": "3000", "DWB_UMMA256_CS": "2"}])
 def test_tcgen05_mixing_variants_vs_reference_golden(variant):
     """Every implementation behind an environment switch on the unet d64 path (switches are read once per process ->
     subprocess) against the reference's eps: the per-tile (operands in shared memory) and the persistent (operands in
     TMEM, TMA-staged inputs) mixing kernel, the persistent kernel with register-loaded inputs (the path of sequence
     lengths outside the BASELINE set), the H = 256 kernel with two epilogue threads per step, the mma.sync pools
-    (default: tcgen05), the S4 convolution with its parked rows in global memory (default: tensor memory), forward
+    and head (default: tcgen05), the S4 convolution with its parked rows in global memory (default: tensor memory), forward
     tile order, persistent S4-convolution grid.  DWB_DEBUG_JITTER makes every epilogue thread of the tcgen05 mixing kernels
     sleep a pseudo-random time (up to N ns) at its phase boundaries: the kernels reuse TMEM columns across phases, no tool
     tracks tensor memory, and the two races this round fixed (profiles/sanitizer_r2b.md) only showed under such perturbation."""
