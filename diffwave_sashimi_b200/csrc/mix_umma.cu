@@ -91,7 +91,6 @@ __device__ __forceinline__ void stat_merge16(const float (&v)[16], int n, float 
     M2 += c2 + delta * delta * ((float)n * w);
 }
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // debug: a per-thread pseudo-random sleep of up to `ns` nanoseconds (MixArgs::jitter), keyed on (thread, point)
 __device__ __forceinline__ void jitter_sleep(int ns, unsigned key) {
