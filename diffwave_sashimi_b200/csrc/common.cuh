@@ -34,6 +34,32 @@ struct LaunchCounter {
     int64_t n = 0;
 };
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// A kernel launched through launch_pdl may begin while its predecessor in the stream is still running: its CTAs are
+// scheduled as soon as every CTA of the predecessor has executed pdl_trigger() (or exited) and resources are free, run
+// their input-independent set-up (barrier init, TMEM allocation, weight / twiddle copies) and then block in
+// pdl_wait() until the predecessor has completed and its writes are visible.  EVERY kernel launched this way must
+// call pdl_wait() before it reads or writes anything a predecessor touches; both calls are no-ops in a normal launch.
+// DWB_PDL=1 turns the attribute on; the default is plain stream order (measured faster, see pdl_enabled in api.cu).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -387,6 +387,8 @@ __global__ void __launch_bounds__(FftCfg<LOG2M>::NT)
 fftconv_kernel(const float *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ part_t,
                long long part_stride_b, float ln_m, float ln_s, const float4 *__restrict__ kc,
                const float2 *__restrict__ tw /* W_n^i, i < M */, float *__restrict__ g, int B, int H, int l) {
+    pdl_trigger();          // launched through launch_pdl: let the next kernel's CTAs set up early, ...
+    pdl_wait();             // ... and wait for the previous kernel before touching activations
     fftconv_body<LOG2M, false>(x, stats, part_t, part_stride_b, ln_m, ln_s, kc, tw, g, B, H, l, OlsArgs{});
 }
 
@@ -720,8 +722,8 @@ static int launch_fftconv(const float *x, const float *stats, const float *part_
         DWB_CUDA(cudaFuncSetAttribute(fftconv_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_set[dev & 15] = true;
     }
-    fftconv_kernel<LOG2M><<<B * H, Cfg::NT, Cfg::SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw, g, B, H, l);
-    DWB_LAUNCH_CHECK();
+    DWB_CUDA(launch_pdl(fftconv_kernel<LOG2M>, dim3(B * H), dim3(Cfg::NT), Cfg::SMEM, st, x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw, g,
+                        B, H, l));
     return DWB_OK;
 }
 

@@ -262,6 +262,7 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
     float *twAr = im + Cfg::PLANE, *twAi = twAr + Cfg::NTW0;       // W_Mh^j
     float *twBr = twAi + Cfg::NTW0, *twBi = twBr + Cfg::NTW0;      // W_M^j
     float *midr = twBi + Cfg::NTW0, *midi = midr + Cfg::NMID;
+    pdl_trigger();
     const int tid = threadIdx.x;
     uint32_t tpark = 0;                                            // this thread's 128 TMEM words
     if constexpr (TPARK) {
@@ -293,6 +294,7 @@ fftconv3_kernel(const float *__restrict__ x, const float *__restrict__ stats, co
     }
     __syncthreads();
     bool tw_pending = twimg != nullptr;
+    pdl_wait();             // TMEM and twiddles are set up; the rows below read the previous kernel's output
 
     const int j0 = 2 * tid;                                         // outer-pass butterflies j0, j0 + 1
     const int pb0 = padf(j0);
@@ -811,9 +813,8 @@ static int launch_fftconv3_t(const float *x, const float *stats, const float *pa
     static const bool pers = [] { const char *e = getenv("DWB_FFT_PERS"); return e && atoi(e) == 1; }();
     static const int stagger = [] { const char *e = getenv("DWB_FFT_STAGGER"); return e ? atoi(e) : 0; }();
     const int resident = nsm * Cfg::MINB, grid = pers ? std::min(B * H, resident) : B * H;
-    fftconv3_kernel<LOG2M, COMPACT, TPARK><<<dim3(grid, 1, 1), Cfg::NT, SMEM, st>>>(x, stats, part_t, psb, ln_m, ln_s, (const float4 *)kc, tw,
-                                                                                  tw2, g, scratch, B, H, l, resident, pers ? stagger : 0, twimg[dev & 15]);
-    DWB_LAUNCH_CHECK();
+    DWB_CUDA(launch_pdl(fftconv3_kernel<LOG2M, COMPACT, TPARK>, dim3(grid, 1, 1), dim3(Cfg::NT), SMEM, st, x, stats, part_t, psb, ln_m, ln_s,
+                        (const float4 *)kc, tw, tw2, g, scratch, B, H, l, resident, pers ? stagger : 0, (const float *)twimg[dev & 15]));
     return DWB_OK;
 }
 

@@ -582,6 +582,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
     uint32_t *tptr = reinterpret_cast<uint32_t *>(sm + P::OFF_TPTR);
     uint64_t *wfull = bars + P::NG * P::NBAR_G, *wempty = wfull + P::NS;
 
+    pdl_trigger();          // the next kernel's CTAs may be scheduled as SMs free up (they block in their own pdl_wait)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int l = LC ? LC : a.l, ntx = ceil_div(l, UM_TT), ntiles = B * ntx;
     const int stride = gridDim.x * P::NG;
@@ -616,6 +617,9 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem0 = *tptr;
+    // Everything above (and the resident weight copies below) is independent of the previous kernel's output; from here on
+    // every warp touches activations.  The weight producer of the resident form waits after its copies are in flight.
+    if (!(P::RESIDENT && warp == EPI_WARPS + P::NG)) pdl_wait();
 
     if (STAGE && tid == 0) {
         tma_prefetch_desc(&tm_x);
@@ -670,6 +674,7 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
                     bulk_g2s(wbuf + (size_t)i * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + i);
                 }
             __syncwarp();
+            pdl_wait();
             if (STAGE) stage_producer();
         } else if (lane == 0) {
             int cnt = 0;
@@ -1155,11 +1160,13 @@ sashimi_mix_umma256_kernel(MixArgs a) {
         for (int i = 0; i < 2 * C::NC1 + 1; ++i) mbar_init(acc1_ready + i, 1);
         fence_mbar_init();
     }
+    pdl_trigger();
     if (warp == MW) tmem_alloc(tptr, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tptr;
+    pdl_wait();             // set-up done; everything below reads or writes activations
 
     if (warp == PW) {
         // ================= weight producer =====================================================
@@ -1679,8 +1686,7 @@ static int launch_umma_pers(const MixArgs &a, int B, cudaStream_t st) {
         if (rc == DWB_OK) rc = make_tmap_rows(&tm_g, a.g, (uint64_t)B * H, (uint64_t)a.l, H, UM_TT);
         if (rc != DWB_OK) return rc;
     }
-    k<<<grid, P::NTHREADS, P::SMEM, st>>>(a, B, stagger, mix_reverse_order() ? 1 : 0, tm_x, tm_g);
-    DWB_LAUNCH_CHECK();
+    DWB_CUDA(launch_pdl(k, dim3(grid), dim3(P::NTHREADS), P::SMEM, st, a, B, stagger, mix_reverse_order() ? 1 : 0, tm_x, tm_g));
     return DWB_OK;
 }
 // Inputs are staged by TMA whenever the rows are 16-byte aligned (l % 4 == 0, aligned base pointers); the stage lengths of the
@@ -1725,8 +1731,7 @@ int mix_umma_launch(const MixArgs &a_in, int B, cudaStream_t st) {
         static const int cs = [] { const char *e = getenv("DWB_UMMA256_CS"); return e ? atoi(e) : 4; }();
         auto k = cs == 2 ? sashimi_mix_umma256_kernel<2> : sashimi_mix_umma256_kernel<4>;
         DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U256::SMEM));
-        k<<<dim3(ceil_div(a.l, UM_TT), B), 128 * (cs == 2 ? 2 : 4) + 64, U256::SMEM, st>>>(a);
-        DWB_LAUNCH_CHECK();
+        DWB_CUDA(launch_pdl(k, dim3(ceil_div(a.l, UM_TT), B), dim3(128 * (cs == 2 ? 2 : 4) + 64), U256::SMEM, st, a));
         return DWB_OK;
     }
     // (H = 128 with four epilogue threads per step or a third weight-ring stage measured no gain: 173 / 172 us against

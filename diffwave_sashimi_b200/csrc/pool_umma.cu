@@ -78,11 +78,13 @@ pool_umma_kernel(PoolUmmaArgs a) {
         fence_mbar_init();
     }
     const uint32_t tcols = (uint32_t)(NC * 128 > 64 ? NC * 128 : 64);       // a power of two >= 32
+    pdl_trigger();
     if (warp == 9) tmem_alloc(tptr, tcols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tptr;
+    if (warp != 8) pdl_wait();        // (the weight producer touches packed weights only)
 
     if (warp == 8) {
         // ================= weight producer =====================================================
@@ -366,8 +368,7 @@ static int launch_pool_umma(const PoolUmmaArgs &g, int B, cudaStream_t st) {
     auto k = pool_umma_kernel<MODE, S>;
     DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PU_SMEM));
     const int lc = MODE != PU_DOWN ? g.li : g.li / S;
-    k<<<dim3(ceil_div(lc, 128), B), PU_THREADS, PU_SMEM, st>>>(g);
-    DWB_LAUNCH_CHECK();
+    DWB_CUDA(launch_pdl(k, dim3(ceil_div(lc, 128), B), dim3(PU_THREADS), PU_SMEM, st, g));
     return DWB_OK;
 }
 

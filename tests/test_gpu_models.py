@@ -342,7 +342,7 @@ def test_errors(dwb):
 
 @pytest.mark.parametrize("variant", [{"DWB_UMMA": "tile"}, {"DWB_UMMA": "pers"}, {"DWB_UMMA_STAGE": "0"}, {"DWB_UMMA256_CS": "2"},
                                      {"DWB_POOL": "mma"}, {"DWB_FFT_TPARK": "0"}, {"DWB_SERPENTINE": "0"}, {"DWB_FFT_PERS": "1"},
-                                     {"DWB_HEAD": "mma"}, {"DWB_DEBUG_JITTER": "20000"}, {"DWB_DEBUG_JITTER": "3000", "DWB_UMMA256_CS": "2"}])
+                                     {"DWB_HEAD": "mma"}, {"DWB_PDL": "1"}, {"DWB_DEBUG_JITTER": "20000"}, {"DWB_DEBUG_JITTER": "3000", "DWB_UMMA256_CS": "2"}])
 def test_tcgen05_mixing_variants_vs_reference_golden(variant):
     """Every implementation behind an environment switch on the unet d64 path (switches are read once per process ->
     subprocess) against the reference's eps: the per-tile (operands in shared memory) and the persistent (operands in
