@@ -73,6 +73,7 @@ struct Op {
     bool mma = false;
     bool umma = false;             // tcgen05 path (mix_umma.cu)
     bool gemm = false;             // tcgen05 GEMM-per-contraction path (mix_gemm_umma.cu): widths mix_umma.cu has no tile for
+    bool gemm2 = false;            // ... with 512 output columns per CTA (pool_umma.cu, H = 512); DWB_GEMM=1 keeps the first form
     uint8_t *Wimg = nullptr;
     float *bimg = nullptr;
     int F = 0;
@@ -456,7 +457,14 @@ static int finalize_sashimi(dwb_plan *p, cudaStream_t st) {
                     p->launches += 1;
                 }
                 o.gemm = !o.umma && p->use_mma && p->use_umma && mix_gemm_supported(H, o.F, l);
-                if (o.gemm) {
+                static const bool gemm1_only = [] { const char *e = getenv("DWB_GEMM"); return e && atoi(e) == 1; }();
+                o.gemm2 = o.gemm && !gemm1_only && mix_gemm2_supported(H, o.F, l);
+                if (o.gemm2) {
+                    void *d;
+                    TRY(dev_alloc(p, mix_gemm2_image_bytes(H, o.F), &d)); o.Wimg = (uint8_t *)d;
+                    TRY(mix_gemm2_pack(H, o.F, o.Wo_t, o.W1_t, o.W2_t, o.Wimg, st));
+                    p->launches += 3;
+                } else if (o.gemm) {
                     void *d;
                     TRY(dev_alloc(p, mix_gemm_image_bytes(H, o.F), &d)); o.Wimg = (uint8_t *)d;
                     TRY(mix_gemm_pack(H, o.F, o.Wo_t, o.W1_t, o.W2_t, o.Wimg, st));
@@ -749,8 +757,9 @@ static int run_network(dwb_plan *p, const float *x, const float *part, long long
                 a.W2_fh = o.W2_f[0]; a.W2_fl = o.W2_f[1];
                 a.Wimg = o.Wimg; a.bimg = o.bimg;
                 TRY(o.umma ? mix_umma_launch(a, B, st)
-                           : (o.gemm ? mix_gemm_launch(a, p->hid_buf, B, st) : (o.mma ? mix_mma_launch(a, B, st) : mix_launch(a, B, st))));
-                p->launches += ((lt && r > o.l) ? 3 : 2) + (o.gemm ? 4 : 0);
+                           : (o.gemm2 ? mix_gemm2_launch(a, p->hid_buf, B, st)
+                                      : (o.gemm ? mix_gemm_launch(a, p->hid_buf, B, st) : (o.mma ? mix_mma_launch(a, B, st) : mix_launch(a, B, st)))));
+                p->launches += ((lt && r > o.l) ? 3 : 2) + (o.gemm2 ? 3 : (o.gemm ? 4 : 0));
                 PROF(DWB_PROF_MIX0 + std::min(stage_of(p, o.l), 3));
             } else {
                 PoolArgs a{};
@@ -1254,7 +1263,7 @@ int dwb_plan_mix_block(dwb_plan *p, int block, int exact, const float *g, const 
             if (o.gemm) {
                 float *hid = nullptr;
                 DWB_CUDA(cudaMalloc(&hid, (size_t)B * o.F * o.l * sizeof(float)));
-                int rc = mix_gemm_launch(a, hid, B, (cudaStream_t)stream);
+                int rc = o.gemm2 ? mix_gemm2_launch(a, hid, B, (cudaStream_t)stream) : mix_gemm_launch(a, hid, B, (cudaStream_t)stream);
                 cudaStreamSynchronize((cudaStream_t)stream);
                 cudaFree(hid);
                 return rc;

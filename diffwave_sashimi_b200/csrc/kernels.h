@@ -90,6 +90,12 @@ bool pool_umma_supported(int Hi, int Ho, int s, bool up, int li);
 size_t pool_umma_image_bytes(int Hi, int Ho, int s, bool up);
 int pool_umma_pack(int Hi, int Ho, int s, bool up, const float *W_t, uint8_t *img, cudaStream_t st);
 int pool_umma_launch(const PoolArgs &a, const uint8_t *Wimg, bool up, int B, cudaStream_t st);
+int mix_gemm_channel_stats(const float *x, float *stats, int H, int l, int B, cudaStream_t st);
+// H = 512 block as three pool_umma-style GEMMs with 512 output columns per CTA (pool_umma.cu)
+bool mix_gemm2_supported(int H, int F, int l);
+size_t mix_gemm2_image_bytes(int H, int F);
+int mix_gemm2_pack(int H, int F, const float *Wo_t, const float *W1_t, const float *W2_t, uint8_t *img, cudaStream_t st);
+int mix_gemm2_launch(const MixArgs &a, float *hid, int B, cudaStream_t st);
 bool head_umma_supported(int C);
 size_t head_umma_image_bytes(int C);
 int head_umma_pack(int C, const float *Wf_t, uint8_t *img, cudaStream_t st);

@@ -235,6 +235,12 @@ channel_stats_kernel(const float *__restrict__ x, float *__restrict__ stats, int
     *reinterpret_cast<float2 *>(stats + ((size_t)b * l + t) * 2) = make_float2(mean, rsqrtf(m2 / (float)H));
 }
 
+int mix_gemm_channel_stats(const float *x, float *stats, int H, int l, int B, cudaStream_t st) {
+    channel_stats_kernel<<<dim3(ceil_div(l, 256), B), 256, 0, st>>>(x, stats, H, l);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+
 // images: G1 (H/64 tiles x H/64 chunks) | G2 (F/128 x H/64) | G3 (H/128 x F/64), 32 KB per stage
 __global__ void mix_gemm_pack_kernel(const float *__restrict__ Wo_t, const float *__restrict__ W1_t, const float *__restrict__ W2_t,
                                      int H, int F, uint8_t *__restrict__ img) {

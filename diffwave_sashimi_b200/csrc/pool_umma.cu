@@ -15,6 +15,12 @@
 // The output head (models/sashimi.py:310-312, wavenet.py:205-209) is the third mode of the same kernel:
 //   eps = wz . relu(Wf LN(x) prescale + bf) + bz,  then the DDPM update  x <- (x - c1 eps)/sqrt(alpha) (+ sigma z)
 // (generate.py:52-54): the loader applies the final LayerNorm, the epilogue thread reduces its columns against wz.
+//
+// Modes GLU / GELU / RES are the three contractions of a DiffWaveBlock whose width does not fit the fused mixing kernels
+// (H = 512, the centre stage of unet d128; models/sashimi.py:157-182): the same CTA shape with 512 output columns per CTA
+// (blockIdx.z selects the column half of the 2H / F wide products), so an A chunk is loaded and split once for four
+// accumulators instead of once per 128 columns as in mix_gemm_umma.cu, and G3 - which sees all H channels - writes the
+// next LayerNorm's statistics itself.
 #include "common.cuh"
 #include "fft_simd2.cuh"
 #include "kernels.h"
@@ -37,8 +43,13 @@ struct PoolUmmaArgs {
     const float *bias;             // (M)
     float *out, *stats_out;        // down: (B,Ho,li/s), (B,li/s,2)   up: (B,Ho,li*s), (B,li*s,2)   head: (B,li), unused
     int Hi, Ho, li, K, M;
-    // head only
-    const float *stats;            // (B,li,2) final LayerNorm statistics or null
+    // block GEMMs (GLU / GELU / RES)
+    int Mc;                        // output columns of one CTA (<= 512); blockIdx.z = column group; M = all columns
+    const float *res;              // GLU: block input x (B,H,l)   RES: x1 (B,H,l) (= out, in place)
+    const float *cond;             // GLU: (cond_batch,H,l) or null
+    int cond_stride_b;
+    // head and GELU
+    const float *stats;            // (B,li,2) LayerNorm statistics applied to A while loading, or null
     float ln_m, ln_s, prescale;
     const float *wz;               // (M)
     float bz;
@@ -46,7 +57,7 @@ struct PoolUmmaArgs {
     const float *const *noise_base;
 };
 
-enum { PU_DOWN = 0, PU_UP = 1, PU_HEAD = 2 };
+enum { PU_DOWN = 0, PU_UP = 1, PU_HEAD = 2, PU_GLU = 3, PU_GELU = 4, PU_RES = 5 };
 
 template <int MODE, int S>
 __global__ void __launch_bounds__(PU_THREADS, 1)
@@ -63,8 +74,10 @@ pool_umma_kernel(PoolUmmaArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, t0 = blockIdx.x * 128;
     const int li = a.li, lo = UP ? li * S : li / S, lc = UP ? li : lo;      // lc: steps of the GEMM's M dimension
-    const int KC = a.K / 64, NC = (a.M + 127) / 128;
-    const int ncols = a.M < 128 ? a.M : 128;        // columns of one accumulator (head with C = 64: one 64-wide tile)
+    constexpr bool BLK = MODE >= PU_GLU;            // block GEMM: a.Mc of the a.M columns per CTA
+    const int Mcta = BLK ? a.Mc : a.M, zc = BLK ? (int)blockIdx.z : 0;
+    const int KC = a.K / 64, NC = (Mcta + 127) / 128;
+    const int ncols = Mcta < 128 ? Mcta : 128;      // columns of one accumulator (head with C = 64: one 64-wide tile)
     if (tid == 0) {
         for (int i = 0; i < PU_NSW; ++i) {
             mbar_init(wfull + i, 1);
@@ -94,7 +107,7 @@ pool_umma_kernel(PoolUmmaArgs a) {
                 const int s = i % PU_NSW, ph = i / PU_NSW;
                 mbar_wait(wempty + s, (ph & 1) ^ 1);
                 mbar_arrive_expect_tx(wfull + s, PU_STAGE);
-                bulk_g2s(ring + (size_t)s * PU_STAGE, a.Wimg + (size_t)i * PU_STAGE, PU_STAGE, wfull + s);
+                bulk_g2s(ring + (size_t)s * PU_STAGE, a.Wimg + ((size_t)zc * n + i) * PU_STAGE, PU_STAGE, wfull + s);
             }
         }
     } else if (warp == 9) {
@@ -137,7 +150,7 @@ pool_umma_kernel(PoolUmmaArgs a) {
         const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
         const size_t cc = valid ? c : 0;
         float hsc = a.prescale, hsh = 0.f;
-        if (MODE == PU_HEAD && a.stats && valid) {
+        if ((MODE == PU_HEAD || MODE == PU_GELU) && a.stats && valid) {
             const float2 ms = *reinterpret_cast<const float2 *>(a.stats + ((size_t)b * li + c) * 2);
             hsc = a.ln_s * ms.y * a.prescale;
             hsh = (a.ln_m - ms.x) * hsc;
@@ -151,7 +164,7 @@ pool_umma_kernel(PoolUmmaArgs a) {
 #pragma unroll
                 for (int i = 0; i < 64; ++i)
                     v[i] = valid ? __ldg(reinterpret_cast<const float *>(ap + (unsigned long long)rowb * (unsigned)i)) : 0.f;
-                if (MODE == PU_HEAD) {           // v = (ln_s rstd)(x - mean + ln_m) prescale
+                if (MODE == PU_HEAD || MODE == PU_GELU) {           // v = (ln_s rstd)(x - mean + ln_m) prescale
 #pragma unroll
                     for (int i = 0; i < 64; ++i) v[i] = valid ? fmaf(v[i], hsc, hsh) : 0.f;
                 }
@@ -186,8 +199,88 @@ pool_umma_kernel(PoolUmmaArgs a) {
 
         mbar_wait(acc_ready, 0);
         tc_fence_after();
-        const int MH = a.M / 2, n0 = cg * MH;                  // this thread's output columns [n0, n0 + MH)
-        if (MODE == PU_HEAD) {
+        const int MH = Mcta / 2, n0 = cg * MH;                 // this thread's output columns [n0, n0 + MH)
+        if (MODE == PU_GLU) {
+            // accumulator nt holds [64 value | 64 gate] columns of channels 64 (zc NC + nt) ..; this thread: NC / 2 accumulators
+            const unsigned rowb = 4u * (unsigned)li;
+#pragma unroll 1
+            for (int nt = cg * (NC / 2); nt < (cg + 1) * (NC / 2); ++nt) {
+                const int h0 = (zc * NC + nt) * 64;
+                const char *xp = reinterpret_cast<const char *>(a.res + ((size_t)b * a.Ho + h0) * li + cc);
+                char *op = reinterpret_cast<char *>(a.out + ((size_t)b * a.Ho + h0) * li + cc);
+                const char *cb = a.cond ? reinterpret_cast<const char *>(a.cond + ((size_t)(a.cond_stride_b ? b : 0) * a.Ho + h0) * li + cc) : nullptr;
+#pragma unroll 1
+                for (int sc = 0; sc < 4; ++sc) {
+                    float av[16], gv[16], xv[16];
+                    tmem_ld16(tl + nt * 128 + sc * 16, av);
+                    tmem_ld16(tl + nt * 128 + 64 + sc * 16, gv);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        xv[i] = valid ? __ldg(reinterpret_cast<const float *>(xp + (unsigned long long)rowb * (unsigned)(sc * 16 + i))) : 0.f;
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int h = h0 + sc * 16 + i;
+                        float y = (av[i] + __ldg(a.bias + h)) * __fdividef(1.0f, 1.0f + __expf(-(gv[i] + __ldg(a.bias + a.Ho + h))));
+                        if (cb && valid) y += __ldg(reinterpret_cast<const float *>(cb + (unsigned long long)rowb * (unsigned)(sc * 16 + i)));
+                        if (valid) *reinterpret_cast<float *>(op + (unsigned long long)rowb * (unsigned)(sc * 16 + i)) = xv[i] + y;
+                    }
+                }
+            }
+        } else if (MODE == PU_GELU) {
+            const unsigned rowb = 4u * (unsigned)li;
+            const int f0 = zc * Mcta + n0;                      // first of this thread's hidden channels
+            char *op = reinterpret_cast<char *>(a.out + ((size_t)b * a.M + f0) * li + cc);
+#pragma unroll 1
+            for (int sc = 0; sc < MH / 16; ++sc) {
+                float v[16];
+                tmem_ld16(tl + n0 + sc * 16, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float z = gelu_fast(v[i] + __ldg(a.bias + f0 + sc * 16 + i));
+                    if (valid) *reinterpret_cast<float *>(op + (unsigned long long)rowb * (unsigned)(sc * 16 + i)) = z;
+                }
+            }
+        } else if (MODE == PU_RES) {
+            // all H channels of the step in this CTA (Mc = M = H): x2 = x1 + (W2 hid + b2) (+skip), statistics for the next norm
+            const unsigned rowb = 4u * (unsigned)li;
+            const char *xp = reinterpret_cast<const char *>(a.res + ((size_t)b * a.M + n0) * li + cc);
+            const char *sp = a.skip ? reinterpret_cast<const char *>(a.skip + ((size_t)b * a.M + n0) * li + cc) : nullptr;
+            char *op = reinterpret_cast<char *>(a.out + ((size_t)b * a.M + n0) * li + cc);
+            float sd = 0.f, sq = 0.f, piv = 0.f;
+#pragma unroll 1
+            for (int sc = 0; sc < MH / 16; ++sc) {
+                float v[16], pre[16];
+                tmem_ld16(tl + n0 + sc * 16, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const unsigned long long o = (unsigned long long)rowb * (unsigned)(sc * 16 + i);
+                    pre[i] = valid ? *reinterpret_cast<const float *>(xp + o) : 0.f;            // x1 (written by G1: plain loads)
+                    if (sp) pre[i] += valid ? __ldg(reinterpret_cast<const float *>(sp + o)) : 0.f;
+                }
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += pre[i] + __ldg(a.bias + n0 + sc * 16 + i);
+                if (sc == 0) piv = v[0];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float d = v[i] - piv;
+                    sd += d;
+                    sq = fmaf(d, d, sq);
+                    if (valid) *reinterpret_cast<float *>(op + (unsigned long long)rowb * (unsigned)(sc * 16 + i)) = v[i];
+                }
+            }
+            const float inv = 1.0f / (float)MH;
+            ex[cg * 128 + r] = make_float2(fmaf(sd, inv, piv), fmaxf(fmaf(-sd * inv, sd, sq), 0.f));
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (cg == 0 && valid) {
+                const float2 e0 = ex[r], e1 = ex[128 + r];
+                const float mt = 0.5f * (e0.x + e1.x), d0 = e0.x - mt, d1 = e1.x - mt;
+                const float m2 = e0.y + e1.y + (d0 * d0 + d1 * d1) * (float)MH;
+                *reinterpret_cast<float2 *>(a.stats_out + ((size_t)b * li + c) * 2) = make_float2(mt, rsqrtf(m2 / (float)a.M));
+            }
+        } else if (MODE == PU_HEAD) {
             float part = 0.f;
 #pragma unroll 1
             for (int sc = 0; sc < MH / 16; ++sc) {
@@ -320,14 +413,17 @@ pool_umma_kernel(PoolUmmaArgs a) {
 }
 
 // image of a transposed weight Wt [K][M]: stages (kc, n-tile) = [128 rows x 64 k] hi block, then lo block (K-major SW128)
-__global__ void pool_umma_pack_kernel(const float *__restrict__ Wt, int K, int M, uint8_t *__restrict__ img) {
+// nsplit column groups of M / nsplit columns each (stage order: group, kc, n-tile inside the group); glu: tile T of 128
+// rows = value rows 64 T .. | gate rows M/2 + 64 T .. (the pairing the GLU epilogue expects)
+__global__ void pool_umma_pack_kernel(const float *__restrict__ Wt, int K, int M, uint8_t *__restrict__ img, int nsplit, int glu) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one (stage, row, 16-byte chunk)
-    const int NC = (M + 127) / 128;
-    if (idx >= (size_t)(K / 64) * NC * 128 * 8) return;
+    const int NCT = (M + 127) / 128, NC = NCT / nsplit, KC = K / 64;
+    if (idx >= (size_t)KC * NCT * 128 * 8) return;
     const size_t stage = idx / (128 * 8);
     const int rem = idx % (128 * 8), row = rem / 8, j8 = rem % 8;
-    const int kc = (int)(stage / NC), nt = (int)(stage % NC);
-    const int n = nt * 128 + row, k0 = kc * 64 + j8 * 8;
+    const int z = (int)(stage / ((size_t)KC * NC)), kc = (int)((stage / NC) % KC), nt = (int)(stage % NC);
+    const int T = z * NC + nt;
+    const int n = glu ? (row < 64 ? T * 64 + row : M / 2 + T * 64 + (row - 64)) : T * 128 + row, k0 = kc * 64 + j8 * 8;
     uint32_t hp[4], lp[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -358,7 +454,7 @@ size_t pool_umma_image_bytes(int Hi, int Ho, int s, bool up) {
 int pool_umma_pack(int Hi, int Ho, int s, bool up, const float *W_t, uint8_t *img, cudaStream_t st) {
     const int M = up ? Ho * s : Ho, K = up ? Hi : Hi * s;
     const size_t total = (size_t)(K / 64) * (M / 128) * 128 * 8;
-    pool_umma_pack_kernel<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(W_t, K, M, img);
+    pool_umma_pack_kernel<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(W_t, K, M, img, 1, 0);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
 }
@@ -368,7 +464,8 @@ static int launch_pool_umma(const PoolUmmaArgs &g, int B, cudaStream_t st) {
     auto k = pool_umma_kernel<MODE, S>;
     DWB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PU_SMEM));
     const int lc = MODE != PU_DOWN ? g.li : g.li / S;
-    DWB_CUDA(launch_pdl(k, dim3(ceil_div(lc, 128), B), dim3(PU_THREADS), PU_SMEM, st, g));
+    const int nz = MODE >= PU_GLU ? g.M / g.Mc : 1;
+    DWB_CUDA(launch_pdl(k, dim3(ceil_div(lc, 128), B, nz), dim3(PU_THREADS), PU_SMEM, st, g));
     return DWB_OK;
 }
 
@@ -390,7 +487,7 @@ bool head_umma_supported(int C) { return C == 64 || C == 128 || C == 256 || C ==
 size_t head_umma_image_bytes(int C) { return (size_t)(C / 64) * ((C + 127) / 128) * PU_STAGE; }
 int head_umma_pack(int C, const float *Wf_t, uint8_t *img, cudaStream_t st) {
     const size_t total = (size_t)(C / 64) * ((C + 127) / 128) * 128 * 8;
-    pool_umma_pack_kernel<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(Wf_t, C, C, img);
+    pool_umma_pack_kernel<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(Wf_t, C, C, img, 1, 0);
     DWB_LAUNCH_CHECK();
     return DWB_OK;
 }
@@ -402,6 +499,43 @@ int head_umma_launch(const HeadArgs &h, const uint8_t *Wimg, int B, cudaStream_t
     g.stats = h.stats; g.ln_m = h.ln_m; g.ln_s = h.ln_s; g.prescale = h.prescale; g.wz = h.wz; g.bz = h.bz;
     g.upd_x = h.upd_x; g.ctl = h.ctl; g.noise_base = h.noise_base;
     return launch_pool_umma<PU_HEAD, 1>(g, B, st);
+}
+
+// ---- DiffWaveBlock channel mixing as three of these launches (H = 512): images G1 (2H columns, GLU pairing, two column
+// groups) | G2 (F columns, two groups) | G3 (H columns, one group)
+bool mix_gemm2_supported(int H, int F, int l) { return H == 512 && F == 2 * H && l >= 1; }
+size_t mix_gemm2_image_bytes(int H, int F) { return ((size_t)(H / 64) * (2 * H / 128) + (size_t)(H / 64) * (F / 128) + (size_t)(F / 64) * (H / 128)) * PU_STAGE; }
+int mix_gemm2_pack(int H, int F, const float *Wo_t, const float *W1_t, const float *W2_t, uint8_t *img, cudaStream_t st) {
+    const size_t n1 = (size_t)(H / 64) * (2 * H / 128), n2 = (size_t)(H / 64) * (F / 128), n3 = (size_t)(F / 64) * (H / 128);
+    pool_umma_pack_kernel<<<(unsigned)ceil_div64((int64_t)n1 * 128 * 8, 256), 256, 0, st>>>(Wo_t, H, 2 * H, img, 2 * H / 512, 1);
+    pool_umma_pack_kernel<<<(unsigned)ceil_div64((int64_t)n2 * 128 * 8, 256), 256, 0, st>>>(W1_t, H, F, img + n1 * PU_STAGE, F / 512, 0);
+    pool_umma_pack_kernel<<<(unsigned)ceil_div64((int64_t)n3 * 128 * 8, 256), 256, 0, st>>>(W2_t, F, H, img + (n1 + n2) * PU_STAGE, 1, 0);
+    DWB_LAUNCH_CHECK();
+    return DWB_OK;
+}
+// a.Wimg = the three images, a.bo / a.b1 / a.b2 fp32 biases; hid = (B, F, l) workspace; 4 launches (G1, stats(x1), G2, G3 + stats)
+int mix_gemm2_launch(const MixArgs &a, float *hid, int B, cudaStream_t st) {
+    DWB_REQUIRE(a.Wimg && hid && B <= 65535, DWB_ERR_STATE, "mix_gemm2: weights were not packed / no workspace");
+    const int H = a.H, F = a.F, l = a.l;
+    const size_t n1 = (size_t)(H / 64) * (2 * H / 128), n2 = (size_t)(H / 64) * (F / 128);
+    PoolUmmaArgs g{};
+    g.li = l; g.Hi = H; g.Ho = H;
+    // G1: x1 = x + GLU(Wo g + bo) (+cond)
+    g.x = a.g; g.Wimg = a.Wimg; g.bias = a.bo; g.res = a.x; g.cond = a.cond; g.cond_stride_b = a.cond_stride_b; g.out = a.out;
+    g.K = H; g.M = 2 * H; g.Mc = 512;
+    int rc = launch_pool_umma<PU_GLU, 1>(g, B, st);
+    if (rc != DWB_OK) return rc;
+    rc = mix_gemm_channel_stats(a.out, a.stats_out, H, l, B, st);
+    if (rc != DWB_OK) return rc;
+    // G2: hid = gelu(W1 LN2(x1) + b1)
+    g.x = a.out; g.stats = a.stats_out; g.ln_m = a.ln2_m; g.ln_s = a.ln2_s; g.prescale = 1.0f; g.Wimg = a.Wimg + n1 * PU_STAGE; g.bias = a.b1;
+    g.res = nullptr; g.cond = nullptr; g.out = hid; g.K = H; g.M = F; g.Mc = 512;
+    rc = launch_pool_umma<PU_GELU, 1>(g, B, st);
+    if (rc != DWB_OK) return rc;
+    // G3: x2 = x1 + W2 hid + b2 (+skip), statistics of x2
+    g.x = hid; g.stats = nullptr; g.Wimg = a.Wimg + (n1 + n2) * PU_STAGE; g.bias = a.b2; g.res = a.out; g.skip = a.skip;
+    g.out = a.out; g.stats_out = a.stats_out; g.Hi = F; g.K = F; g.M = H; g.Mc = H;
+    return launch_pool_umma<PU_RES, 1>(g, B, st);
 }
 
 }  // namespace dwb

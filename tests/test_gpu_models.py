@@ -371,3 +371,16 @@ def test_tcgen05_mixing_variants_vs_reference_golden(variant):
     rel = float([l for l in r.stdout.splitlines() if l.startswith("REL")][0].split()[1])
     print(f"{variant}: rel_l2 {rel:.2e}")
     assert rel < 1e-4
+
+
+def test_h512_first_gemm_form_vs_oracle():
+    """DWB_GEMM=1 keeps the H = 512 block on mix_gemm_umma.cu (one 128-column tile per CTA) instead of the 512-column form in
+    pool_umma.cu that the default takes (covered by test_tensor_core_mixing_vs_oracle_fp64[128-512-...] and the unet d128 golden);
+    the switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_models.py"), "-m", "gpu", "-x", "-q", "-k",
+                        "tensor_core_mixing_vs_oracle_fp64 and 128-512"], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, DWB_GEMM="1"), cwd=root)
+    assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
