@@ -88,7 +88,8 @@ def kernel_label(kname, cfg, B):
         k = {64: "sashimi_mix_umma_pers_kernel<64,2>", 128: "sashimi_mix_umma_pers_kernel<128,2>",
              256: "sashimi_mix_umma256_kernel"}.get(H)
         if k is None:
-            k = "mix_gemm_umma_kernel x3 + channel_stats_kernel x2" if H % 128 == 0 else f"sashimi_mix_mma_kernel<{H}> (mma.sync)"
+            k = ("pool_umma_kernel<GLU|GELU|RES> + channel_stats_kernel" if H == 512 else "mix_gemm_umma_kernel x3 + channel_stats_kernel x2") \
+                if H % 128 == 0 else f"sashimi_mix_mma_kernel<{H}> (mma.sync)"
         return f"{k} (H={H}, l={l})"
     return kname
 
