@@ -172,7 +172,7 @@ sashimi_mix_umma_kernel(MixArgs a) {
     const int b = a.rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y, t0 = (a.rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * UM_TT, l = a.l;
     long long *trace = a.trace ? a.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
 #define UM_TRACE(slot) do { if (trace && tid == 0) trace[slot] = clock64(); } while (0)
-#define UM_TRACE_MMA(slot) do { if (trace) trace[slot] = clock64(); } while (0)
+#define UM_TRACE_MMA(slot) do { if (trace && lane == 0) trace[slot] = clock64(); } while (0)
     UM_TRACE(0);
 
     // epilogue threads: one time step each (row r of the tile), column group cg
@@ -224,20 +224,23 @@ sashimi_mix_umma_kernel(MixArgs a) {
         }
     } else if (warp == 4 * CS + 1) {
         // ================= MMA issuer ==========================================================
-        if (lane == 0) {
+        {   // all 32 lanes run the loops; the *_w forms elect the issuing lane
             const uint32_t slot0 = smem_u32(slots), ring0 = smem_u32(ring);
             // one [128 x NR] x K=64 block: 3 split terms x 4 k-steps
             auto issue_block = [&](uint32_t d, uint32_t abase, uint32_t bbase, int NR, bool acc0) {
                 const uint32_t idesc = idesc_bf16(128, NR);
+                if (elect_one()) {      // one election per block of 12 MMAs
 #pragma unroll
-                for (int term = 0; term < 3; ++term) {
-                    const uint32_t ao = abase + (term == 1 ? UM_SLOT / 2 : 0);
-                    const uint32_t bo = bbase + (term == 2 ? NR * 128 : 0);
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t ao = abase + (term == 1 ? UM_SLOT / 2 : 0);
+                        const uint32_t bo = bbase + (term == 2 ? NR * 128 : 0);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_bf16_ss(d, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
-                                    (acc0 || term > 0 || ks > 0) ? 1u : 0u);
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_bf16_ss(d, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
+                                        (acc0 || term > 0 || ks > 0) ? 1u : 0u);
+                    }
                 }
+                __syncwarp();
             };
             int i = 0;
 #pragma unroll 1
@@ -253,9 +256,9 @@ sashimi_mix_umma_kernel(MixArgs a) {
                         mbar_wait(wfull + s, (i / C::NS) & 1);
                         tc_fence_after();
                         issue_block(tmem + nc * 128, slot0 + kc * UM_SLOT, ring0 + s * UM_STAGE, 128, kc > 0);
-                        mma_commit(wempty + s);
+                        mma_commit_w(wempty + s);
                     }
-                    mma_commit((gemm == 0 ? acc1_ready : acc2_ready) + nc);
+                    mma_commit_w((gemm == 0 ? acc1_ready : acc2_ready) + nc);
                 }
             }
 #pragma unroll 1
@@ -272,12 +275,12 @@ sashimi_mix_umma_kernel(MixArgs a) {
                     issue_block(tmem + C::R3 + nc * 128, slot0 + C::hid_slot(kc) * UM_SLOT,
                                 ring0 + s * UM_STAGE + (j % C::BPS3) * C::NR3 * 256, C::NR3, true);
                     if (j % C::BPS3 == C::BPS3 - 1) {
-                        mma_commit(wempty + s);
+                        mma_commit_w(wempty + s);
                         ++i;
                     }
                 }
             }
-            mma_commit(acc3_ready);
+            mma_commit_w(acc3_ready);
             UM_TRACE_MMA(14);
         }
     } else {
@@ -549,7 +552,7 @@ struct PCfg {
     // warps: NG epilogue groups | NG MMA issuers | weight producer | (streaming weights only) input-staging producer;
     // with resident weights the weight producer is idle after its first copies and stages the inputs itself
     static constexpr int NTHREADS = NG * EPI + NG * 32 + 32 + (RESIDENT ? 0 : 32);
-    static constexpr int NS = RESIDENT ? U::NSTG : 2;          // weight buffers (RESIDENT: one per stage; a third streaming stage measured no gain)
+    static constexpr int NS = RESIDENT ? U::NSTG : 3;          // weight buffers (RESIDENT: one per stage)
     // biases in shared memory.  (H = 128 measured with a third ring stage in their place and the biases through L1:
     // 191 us against 167 us - the uniform bias loads sit on the epilogues' critical path.)
     static constexpr bool BIAS_SMEM = true;
@@ -563,7 +566,9 @@ struct PCfg {
     static constexpr int OFF_BIAS = OFF_W + NS * UM_STAGE;
     static constexpr int OFF_BAR = OFF_BIAS + (BIAS_SMEM ? 5 * H * 4 : 0);
     static constexpr int OFF_TPTR = OFF_BAR + NBAR * 8;
-    static constexpr int SMEM = OFF_TPTR + 16 + 1024;          // + alignment slack
+    // no alignment slack: the third ring stage of H = 128 leaves 328 bytes.  Dynamic shared memory starts 1024-aligned when a
+    // kernel has no static shared memory; the kernel checks it and traps otherwise
+    static constexpr int SMEM = OFF_TPTR + 16;
     static_assert(4 * H <= GCOLS, "TMEM budget: accumulator (2H) + x1 (H) + A operand (H) columns per group");
     static_assert(SMEM <= 227 * 1024, "persistent tile set does not fit shared memory");
 };
@@ -575,7 +580,8 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
     using P = PCfg<H, CS>;
     using C = UCfg<H, CS>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sm = smem_raw;
+    if (smem_u32(smem_raw) & 1023u) __trap();                   // SW128 operands and TMA boxes need the 1024-byte alignment
     uint8_t *wbuf = sm + P::OFF_W;
     float *bias_s = reinterpret_cast<float *>(sm + P::OFF_BIAS);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + P::OFF_BAR);
@@ -689,9 +695,9 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
     } else if (warp >= EPI_WARPS + P::NG) {
         // (staging warp of an instantiation without staging: nothing to do)
     } else if (warp >= EPI_WARPS) {
-        // ================= MMA issuer of group grp ==============================================
+        // ================= MMA issuer of group grp (all 32 lanes run the loops; one elected lane issues) ==========
         const int grp = warp - EPI_WARPS;
-        if (lane == 0) {
+        {
             uint64_t *gb = bars + grp * P::NBAR_G;
             uint64_t *g_ready = gb, *z_ready = gb + 1, *hid_ready = gb + 2, *acc1_ready = hid_ready + C::KC3,
                      *acc2_ready = acc1_ready + C::NC1, *acc3_ready = acc2_ready + C::NC1;
@@ -700,59 +706,79 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
             // one [128 x NR] x K = 64 block, A operand in TMEM ([8 hi | 8 lo] columns per K = 16 step): 3 split terms x 4 k-steps
             auto issue_block = [&](uint32_t d, uint32_t a_tmem, uint32_t bbase, int NR, bool acc0) {
                 const uint32_t idesc = idesc_bf16(128, NR);
+                if (elect_one()) {
 #pragma unroll
-                for (int term = 0; term < 3; ++term) {
-                    const uint32_t ao = a_tmem + (term == 1 ? 8 : 0);
-                    const uint32_t bo = bbase + (term == 2 ? NR * 128 : 0);
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t ao = a_tmem + (term == 1 ? 8 : 0);
+                        const uint32_t bo = bbase + (term == 2 ? NR * 128 : 0);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_bf16_ts(d, ao + ks * 16, smem_desc_sw128(bo + ks * 32), idesc, (acc0 || term > 0 || ks > 0) ? 1u : 0u);
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_bf16_ts(d, ao + ks * 16, smem_desc_sw128(bo + ks * 32), idesc, (acc0 || term > 0 || ks > 0) ? 1u : 0u);
+                    }
                 }
+                __syncwarp();
+            };
+            auto commit = [&](uint64_t *bar) {
+                if (elect_one()) mma_commit(bar);
+                __syncwarp();
             };
             int cnt = 0;     // weight stages consumed so far (ring position when streaming)
             uint32_t ph = 0;
+            // debug trace (a.trace): cycles the issuer of group 0 spends waiting, second tile: [10] g/z operands, [11] weights, [12] hidden chunks, [13] whole tile
+            const bool mtr = trace && grp == 0;
+            long long w_op = 0, w_wt = 0, w_hid = 0, t_tile = 0;
+            int mit = 0;
+#define MW(acc, stmt) do { if (mtr && mit == 1) { const long long c0_ = clock64(); stmt; acc += clock64() - c0_; } else { stmt; } } while (0)
 #pragma unroll 1
-            for (int tile = blockIdx.x * P::NG + grp; tile < ntiles; tile += stride, ph ^= 1) {
+            for (int tile = blockIdx.x * P::NG + grp; tile < ntiles; tile += stride, ph ^= 1, ++mit) {
+                if (mtr && mit == 1) t_tile = clock64();
                 int i = 0;   // stage index inside the tile
 #pragma unroll 1
                 for (int gemm = 0; gemm < 2; ++gemm) {
-                    mbar_wait(gemm == 0 ? g_ready : z_ready, ph);
+                    MW(w_op, mbar_wait(gemm == 0 ? g_ready : z_ready, ph));
                     tc_fence_after();
 #pragma unroll 1
                     for (int nc = 0; nc < C::NC1; ++nc) {
 #pragma unroll 1
                         for (int kc = 0; kc < C::KC1; ++kc, ++i, ++cnt) {
                             const int s = P::RESIDENT ? i : cnt % P::NS;
-                            mbar_wait(wfull + s, P::RESIDENT ? 0u : (uint32_t)((cnt / P::NS) & 1));
+                            MW(w_wt, mbar_wait(wfull + s, P::RESIDENT ? 0u : (uint32_t)((cnt / P::NS) & 1)));
                             tc_fence_after();
                             issue_block(tmem + nc * 128, tmem + P::AOP + 64 * kc, w0 + s * UM_STAGE, 128, kc > 0);
-                            if (!P::RESIDENT) mma_commit(wempty + s);
+                            if (!P::RESIDENT) commit(wempty + s);
                         }
-                        mma_commit((gemm == 0 ? acc1_ready : acc2_ready) + nc);
+                        commit((gemm == 0 ? acc1_ready : acc2_ready) + nc);
                     }
                 }
 #pragma unroll 1
                 for (int kc = 0; kc < C::KC3; ++kc) {
-                    mbar_wait(hid_ready + kc, ph);
+                    MW(w_hid, mbar_wait(hid_ready + kc, ph));
                     tc_fence_after();
 #pragma unroll 1
                     for (int nc = 0; nc < C::NC3; ++nc) {
                         const int j = kc * C::NC3 + nc;
                         const int s = P::RESIDENT ? i : cnt % P::NS;
                         if (j % C::BPS3 == 0) {
-                            mbar_wait(wfull + s, P::RESIDENT ? 0u : (uint32_t)((cnt / P::NS) & 1));
+                            MW(w_wt, mbar_wait(wfull + s, P::RESIDENT ? 0u : (uint32_t)((cnt / P::NS) & 1)));
                             tc_fence_after();
                         }
                         issue_block(tmem + P::R3 + nc * 128, tmem + 64 * kc, w0 + s * UM_STAGE + (j % C::BPS3) * C::NR3 * 256, C::NR3, true);
                         if (j % C::BPS3 == C::BPS3 - 1) {
-                            if (!P::RESIDENT) mma_commit(wempty + s);
+                            if (!P::RESIDENT) commit(wempty + s);
                             ++i;
                             ++cnt;
                         }
                     }
                 }
-                mma_commit(acc3_ready);
+                commit(acc3_ready);
+                if (mtr && mit == 1 && lane == 0) {
+                    trace[10] = w_op;
+                    trace[11] = w_wt;
+                    trace[12] = w_hid;
+                    trace[13] = clock64() - t_tile;
+                }
             }
+#undef MW
         }
     } else {
         // ================= epilogue threads of group grp =========================================
@@ -1180,7 +1206,7 @@ sashimi_mix_umma256_kernel(MixArgs a) {
         }
     } else if (warp == MW) {
         // ================= MMA issuer ==========================================================
-        if (lane == 0) {
+        {   // all 32 lanes run the loops; the *_w forms elect the issuing lane
             const uint32_t slot0 = smem_u32(slots), ring0 = smem_u32(ring);
             constexpr uint32_t idesc = idesc_bf16(128, 128);
             int i = 0;                                    // weight stage counter
@@ -1191,7 +1217,7 @@ sashimi_mix_umma256_kernel(MixArgs a) {
                 return ring0 + s * UM_STAGE;
             };
             auto done_stage = [&]() {
-                mma_commit(wempty + (i % C::NS));
+                mma_commit_w(wempty + (i % C::NS));
                 ++i;
             };
             // D[R1(nc)] = A[slots, all K] x stage blocks (SS form)
@@ -1199,30 +1225,36 @@ sashimi_mix_umma256_kernel(MixArgs a) {
 #pragma unroll 1
                 for (int kc = 0; kc < C::KC1; ++kc) {
                     const uint32_t bbase = next_stage(), abase = slot0 + kc * UM_SLOT;
+                    if (elect_one()) {      // one election per block of 12 MMAs
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t ao = abase + (term == 1 ? UM_SLOT / 2 : 0), bo = bbase + (term == 2 ? UM_STAGE / 2 : 0);
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t ao = abase + (term == 1 ? UM_SLOT / 2 : 0), bo = bbase + (term == 2 ? UM_STAGE / 2 : 0);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_bf16_ss(tmem + C::r1(nc), smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
-                                        (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_bf16_ss(tmem + C::r1(nc), smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
+                                            (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                        }
                     }
+                    __syncwarp();
                     done_stage();
                 }
-                mma_commit(ready);
+                mma_commit_w(ready);
             };
             // R3[nb] += hidden K chunk kc (in place in R1(kc / 2), columns 64 (kc & 1) ..) x stage (TS form: A from TMEM)
             auto gemm_ts = [&](int kc) {
 #pragma unroll 1
                 for (int nb = 0; nb < C::NB3; ++nb) {
                     const uint32_t bbase = next_stage(), abase = tmem + C::r1(kc >> 1) + 64 * (kc & 1);
+                    if (elect_one()) {      // one election per block of 12 MMAs
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t ao = abase + (term == 1 ? 8 : 0), bo = bbase + (term == 2 ? UM_STAGE / 2 : 0);
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t ao = abase + (term == 1 ? 8 : 0), bo = bbase + (term == 2 ? UM_STAGE / 2 : 0);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_bf16_ts(tmem + C::R3 + nb * 128, ao + ks * 16, smem_desc_sw128(bo + ks * 32), idesc, 1u);
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_bf16_ts(tmem + C::R3 + nb * 128, ao + ks * 16, smem_desc_sw128(bo + ks * 32), idesc, 1u);
+                        }
                     }
+                    __syncwarp();
                     done_stage();
                 }
             };
@@ -1250,7 +1282,7 @@ sashimi_mix_umma256_kernel(MixArgs a) {
                     gemm_ts(2 * nc + cg);
                 }
             }
-            mma_commit(acc3_ready);
+            mma_commit_w(acc3_ready);
         }
     } else {
         // ================= epilogue threads: one time step each, column group cg ================

@@ -112,7 +112,7 @@ pool_umma_kernel(PoolUmmaArgs a) {
         }
     } else if (warp == 9) {
         // ================= MMA issuer ==========================================================
-        if (lane == 0) {
+        {   // all 32 lanes run the loops; the *_w forms elect the issuing lane
             const uint32_t slab0 = smem_u32(slabs), ring0 = smem_u32(ring);
             const uint32_t idesc = idesc_bf16(128, ncols);
             int i = 0;
@@ -128,19 +128,22 @@ pool_umma_kernel(PoolUmmaArgs a) {
                     mbar_wait(wfull + s, (i / PU_NSW) & 1);
                     tc_fence_after();
                     const uint32_t bbase = ring0 + s * PU_STAGE;
+                    if (elect_one()) {      // one election per block of 12 MMAs
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t ao = abase + (term == 1 ? PU_SLAB / 2 : 0), bo = bbase + (term == 2 ? PU_STAGE / 2 : 0);
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t ao = abase + (term == 1 ? PU_SLAB / 2 : 0), bo = bbase + (term == 2 ? PU_STAGE / 2 : 0);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_bf16_ss(tmem + nt * 128, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
-                                        (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_bf16_ss(tmem + nt * 128, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc,
+                                            (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                        }
                     }
-                    mma_commit(wempty + s);
+                    __syncwarp();
+                    mma_commit_w(wempty + s);
                 }
-                mma_commit(uempty + us);
+                mma_commit_w(uempty + us);
             }
-            mma_commit(acc_ready);
+            mma_commit_w(acc_ready);
         }
     } else {
         // ================= loaders, then epilogue: one step per thread ===========================

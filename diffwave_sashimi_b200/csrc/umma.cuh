@@ -81,6 +81,23 @@ __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// One lane of a converged warp (the same lane for the same mask).  The MMA-issuer warps run their loops with all 32 lanes and
+// guard only the tcgen05.mma / tcgen05.commit instructions with this: inside an `if (lane == 0)` region the compiler has to
+// move every descriptor into uniform registers through a per-instruction broadcast loop (ELECT / R2UR.BROADCAST / BRA.U.ANY,
+// ~100 cycles per MMA, measured: the single issuing thread was the tensor pipe's bottleneck); in convergent code the
+// descriptors are uniform values from the start.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMEM ---------------------------------------------------------------------------------
 // whole warp; ncols power of two in [32, 512]; the address is written to *dst (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
@@ -178,6 +195,19 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 &a, const u
 // all tcgen05.mma issued so far by this thread -> one arrival on bar when they have completed
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// warp-level forms for the MMA-issuer warps (all 32 lanes converged; see elect_one): one elected lane issues.  elect.sync is
+// itself a convergence point of the full warp, and the same lane is elected every time, so tcgen05.commit tracks the MMAs
+// issued through these wrappers.
+__device__ __forceinline__ void mma_bf16_ss_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one()) mma_bf16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+}
+__device__ __forceinline__ void mma_bf16_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one()) mma_bf16_ts(d_tmem, a_tmem, bdesc, idesc, accumulate);
+}
+__device__ __forceinline__ void mma_commit_w(uint64_t *bar) {
+    if (elect_one()) mma_commit(bar);
 }
 
 // ---- fp32 -> (hi, lo) bf16 split of 8 consecutive K elements, one 16-byte chunk each --------

@@ -98,7 +98,7 @@ wave_block_umma_kernel(WaveBlockArgs a) {
     const int b = blockIdx.y, t0 = blockIdx.x * WU_TT, L = a.L, d = a.dilation;
     long long *trace = a.trace ? a.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
 #define WU_TRACE(slot) do { if (trace && tid == 0) trace[slot] = clock64(); } while (0)
-#define WU_TRACE_MMA(slot) do { if (trace) trace[slot] = clock64(); } while (0)
+#define WU_TRACE_MMA(slot) do { if (trace && lane == 0) trace[slot] = clock64(); } while (0)
     WU_TRACE(0);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -171,7 +171,7 @@ wave_block_umma_kernel(WaveBlockArgs a) {
         }
     } else if (warp == 9) {
         // ================= MMA issuer ==========================================================
-        if (lane == 0) {
+        {   // all 32 lanes run the loops; the *_w forms elect the issuing lane
             const uint32_t slab0 = smem_u32(slabs), ring0 = smem_u32(ring);
             constexpr uint32_t idesc = idesc_bf16(128, 128), idesc1 = idesc_bf16(128, 256);
             int i = 0;                                    // phase-2 weight stage counter
@@ -182,7 +182,7 @@ wave_block_umma_kernel(WaveBlockArgs a) {
                 return ring0 + s * WU_STAGE;
             };
             auto done_stage = [&]() {
-                mma_commit(wempty + (i % W::NSW));
+                mma_commit_w(wempty + (i % W::NSW));
                 ++i;
             };
             // ---- phase 1: D[:, 0:2C) = sum over (tap, channel chunk) slabs, one N = 256 MMA per 256 columns
@@ -201,20 +201,23 @@ wave_block_umma_kernel(WaveBlockArgs a) {
                     tc_fence_after();
                     if (i1 == 0) WU_TRACE_MMA(14);
                     const uint32_t bbase = ring0 + s * WU_STAGE1;
+                    if (elect_one()) {      // one election per block of 12 MMAs
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t ao = abase + (term == 1 ? WU_SLAB / 2 : 0), bo = bbase + (term == 2 ? WU_STAGE1 / 2 : 0);
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t ao = abase + (term == 1 ? WU_SLAB / 2 : 0), bo = bbase + (term == 2 ? WU_STAGE1 / 2 : 0);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_bf16_ss(tmem + nh * 256, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc1,
-                                        (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_bf16_ss(tmem + nh * 256, smem_desc_sw128(ao + ks * 32), smem_desc_sw128(bo + ks * 32), idesc1,
+                                            (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                        }
                     }
-                    mma_commit(p1empty + s);
+                    __syncwarp();
+                    mma_commit_w(p1empty + s);
                 }
-                mma_commit(uempty + us);
+                mma_commit_w(uempty + us);
                 if (kc == 0) WU_TRACE_MMA(8);
             }
-            mma_commit(acc1_ready);
+            mma_commit_w(acc1_ready);
             WU_TRACE_MMA(9);
             // ---- phase 2: [W_res; W_skip] o, 128 output rows at a time, A = packed o in TMEM
 #pragma unroll 1
@@ -231,17 +234,20 @@ wave_block_umma_kernel(WaveBlockArgs a) {
                     mbar_wait(o_ready + kc, 0);
                     tc_fence_after();
                     const uint32_t bbase = next_stage();
+                    if (elect_one()) {      // one election per block of 12 MMAs
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t bo = bbase + (term == 2 ? WU_STAGE / 2 : 0);
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t bo = bbase + (term == 2 ? WU_STAGE / 2 : 0);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_bf16_ts(dcol, tmem + kc * 64 + ks * 16 + (term == 1 ? 8 : 0), smem_desc_sw128(bo + ks * 32), idesc,
-                                        (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                            for (int ks = 0; ks < 4; ++ks)
+                                mma_bf16_ts(dcol, tmem + kc * 64 + ks * 16 + (term == 1 ? 8 : 0), smem_desc_sw128(bo + ks * 32), idesc,
+                                            (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                        }
                     }
+                    __syncwarp();
                     done_stage();
                 }
-                mma_commit(d2_ready + j);
+                mma_commit_w(d2_ready + j);
                 if (j == 0) WU_TRACE_MMA(10);
             }
             WU_TRACE_MMA(11);

@@ -35,3 +35,6 @@ for blk, H, l in [(0, 64, 16000), (1, 128, 4000), (2, 256, 1000)]:
     med = rel.median(0).values
     for i, n in enumerate(names):
         print(f"   {n:10s} {med[i]:9.0f}")
+    if pers:
+        raw = t[:, 10:14].median(0).values
+        print(f"   MMA issuer of group 0, second tile: waits for g/z operands {raw[0]:.0f}, weights {raw[1]:.0f}, hidden chunks {raw[2]:.0f} of {raw[3]:.0f} cycles (issue to issue)")
