@@ -682,14 +682,18 @@ sashimi_mix_umma_pers_kernel(MixArgs a, int B, int stagger_ns, int rev, const __
             __syncwarp();
             pdl_wait();
             if (STAGE) stage_producer();
-        } else if (lane == 0) {
+        } else {
+            // streamed weights: all lanes run the loop (uniform addresses), one elected lane issues the copy
             int cnt = 0;
             for (int tile = blockIdx.x * P::NG; tile < ntiles; tile += stride)
                 for (int i = 0; i < C::NSTG; ++i, ++cnt) {
                     const int s = cnt % P::NS;
                     mbar_wait(wempty + s, ((cnt / P::NS) & 1) ^ 1);
-                    mbar_arrive_expect_tx(wfull + s, UM_STAGE);
-                    bulk_g2s(wbuf + (size_t)s * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + s);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(wfull + s, UM_STAGE);
+                        bulk_g2s(wbuf + (size_t)s * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + s);
+                    }
+                    __syncwarp();
                 }
         }
     } else if (warp >= EPI_WARPS + P::NG) {
@@ -1195,14 +1199,15 @@ sashimi_mix_umma256_kernel(MixArgs a) {
     pdl_wait();             // set-up done; everything below reads or writes activations
 
     if (warp == PW) {
-        // ================= weight producer =====================================================
-        if (lane == 0) {
-            for (int i = 0; i < C::NSTG; ++i) {
-                const int s = i % C::NS, n = i / C::NS;
-                mbar_wait(wempty + s, (n & 1) ^ 1);
+        // ================= weight producer (all lanes run the loop, one elected lane issues the copy) ==========
+        for (int i = 0; i < C::NSTG; ++i) {
+            const int s = i % C::NS, n = i / C::NS;
+            mbar_wait(wempty + s, (n & 1) ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(wfull + s, UM_STAGE);
                 bulk_g2s(ring + (size_t)s * UM_STAGE, a.Wimg + (size_t)i * UM_STAGE, UM_STAGE, wfull + s);
             }
+            __syncwarp();
         }
     } else if (warp == MW) {
         // ================= MMA issuer ==========================================================
