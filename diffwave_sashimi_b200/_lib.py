@@ -67,6 +67,13 @@ SIGNATURES = {
     "dwb_mel_frames": [_I, _I, _I, ctypes.POINTER(_I)],
     "dwb_mel_spectrogram": [_P, _I, _I, _F, _P, _I, _I, _P, _I, _F, _P, _P],
     "dwb_fftconv": [_P, _P, _P, _I64, _F, _F, _P, _P, _I, _I, _I, _P],
+    "dwb_trainer_layout": [ctypes.POINTER(Config), _I, ctypes.c_char_p, _I, ctypes.POINTER(_I64), ctypes.POINTER(_I64),
+                           ctypes.POINTER(_I), ctypes.POINTER(_I64)],
+    "dwb_trainer_create": [ctypes.POINTER(Config), _I, _I, _I, ctypes.POINTER(_P)],
+    "dwb_trainer_destroy": [_P],
+    "dwb_trainer_info": [_P, ctypes.POINTER(_I64), ctypes.POINTER(_I64)],
+    "dwb_trainer_loss_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "dwb_adam_step": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P],
 }
 
 PROF_CATEGORIES = ["embed", "init_conv", "head", "pool", "fftconv_s0", "fftconv_s1", "fftconv_s2", "fftconv_s3",

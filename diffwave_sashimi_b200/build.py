@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdwb.so")
-SOURCES = ["api.cu", "fftconv.cu", "fftconv3.cu", "s4_kernelgen.cu", "sashimi_kernels.cu", "wavenet_kernels.cu", "mix_mma.cu", "wavenet_mma.cu", "mix_umma.cu", "wave_umma.cu", "cauchy_ops.cu", "mel_frontend.cu", "mix_gemm_umma.cu", "pool_umma.cu"]
+SOURCES = ["api.cu", "fftconv.cu", "fftconv3.cu", "s4_kernelgen.cu", "sashimi_kernels.cu", "wavenet_kernels.cu", "mix_mma.cu", "wavenet_mma.cu", "mix_umma.cu", "wave_umma.cu", "cauchy_ops.cu", "mel_frontend.cu", "mix_gemm_umma.cu", "pool_umma.cu", "train_wavenet.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", *os.environ.get("DWB_NVCC_EXTRA", "").split(),
          "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]

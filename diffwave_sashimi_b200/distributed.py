@@ -77,3 +77,24 @@ def generate_sharded(net, n_clips, L, diffusion_hyperparams, seed, condition=Non
     else:
         local = torch.empty((0, 1, L), device=eng.device)
     return gather_samples(local, n_clips, rank, world)
+
+
+# ---- data-parallel training (distributed_util.py:97-149) ---------------------------------------------------------
+def broadcast_flat(params, src=0):
+    """Rank `src`'s flat parameter buffer to every rank: ONE broadcast where the reference broadcasts each
+    state_dict tensor separately (distributed_util.py:107-110)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(params, src)
+
+
+def allreduce_flat(grads, average=True):
+    """Sum (or mean) of the flat gradient buffer over ranks, in place, in ONE all-reduce; returns the world size.
+    The reference flattens every gradient into a scratch tensor, all-reduces, divides and copies back per step
+    (distributed_util.py:119-138); the trainer's gradients already are one contiguous buffer, and with
+    average=False the 1/world_size is left to the fused Adam kernel (Trainer.step)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world > 1:
+        dist.all_reduce(grads)
+        if average:
+            grads /= world
+    return world

@@ -119,6 +119,31 @@ def rewrite_fresh_kernels(blocks, sd):
         yield k, newC, l
 
 
+def config_struct(cfg: dict) -> Config:
+    """The reference's constructor kwargs (configs/model/*.yaml) as the C ABI's dwb_config."""
+    sashimi = cfg["_name_"] == "sashimi"
+    c = Config()
+    c.model = _lib.MODEL_SASHIMI if sashimi else _lib.MODEL_WAVENET
+    c.unconditional = int(bool(cfg.get("unconditional", False)))
+    c.embed_in = cfg.get("diffusion_step_embed_dim_in", 128)
+    c.embed_mid = cfg.get("diffusion_step_embed_dim_mid", 512)
+    c.embed_out = cfg.get("diffusion_step_embed_dim_out", 512)
+    c.mel_bands = 80
+    if sashimi:
+        pool = list(cfg["pool"])
+        if len(pool) > _lib.DWB_MAX_POOL:
+            raise ValueError("too many pool stages")
+        c.d_model, c.n_layers, c.n_pool = cfg["d_model"], cfg["n_layers"], len(pool)
+        for i, p in enumerate(pool):
+            c.pool[i] = p
+        c.expand, c.ff, c.unet, c.L = cfg["expand"], cfg["ff"], int(bool(cfg.get("unet", True))), cfg["L"]
+        c.d_state_half = 32
+    else:
+        c.res_channels, c.skip_channels = cfg["res_channels"], cfg["skip_channels"]
+        c.num_res_layers, c.dilation_cycle = cfg["num_res_layers"], cfg["dilation_cycle"]
+    return c
+
+
 class Engine:
     """One libdwb plan for one model on one device."""
 
@@ -134,25 +159,7 @@ class Engine:
         self.device = torch.device(device)
         self.cfg = dict(cfg)
         self.sashimi = cfg["_name_"] == "sashimi"
-        c = Config()
-        c.model = _lib.MODEL_SASHIMI if self.sashimi else _lib.MODEL_WAVENET
-        c.unconditional = int(bool(cfg.get("unconditional", False)))
-        c.embed_in = cfg.get("diffusion_step_embed_dim_in", 128)
-        c.embed_mid = cfg.get("diffusion_step_embed_dim_mid", 512)
-        c.embed_out = cfg.get("diffusion_step_embed_dim_out", 512)
-        c.mel_bands = 80
-        if self.sashimi:
-            pool = list(cfg["pool"])
-            if len(pool) > _lib.DWB_MAX_POOL:
-                raise ValueError("too many pool stages")
-            c.d_model, c.n_layers, c.n_pool = cfg["d_model"], cfg["n_layers"], len(pool)
-            for i, p in enumerate(pool):
-                c.pool[i] = p
-            c.expand, c.ff, c.unet, c.L = cfg["expand"], cfg["ff"], int(bool(cfg.get("unet", True))), cfg["L"]
-            c.d_state_half = 32
-        else:
-            c.res_channels, c.skip_channels = cfg["res_channels"], cfg["skip_channels"]
-            c.num_res_layers, c.dilation_cycle = cfg["num_res_layers"], cfg["dilation_cycle"]
+        c = config_struct(cfg)
         self._c = c
         with torch.cuda.device(self.device):
             check(lib().dwb_plan_create(ctypes.byref(c), self.device.index or 0, ctypes.byref(self._plan)))

@@ -209,6 +209,35 @@ int dwb_fftconv_prepare(const float *k, const float *D, int H, int l, float *kf,
 int dwb_fftconv(const float *x, const float *stats, const float *part_t, int64_t part_stride_b,
                 float ln_m, float ln_s, const float *kf, float *g, int B, int H, int l, void *stream);
 
+/* ---- training step (WaveNet backbone, unconditional) -----------------------------------------
+ * Replaces, for model._name_ = wavenet:   optimizer.zero_grad(); loss = training_loss(net, nn.MSELoss(), audio, dh);
+ * loss.backward(); optimizer.step()        (train.py:137-143,198-222; torch.optim.Adam, train.py:92)
+ * Parameters, gradients and the two Adam moments are four flat f32 device buffers owned by the CALLER, laid out in
+ * net.parameters() order of models/wavenet.py (dwb_trainer_layout; the names are the reference's state_dict keys).  The
+ * host mirror makes every nn.Parameter / .grad a view of them, so checkpoints keep the reference's format and the
+ * data-parallel gradient exchange (distributed_util.py:97-149) is one all-reduce of one contiguous buffer.
+ * SaShiMi and mel-conditioned models return DWB_ERR_UNSUPPORTED. */
+typedef struct dwb_trainer dwb_trainer;
+/* Pure host function (no device needed): number of parameters and total f32 count; with index >= 0 also entry
+ * `index`: its state_dict key (copied into name[name_cap]), float offset and element count.  Any out pointer may be NULL. */
+int dwb_trainer_layout(const dwb_config *cfg, int index, char *name, int name_cap, int64_t *offset, int64_t *numel,
+                       int *n_params, int64_t *total);
+/* activation workspace for batches of exactly (B,1,L); owned by the trainer */
+int dwb_trainer_create(const dwb_config *cfg, int device, int B, int L, dwb_trainer **out);
+int dwb_trainer_destroy(dwb_trainer *trainer);
+int dwb_trainer_info(dwb_trainer *trainer, int64_t *workspace_bytes, int64_t *launches);
+/* One loss + backward:  x_t = coef[b,0] audio + coef[b,1] z;  eps = net((x_t, steps));  loss = mean((eps - z)^2);
+ * grads = d loss / d params (overwritten, not accumulated).
+ *   params, grads  flat buffers (dwb_trainer_layout)      audio, z (B,1,L)      steps (B) f32 diffusion steps
+ *   coef (B,2) = (sqrt(alpha_bar_t), sqrt(1 - alpha_bar_t)) computed by the caller in torch fp32 (train.py:219)
+ *   eps_out (B,1,L) or NULL      loss: one device float.  Enqueues on `stream`; does not synchronise. */
+int dwb_trainer_loss_backward(dwb_trainer *trainer, const float *params, float *grads, const float *audio, const float *z,
+                              const float *steps, const float *coef, float *eps_out, float *loss, void *stream);
+/* torch.optim.Adam.step() (amsgrad off, weight_decay 0) over flat buffers of n floats in ONE launch; `step` counts
+ * from 1; gradients are multiplied by grad_scale first (1/world_size after a summing all-reduce). */
+int dwb_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int64_t step, float grad_scale, void *stream);
+
 /* ---- debug ---------------------------------------------------------------------------------------------------
  * One tcgen05 WaveNet layer on caller tensors, writing 16 clock64 phase timestamps per CTA to `trace`
  * ((B * ceil(L/128)) x 16 int64; tools/trace_wave.py prints the phase durations). */

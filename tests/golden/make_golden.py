@@ -79,11 +79,14 @@ def save(name, **arrs):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--train", action="store_true", help="training-step fixtures only (train_*.npz)")
     ap.add_argument("--extra", action="store_true", help="round-2 fixtures only (new files; the round-1 files are left untouched)")
     args = ap.parse_args()
     ns = refshim.load(parity=True)
     if args.extra:
         return make_extra(ns)
+    if args.train:
+        return make_train(ns)
 
     # --- schedule ---------------------------------------------------------------------
     for tag, kw in (("T200", dict(T=200, beta_0=1e-4, beta_T=0.02)), ("T50", dict(T=50, beta_0=1e-4, beta_T=0.05)),
@@ -197,6 +200,81 @@ def make_full(ns):
             for tv in (tval, 0.0):
                 outs[f"eps_t{int(tv)}"] = net((x, tv * torch.ones(B, 1)), mel_spec=mel).numpy()
         save(name, cfg=np.array(repr(dict(cfg))), seed=0, xseed=5, **outs)
+
+
+TRAIN_TINY = {
+    "train_wnet_a": dict(over=dict(res_channels=16, skip_channels=8, num_res_layers=7, dilation_cycle=5, **SMALL_EMB), B=2, L=300),
+    # widths and a length that are not multiples of the 64-wide GEMM tiles, dilation up to 8 on 200 samples
+    "train_wnet_b": dict(over=dict(res_channels=40, skip_channels=24, num_res_layers=5, dilation_cycle=4, **SMALL_EMB), B=3, L=200),
+}
+
+
+def ref_training_loss(net, audio, dh, steps, z):
+    """train.py:198-222 with the two random draws (diffusion_steps, z) passed in instead of drawn."""
+    B = audio.shape[0]
+    ab = dh["Alpha_bar"]
+    steps = steps.view(B, 1, 1)
+    x_t = torch.sqrt(ab[steps]) * audio + torch.sqrt(1 - ab[steps]) * z
+    eps = net((x_t, steps.view(B, 1),), mel_spec=None)
+    return torch.nn.MSELoss()(eps, z), eps
+
+
+def make_train(ns):
+    """Training-step fixtures from the unmodified reference modules + torch autograd + torch.optim.Adam (train.py:84-143):
+      train_wnet_{a,b}.npz     tiny WaveNets: start state_dict, three (audio, steps, z) batches, loss / eps / every
+                               parameter gradient of batch 0, losses and the state_dict after three Adam steps (lr 2e-4)
+      train_full_wnet_h128_d30 BASELINE configs[0] at B=1, L=16000 on our seeded weights: loss, the L2 norm of every
+                               parameter gradient and a few complete gradient tensors
+    """
+    import diffwave_sashimi_b200 as dwb
+    dh = ns.utils.calc_diffusion_hyperparams(T=50, beta_0=1e-4, beta_T=0.05, fast=False)
+    for name, spec in TRAIN_TINY.items():
+        cfg, net = build(ns, "wnet_h128_d30", spec["over"])
+        net.train()
+        B, L = spec["B"], spec["L"]
+        g = torch.Generator().manual_seed(21)
+        arrs = dict(cfg=np.array(repr(dict(cfg))), T=50, beta_0=1e-4, beta_T=0.05, lr=2e-4,
+                    **{"sd0/" + k: v.detach().clone().numpy() for k, v in net.state_dict().items()})
+        opt = torch.optim.Adam(net.parameters(), lr=2e-4)
+        losses = []
+        for it in range(3):
+            audio = torch.rand(B, 1, L, generator=g) * 2 - 1
+            steps = torch.randint(50, size=(B,), generator=g)
+            z = torch.randn(B, 1, L, generator=g)
+            opt.zero_grad()
+            loss, eps = ref_training_loss(net, audio, dh, steps, z)
+            loss.backward()
+            if it == 0:
+                arrs["eps0"] = eps.detach().numpy()
+                for k, p in net.named_parameters():
+                    arrs["grad0/" + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().clone().numpy()
+                    arrs["hasgrad/" + k] = np.array(p.grad is not None)
+            opt.step()
+            losses.append(float(loss))
+            arrs[f"audio{it}"], arrs[f"steps{it}"], arrs[f"z{it}"] = audio.numpy(), steps.numpy(), z.numpy()
+        arrs["losses"] = np.array(losses, dtype=np.float64)
+        arrs.update({"sd3/" + k: v.detach().clone().numpy() for k, v in net.state_dict().items()})
+        save(name, **arrs)
+
+    base = "wnet_h128_d30"
+    cfg = refshim.Cfg(refshim.MODEL_CFGS[base])
+    net = ns.models.construct_model(cfg).train()
+    net.load_state_dict(dwb.init.seeded_state_dict(dict(cfg), seed=0))
+    dh = ns.utils.calc_diffusion_hyperparams(T=200, beta_0=1e-4, beta_T=0.02, fast=False)
+    g = torch.Generator().manual_seed(22)
+    audio = torch.rand(1, 1, 16000, generator=g) * 2 - 1
+    steps = torch.tensor([137])
+    z = torch.randn(1, 1, 16000, generator=g)
+    loss, _ = ref_training_loss(net, audio, dh, steps, z)
+    loss.backward()
+    names = [k for k, _ in net.named_parameters()]
+    norms = np.array([float(p.grad.double().norm()) if p.grad is not None else 0.0 for _, p in net.named_parameters()])
+    keep = ["residual_layer.fc_t2.bias", "final_conv.2.conv.weight", "residual_layer.residual_blocks.0.dilated_conv_layer.conv.bias",
+            "residual_layer.residual_blocks.29.skip_conv.weight_g", "residual_layer.residual_blocks.13.res_conv.weight_v",
+            "init_conv.0.conv.weight_v"]
+    gd = dict(net.named_parameters())
+    save("train_full_" + base, cfg=np.array(repr(dict(cfg))), seed=0, xseed=22, step=137, loss=float(loss), names=np.array(names),
+         grad_norms=norms, **{"grad/" + k: gd[k].grad.numpy() for k in keep})
 
 
 def make_extra(ns):

@@ -78,3 +78,44 @@ def test_shard_ranges_cover_batch():
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+
+
+def _train_worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from diffwave_sashimi_b200 import distributed as D
+    D.init("gloo")
+    g = torch.Generator().manual_seed(100 + rank)
+    params = torch.randn(n, generator=g)
+    grads = torch.randn(n, generator=g)
+    D.broadcast_flat(params, 0)
+    summed = grads.clone()
+    w = D.allreduce_flat(summed, average=False)
+    mean = grads.clone()
+    D.allreduce_flat(mean, average=True)
+    if rank == 1:
+        q.put((params, summed, mean, w))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_two_ranks():
+    """The training path's two collectives on the flat buffers (the reference's apply_gradient_allreduce,
+    distributed_util.py:97-149): parameters follow rank 0, gradients are averaged."""
+    n, world = 1001, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    params, summed, mean, w = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    gens = [torch.Generator().manual_seed(100 + r) for r in range(world)]
+    p0, g0 = torch.randn(n, generator=gens[0]), torch.randn(n, generator=gens[0])
+    _, g1 = torch.randn(n, generator=gens[1]), torch.randn(n, generator=gens[1])
+    assert w == 2 and torch.equal(params, p0)
+    assert torch.allclose(summed, g0 + g1) and torch.allclose(mean, (g0 + g1) / 2)
