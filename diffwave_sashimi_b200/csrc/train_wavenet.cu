@@ -23,6 +23,7 @@
 // Weight norm W = g v / |v| (per output row) is folded before the forward and un-folded after the backward:
 //   dg = <dW, v> / |v|;  dv = (g / |v|) dW - (g <dW, v> / |v|^3) v.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -34,7 +35,14 @@
 namespace dwb {
 namespace train {
 
-constexpr int TM = 64, TN = 64, TK = 16, NT = 256;
+constexpr int TK = 16, NT = 256;
+// Tiles are (64 W) x (64 W) outputs per 256-thread CTA, (4 W) x (4 W) per thread as W x W blocks of 4 x 4 spaced 64 apart
+// (conflict-free float4 shared-memory reads).  W = 2 is the default (16 FMAs per shared-memory load instead of 8);
+// DWB_TRAIN_TILE=64 selects W = 1.
+static int tile_w() {
+    static const int w = [] { const char *e = getenv("DWB_TRAIN_TILE"); return (e && atoi(e) == 64) ? 1 : 2; }();
+    return w;
+}
 
 // Y[b,m,l] = alpha * sum_tap sum_k A(tap,m,k) X'[b,k,l+shift_tap] + bias_scale * bias[m] + beta * R[b,m,l]   (then ReLU)
 // X'[b,k,l] = X[b,k,l] + rowadd[b,k] for 0 <= l < L, 0 outside.  A(tap,m,k) = A[tap*a_tap + m*a_m + k*a_k].
@@ -48,36 +56,47 @@ struct GemmArgs {
     int relu;
 };
 
-__device__ __forceinline__ void tile_fma(const float (*As)[TM + 4], const float (*Bs)[TN + 4], int ty, int tx, float (&acc)[4][4]) {
+template <int W>
+__device__ __forceinline__ void tile_fma(const float (*As)[64 * W + 4], const float (*Bs)[64 * W + 4], int ty, int tx,
+                                         float (&acc)[4 * W][4 * W]) {
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
-        const float4 a = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
-        const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        float av[4 * W], bv[4 * W];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int w = 0; w < W; ++w) {
+            const float4 a = *reinterpret_cast<const float4 *>(&As[kk][w * 64 + ty * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][w * 64 + tx * 4]);
+            av[4 * w] = a.x; av[4 * w + 1] = a.y; av[4 * w + 2] = a.z; av[4 * w + 3] = a.w;
+            bv[4 * w] = b.x; bv[4 * w + 1] = b.y; bv[4 * w + 2] = b.z; bv[4 * w + 3] = b.w;
+        }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int i = 0; i < 4 * W; ++i)
+#pragma unroll
+            for (int j = 0; j < 4 * W; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
 }
+// row / column of accumulator element i of thread coordinate t inside the tile
+__device__ __forceinline__ int tile_pos(int t, int i) { return (i >> 2) * 64 + t * 4 + (i & 3); }
 
+template <int W>
 __global__ void __launch_bounds__(NT) cgemm_kernel(GemmArgs p) {
-    __shared__ __align__(16) float As[TK][TM + 4];
-    __shared__ __align__(16) float Bs[TK][TN + 4];
-    const int b = blockIdx.z, m0 = blockIdx.y * TM, l0 = blockIdx.x * TN;
+    constexpr int T = 64 * W;
+    __shared__ __align__(16) float As[TK][T + 4];
+    __shared__ __align__(16) float Bs[TK][T + 4];
+    const int b = blockIdx.z, m0 = blockIdx.y * T, l0 = blockIdx.x * T;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    float acc[4][4] = {};
+    float acc[4 * W][4 * W] = {};
     const float *Xb = p.X + (size_t)b * p.K * p.L;
     const float *ra = p.rowadd ? p.rowadd + (size_t)b * p.K : nullptr;
     for (int tap = 0; tap < p.ntap; ++tap) {
-        const int sh = p.shift[tap];
+        const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
         for (int k0 = 0; k0 < p.K; k0 += TK) {
-            for (int e = tid; e < TK * TM; e += NT) {
+            for (int e = tid; e < TK * T; e += NT) {
                 const int kk = e & (TK - 1), mm = e / TK, m = m0 + mm, k = k0 + kk;
                 As[kk][mm] = (m < p.M && k < p.K) ? p.A[tap * p.a_tap + m * p.a_m + k * p.a_k] : 0.f;
             }
-            for (int e = tid; e < TK * TN; e += NT) {
-                const int ll = e & (TN - 1), kk = e / TN, k = k0 + kk, l = l0 + ll + sh;
+            for (int e = tid; e < TK * T; e += NT) {
+                const int ll = e & (T - 1), kk = e / T, k = k0 + kk, l = l0 + ll + sh;
                 float v = 0.f;
                 if (k < p.K && l >= 0 && l < p.L) {
                     v = Xb[(size_t)k * p.L + l];
@@ -86,18 +105,18 @@ __global__ void __launch_bounds__(NT) cgemm_kernel(GemmArgs p) {
                 Bs[kk][ll] = v;
             }
             __syncthreads();
-            tile_fma(As, Bs, ty, tx, acc);
+            tile_fma<W>(As, Bs, ty, tx, acc);
             __syncthreads();
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < 4 * W; ++i) {
+        const int m = m0 + tile_pos(ty, i);
         if (m >= p.M) continue;
         const float bm = p.bias ? p.bias_scale * p.bias[m] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int l = l0 + tx * 4 + j;
+        for (int j = 0; j < 4 * W; ++j) {
+            const int l = l0 + tile_pos(tx, j);
             if (l >= p.L) continue;
             const size_t idx = ((size_t)b * p.M + m) * p.L + l;
             float v = fmaf(p.alpha, acc[i][j], bm);
@@ -117,26 +136,28 @@ struct WgradArgs {
     float alpha;
 };
 
+template <int W>
 __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs p) {
-    __shared__ __align__(16) float As[TK][TM + 4];
-    __shared__ __align__(16) float Bs[TK][TN + 4];
+    constexpr int T = 64 * W;
+    __shared__ __align__(16) float As[TK][T + 4];
+    __shared__ __align__(16) float Bs[TK][T + 4];
     const int nchunk = (p.L + p.lchunk - 1) / p.lchunk;
     const int b = blockIdx.x / nchunk, ch = blockIdx.x % nchunk;
-    const int tiles_k = (p.K + TN - 1) / TN;
-    const int m0 = (blockIdx.y / tiles_k) * TM, k0 = (blockIdx.y % tiles_k) * TN;
-    const int tap = blockIdx.z, sh = p.shift[tap];
+    const int tiles_k = (p.K + T - 1) / T;
+    const int m0 = (blockIdx.y / tiles_k) * T, k0 = (blockIdx.y % tiles_k) * T;
+    const int tap = blockIdx.z, sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int lbeg = ch * p.lchunk, lend = min(p.L, lbeg + p.lchunk);
     const float *dYb = p.dY + (size_t)b * p.M * p.L;
     const float *Xb = p.X + (size_t)b * p.K * p.L;
     const float *ra = p.rowadd ? p.rowadd + (size_t)b * p.K : nullptr;
-    float acc[4][4] = {};
+    float acc[4 * W][4 * W] = {};
     for (int l0 = lbeg; l0 < lend; l0 += TK) {
-        for (int e = tid; e < TK * TM; e += NT) {
+        for (int e = tid; e < TK * T; e += NT) {
             const int ll = e & (TK - 1), mm = e / TK, m = m0 + mm, l = l0 + ll;
             As[ll][mm] = (m < p.M && l < lend) ? dYb[(size_t)m * p.L + l] : 0.f;
         }
-        for (int e = tid; e < TK * TN; e += NT) {
+        for (int e = tid; e < TK * T; e += NT) {
             const int ll = e & (TK - 1), kk = e / TK, k = k0 + kk, l = l0 + ll, ls = l + sh;
             float v = 0.f;
             if (k < p.K && l < lend && ls >= 0 && ls < p.L) {
@@ -146,16 +167,16 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs p) {
             Bs[ll][kk] = v;
         }
         __syncthreads();
-        tile_fma(As, Bs, ty, tx, acc);
+        tile_fma<W>(As, Bs, ty, tx, acc);
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < 4 * W; ++i) {
+        const int m = m0 + tile_pos(ty, i);
         if (m >= p.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = k0 + tx * 4 + j;
+        for (int j = 0; j < 4 * W; ++j) {
+            const int k = k0 + tile_pos(tx, j);
             if (k >= p.K) continue;
             atomicAdd(&p.dW[tap * p.o_tap + m * p.o_m + k * p.o_k], p.alpha * acc[i][j]);
         }
@@ -451,8 +472,13 @@ static int run_gemm(Trainer *tr, cudaStream_t st, const float *A, long long a_ta
     p.M = M; p.K = K; p.L = tr->L; p.ntap = ntap;
     p.shift[0] = s0; p.shift[1] = s1; p.shift[2] = s2;
     p.alpha = alpha; p.bias_scale = bias_scale; p.beta = beta; p.relu = relu;
-    dim3 grid(ceil_div(tr->L, TN), ceil_div(M, TM), tr->B);
-    TR_LAUNCH(tr, cgemm_kernel<<<grid, NT, 0, st>>>(p));
+    // narrow outputs (the 1-channel head, tiny test models) keep the 64-wide tile
+    const int W = (tile_w() == 2 && M > 64) ? 2 : 1, T = 64 * W;
+    dim3 grid(ceil_div(tr->L, T), ceil_div(M, T), tr->B);
+    if (W == 2)
+        TR_LAUNCH(tr, cgemm_kernel<2><<<grid, NT, 0, st>>>(p));
+    else
+        TR_LAUNCH(tr, cgemm_kernel<1><<<grid, NT, 0, st>>>(p));
     return DWB_OK;
 }
 
@@ -465,8 +491,12 @@ static int run_wgrad(Trainer *tr, cudaStream_t st, const float *dY, const float 
     p.shift[0] = s0; p.shift[1] = s1; p.shift[2] = s2;
     p.lchunk = 1024;
     p.alpha = alpha;
-    dim3 grid(tr->B * ceil_div(tr->L, p.lchunk), ceil_div(M, TM) * ceil_div(K, TN), ntap);
-    TR_LAUNCH(tr, wgrad_kernel<<<grid, NT, 0, st>>>(p));
+    const int W = (tile_w() == 2 && M > 64 && K > 64) ? 2 : 1, T = 64 * W;
+    dim3 grid(tr->B * ceil_div(tr->L, p.lchunk), ceil_div(M, T) * ceil_div(K, T), ntap);
+    if (W == 2)
+        TR_LAUNCH(tr, wgrad_kernel<2><<<grid, NT, 0, st>>>(p));
+    else
+        TR_LAUNCH(tr, wgrad_kernel<1><<<grid, NT, 0, st>>>(p));
     return DWB_OK;
 }
 

@@ -2,7 +2,10 @@
     python tools/bench_train.py [wnet_h128_d30|wnet_h256_d36] [B] [steps]
 Prints ms per step, clips/s and the fp32 FLOP rate (3x the forward's algorithmic flops)."""
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 
