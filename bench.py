@@ -231,6 +231,44 @@ def build_net(name, dev):
     return net.to(dev).eval()
 
 
+def measure_training(name, B, dev, steps=2, warmup=1):
+    """Device time of the native training step (loss + backward + Adam, csrc/train_wavenet.cu) on
+    config `name` at B clips of L samples; fp32 flops = 3x the forward's algorithmic flops."""
+    import torch
+    import diffwave_sashimi_b200 as dwb
+    from diffwave_sashimi_b200.training import Trainer
+    spec = CONFIGS[name]
+    net = build_net(name, dev).train()
+    tr = Trainer(net, B, L)
+    dh = dwb.calc_diffusion_hyperparams(spec["T"], BETA_0, spec["beta_T"])
+    g = torch.Generator().manual_seed(99)
+    audio = (torch.rand(B, 1, L, generator=g) * 2 - 1).to(dev)
+    z, t = torch.randn(B, 1, L, generator=g).to(dev), torch.randint(spec["T"], (B,), generator=g)
+    for _ in range(warmup):
+        tr.loss_backward(audio, dh, diffusion_steps=t, z=z)
+        tr.step()
+    n0 = tr.info()["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        loss = tr.loss_backward(audio, dh, diffusion_steps=t, z=z)
+        tr.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    c = spec["cfg"]
+    C, S, N = c["res_channels"], c["skip_channels"], c["num_res_layers"]
+    fwd = N * (12 * C * C * L + 2 * C * C * L + 2 * C * S * L) + 2 * S * S * L + 2 * S * L + 2 * C * L
+    out = {"workload": f"one optimizer step (loss + backward + Adam) of {spec['workload'].split(' T=')[0]}, L={L}", "batch": B,
+           "ms_per_step": round(ms, 2), "value": round(B / ms * 1e3, 3), "unit": "clips/s per optimizer step", "steps": steps,
+           "warmup": warmup, "dtype": "f32", "tflops_fp32": round(3 * fwd * B / ms / 1e9, 2), "loss": round(float(loss), 6),
+           "finite": bool(torch.isfinite(loss)), "gpu_launches": (tr.info()["launches"] - n0) // steps + 1,
+           "note": "first correct path: exact-fp32 SIMT GEMM tiles, no tensor cores; not part of the headline metric"}
+    tr.close()
+    return out
+
+
 def measure(name, B, K, W, dev, world=1, rank=0, full=True):
     """Resident + end-to-end timing of config `name` at B clips per GPU; full=False: resident timing only."""
     import torch
@@ -471,6 +509,11 @@ def main():
             del r, e, n
             torch.cuda.empty_cache()
         line["other_configs"] = others
+        try:
+            line["training_step"] = measure_training("wnet_h128_d30", 8, dev)
+        except Exception as e:       # the training row must never cost the headline line
+            line["training_step"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb, _, _ = cpu_arm(name, steps=2, warmup=1)
         line["cpu_baseline"] = cb

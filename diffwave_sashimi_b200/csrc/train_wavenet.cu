@@ -489,9 +489,13 @@ static int run_wgrad(Trainer *tr, cudaStream_t st, const float *dY, const float 
     p.o_tap = o_tap; p.o_m = o_m; p.o_k = o_k;
     p.M = M; p.K = K; p.L = tr->L; p.ntap = ntap;
     p.shift[0] = s0; p.shift[1] = s1; p.shift[2] = s2;
-    p.lchunk = 1024;
     p.alpha = alpha;
     const int W = (tile_w() == 2 && M > 64 && K > 64) ? 2 : 1, T = 64 * W;
+    // time chunk per CTA: at least two waves of CTAs (2 resident per SM x 148 SMs) however few output tiles the weight has
+    // (a 128 x 128 res_conv is ONE tile), at most 2048 samples so that the atomics stay a small share
+    const int per_chunk = tr->B * ceil_div(M, T) * ceil_div(K, T) * ntap;
+    const int want_chunks = std::max(1, ceil_div(592, per_chunk));
+    p.lchunk = std::min(2048, std::max(128, ceil_div(ceil_div(tr->L, want_chunks), TK) * TK));
     dim3 grid(tr->B * ceil_div(tr->L, p.lchunk), ceil_div(M, T) * ceil_div(K, T), ntap);
     if (W == 2)
         TR_LAUNCH(tr, wgrad_kernel<2><<<grid, NT, 0, st>>>(p));

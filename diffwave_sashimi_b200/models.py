@@ -4,8 +4,9 @@
 state_dict keys and shapes, so `load_state_dict(checkpoint['model_state_dict'])`
 works unchanged.  The modules are parameter containers: `forward((audio, steps), mel_spec)` hands
 the tensors to the CUDA engine (`engine.Engine`).  There is deliberately no PyTorch or CPU
-execution path — autograd/training is outside this package's scope — so a
-call without CUDA tensors, or with the native library missing, raises.
+execution path and no autograd: training goes through `training.Trainer` (native backward + Adam,
+WaveNet only), so a forward under autograd, without CUDA tensors, or with the
+native library missing, raises.
 """
 import math
 
@@ -139,7 +140,8 @@ class _EngineBacked(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise RuntimeError(
                 "diffwave_sashimi_b200 modules run the inference engine only: call under torch.no_grad(). "
-                "Training (autograd) is outside the hot path this package replaces.")
+                "There is no autograd path; training runs through diffwave_sashimi_b200.training.Trainer "
+                "(native backward, model=wavenet).")
         if not audio.is_cuda:
             raise RuntimeError("diffwave_sashimi_b200 has no CPU path: move the model and inputs to a B200 (.cuda())")
         return self._engine_get().forward(audio, diffusion_steps, mel_spec)

@@ -88,7 +88,7 @@ def train(rank, world, diffusion_cfg, model_cfg, dataset_cfg, name=None, ckpt_it
                 p.copy_(ck["model_state_dict"][k])
         if "optimizer_state_dict" in ck:
             trainer.load_state_dict(ck["optimizer_state_dict"])
-            trainer.lr = learning_rate               # the reference resets the learning rate too (train.py:104-105)
+            trainer.lr = float(learning_rate)            # the reference resets the learning rate too (train.py:104-105)
         print(f"Successfully loaded model at iteration {it0}")
     else:
         print("No valid checkpoint model found - training from scratch.")
