@@ -72,6 +72,7 @@ SIGNATURES = {
     "dwb_trainer_create": [ctypes.POINTER(Config), _I, _I, _I, ctypes.POINTER(_P)],
     "dwb_trainer_destroy": [_P],
     "dwb_trainer_info": [_P, ctypes.POINTER(_I64), ctypes.POINTER(_I64)],
+    "dwb_trainer_set_gemm": [_P, _I],
     "dwb_trainer_loss_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "dwb_adam_step": [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I64, _F, _P],
 }

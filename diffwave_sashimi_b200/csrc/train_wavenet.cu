@@ -30,6 +30,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace dwb {
@@ -39,6 +41,15 @@ constexpr int TK = 16, NT = 256;
 // Tiles are (64 W) x (64 W) outputs per 256-thread CTA, (4 W) x (4 W) per thread as W x W blocks of 4 x 4 spaced 64 apart
 // (conflict-free float4 shared-memory reads).  W = 2 is the default (16 FMAs per shared-memory load instead of 8);
 // DWB_TRAIN_TILE=64 selects W = 1.
+// DWB_TRAIN_GEMM=mma|simt selects the GEMM family of the training step (tensor-core split-bf16 / exact fp32)
+constexpr bool kTrainMmaDefault = false;
+static bool train_mma() {
+    static const bool on = [] {
+        const char *e = getenv("DWB_TRAIN_GEMM");
+        return e ? strcmp(e, "mma") == 0 : kTrainMmaDefault;
+    }();
+    return on;
+}
 static int tile_w() {
     static const int w = [] { const char *e = getenv("DWB_TRAIN_TILE"); return (e && atoi(e) == 64) ? 1 : 2; }();
     return w;
@@ -181,6 +192,184 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs p) {
             atomicAdd(&p.dW[tap * p.o_tap + m * p.o_m + k * p.o_k], p.alpha * acc[i][j]);
         }
     }
+}
+
+// ---- tensor-core forms of the two GEMM kernels ------------------------------------------------------------------
+// Same contracts as cgemm_kernel / wgrad_kernel.  fp32 operands are split x = hi + lo into bf16 halves while they are
+// staged into shared memory and every product is hi*hi + lo*hi + hi*lo on mma.sync.m16n8k16 with fp32 accumulation
+// (the inference kernels' precision choice, DESIGN.md section 4: ~2^-17 per product).  One CTA = 128 x 128 outputs, 8 warps as
+// 2 (rows) x 4 (columns), a warp = 64 x 32 = 4 x 4 MMA tiles; the reduction dimension advances 32 at a time.
+constexpr int MT_ = 128, MK = 32, MSA = MK + 8, MSB = MT_ + 8;      // MSA / MSB: bf16 row strides that keep ldmatrix conflict free
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void *p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// two consecutive elements of a row -> packed bf16 hi and lo words
+__device__ __forceinline__ void split_pair(float v0, float v1, __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+    *reinterpret_cast<__nv_bfloat162 *>(hi) = __halves2bfloat162(h0, h1);
+    *reinterpret_cast<__nv_bfloat162 *>(lo) = __halves2bfloat162(__float2bfloat16_rn(v0 - __bfloat162float(h0)),
+                                                                 __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+}
+// acc += A[128 x 32] * B[32 x 128] for this warp's 64 x 32 block.  A tiles: [row][k] (k contiguous).
+// BT = false: B tiles are [k][col] (col contiguous, ldmatrix.trans);  BT = true: B tiles are [col][k] (k contiguous).
+template <bool BT>
+__device__ __forceinline__ void warp_mma_tile(const __nv_bfloat16 *Ah, const __nv_bfloat16 *Al, const __nv_bfloat16 *Bh,
+                                              const __nv_bfloat16 *Bl, int wm, int wn, int lane, float (&acc)[4][4][4]) {
+#pragma unroll
+    for (int ks = 0; ks < MK / 16; ++ks) {
+        uint32_t bh[2][4], bl[2][4];
+#pragma unroll
+        for (int n2 = 0; n2 < 2; ++n2) {
+            if (BT) {       // matrices: (cols 0-7, k 0-7), (cols 0-7, k 8-15), (cols 8-15, k 0-7), (cols 8-15, k 8-15)
+                const int col = wn * 32 + n2 * 16 + (lane & 7) + (lane >> 4) * 8, k = ks * 16 + ((lane >> 3) & 1) * 8;
+                ldsm_x4(bh[n2], Bh + col * MSA + k);
+                ldsm_x4(bl[n2], Bl + col * MSA + k);
+            } else {        // rows k 0-7 / 8-15 at cols 0-7, then at cols 8-15, transposed on the way in
+                const int k = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = wn * 32 + n2 * 16 + (lane >> 4) * 8;
+                uint32_t a = (uint32_t)__cvta_generic_to_shared(Bh + k * MSB + col);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                             : "=r"(bh[n2][0]), "=r"(bh[n2][1]), "=r"(bh[n2][2]), "=r"(bh[n2][3]) : "r"(a));
+                a = (uint32_t)__cvta_generic_to_shared(Bl + k * MSB + col);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                             : "=r"(bl[n2][0]), "=r"(bl[n2][1]), "=r"(bl[n2][2]), "=r"(bl[n2][3]) : "r"(a));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t ah[4], al[4];      // rows 0-7 / 8-15 at k 0-7, then at k 8-15
+            const int row = wm * 64 + i * 16 + (lane & 15), k = ks * 16 + (lane >> 4) * 8;
+            ldsm_x4(ah, Ah + row * MSA + k);
+            ldsm_x4(al, Al + row * MSA + k);
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    mma16816(acc[i][2 * n2 + h], ah, bh[n2][2 * h], bh[n2][2 * h + 1]);
+                    mma16816(acc[i][2 * n2 + h], al, bh[n2][2 * h], bh[n2][2 * h + 1]);
+                    mma16816(acc[i][2 * n2 + h], ah, bl[n2][2 * h], bl[n2][2 * h + 1]);
+                }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NT) cgemm_mma_kernel(GemmArgs p) {
+    __shared__ __align__(16) __nv_bfloat16 Ah[MT_ * MSA], Al[MT_ * MSA], Bh[MK * MSB], Bl[MK * MSB];
+    const int b = blockIdx.z, m0 = blockIdx.y * MT_, l0 = blockIdx.x * MT_;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
+    float acc[4][4][4] = {};
+    const float *Xb = p.X + (size_t)b * p.K * p.L;
+    const float *ra = p.rowadd ? p.rowadd + (size_t)b * p.K : nullptr;
+    for (int tap = 0; tap < p.ntap; ++tap) {
+        const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
+        for (int k0 = 0; k0 < p.K; k0 += MK) {
+            for (int e = tid; e < MT_ * MK / 2; e += NT) {             // A: weights, pairs along k
+                const int kk = (e & (MK / 2 - 1)) * 2, mm = e / (MK / 2), m = m0 + mm, k = k0 + kk;
+                float v0 = 0.f, v1 = 0.f;
+                if (m < p.M) {
+                    const float *a = p.A + tap * p.a_tap + m * p.a_m + k * p.a_k;
+                    if (k < p.K) v0 = a[0];
+                    if (k + 1 < p.K) v1 = a[p.a_k];
+                }
+                split_pair(v0, v1, Ah + mm * MSA + kk, Al + mm * MSA + kk);
+            }
+            for (int e = tid; e < MK * MT_ / 2; e += NT) {             // B: activations, pairs along time
+                const int ll = (e & (MT_ / 2 - 1)) * 2, kk = e / (MT_ / 2), k = k0 + kk, l = l0 + ll + sh;
+                float v0 = 0.f, v1 = 0.f;
+                if (k < p.K) {
+                    const float *x = Xb + (size_t)k * p.L;
+                    const float r = ra ? ra[k] : 0.f;
+                    if (l >= 0 && l < p.L) v0 = x[l] + r;
+                    if (l + 1 >= 0 && l + 1 < p.L) v1 = x[l + 1] + r;
+                }
+                split_pair(v0, v1, Bh + kk * MSB + ll, Bl + kk * MSB + ll);
+            }
+            __syncthreads();
+            warp_mma_tile<false>(Ah, Al, Bh, Bl, wm, wn, lane, acc);
+            __syncthreads();
+        }
+    }
+    const int g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const int m = m0 + wm * 64 + i * 16 + g + hrow * 8;
+            if (m >= p.M) continue;
+            const float bm = p.bias ? p.bias_scale * p.bias[m] : 0.f;
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int l = l0 + wn * 32 + n * 8 + t2 + c;
+                    if (l >= p.L) continue;
+                    const size_t idx = ((size_t)b * p.M + m) * p.L + l;
+                    float v = fmaf(p.alpha, acc[i][n][hrow * 2 + c], bm);
+                    if (p.R) v = fmaf(p.beta, p.R[idx], v);
+                    if (p.relu) v = fmaxf(v, 0.f);
+                    p.Y[idx] = v;
+                }
+        }
+}
+
+__global__ void __launch_bounds__(NT) wgrad_mma_kernel(WgradArgs p) {
+    __shared__ __align__(16) __nv_bfloat16 Ah[MT_ * MSA], Al[MT_ * MSA], Bh[MT_ * MSA], Bl[MT_ * MSA];
+    const int nchunk = (p.L + p.lchunk - 1) / p.lchunk;
+    const int b = blockIdx.x / nchunk, ch = blockIdx.x % nchunk;
+    const int tiles_k = (p.K + MT_ - 1) / MT_;
+    const int m0 = (blockIdx.y / tiles_k) * MT_, k0 = (blockIdx.y % tiles_k) * MT_;
+    const int tap = blockIdx.z, sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp & 1, wn = warp >> 1;
+    const int lbeg = ch * p.lchunk, lend = min(p.L, lbeg + p.lchunk);
+    const float *dYb = p.dY + (size_t)b * p.M * p.L;
+    const float *Xb = p.X + (size_t)b * p.K * p.L;
+    const float *ra = p.rowadd ? p.rowadd + (size_t)b * p.K : nullptr;
+    float acc[4][4][4] = {};
+    for (int l0 = lbeg; l0 < lend; l0 += MK) {
+        for (int e = tid; e < MT_ * MK / 2; e += NT) {
+            const int ll = (e & (MK / 2 - 1)) * 2, r = e / (MK / 2), l = l0 + ll;
+            float a0 = 0.f, a1 = 0.f, x0 = 0.f, x1 = 0.f;
+            const int m = m0 + r, k = k0 + r;
+            if (m < p.M) {
+                if (l < lend) a0 = dYb[(size_t)m * p.L + l];
+                if (l + 1 < lend) a1 = dYb[(size_t)m * p.L + l + 1];
+            }
+            if (k < p.K) {
+                const float *x = Xb + (size_t)k * p.L;
+                const float rr = ra ? ra[k] : 0.f;
+                const int ls = l + sh;
+                if (l < lend && ls >= 0 && ls < p.L) x0 = x[ls] + rr;
+                if (l + 1 < lend && ls + 1 >= 0 && ls + 1 < p.L) x1 = x[ls + 1] + rr;
+            }
+            split_pair(a0, a1, Ah + r * MSA + ll, Al + r * MSA + ll);
+            split_pair(x0, x1, Bh + r * MSA + ll, Bl + r * MSA + ll);
+        }
+        __syncthreads();
+        warp_mma_tile<true>(Ah, Al, Bh, Bl, wm, wn, lane, acc);
+        __syncthreads();
+    }
+    const int g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            const int m = m0 + wm * 64 + i * 16 + g + hrow * 8;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int k = k0 + wn * 32 + n * 8 + t2 + c;
+                    if (k >= p.K) continue;
+                    atomicAdd(&p.dW[tap * p.o_tap + m * p.o_m + k * p.o_k], p.alpha * acc[i][n][hrow * 2 + c]);
+                }
+        }
 }
 
 __device__ __forceinline__ float block_sum(float v) {
@@ -446,6 +635,7 @@ struct Trainer {
     // step embedding
     float *e0, *z1, *e1, *z2, *e2, *part, *dpart, *de2, *de1, *tmp, *rs_dS;
     int64_t launches = 0;
+    bool mma = false;       // GEMM family: split-bf16 tensor cores / exact fp32 (dwb_trainer_set_gemm, DWB_TRAIN_GEMM)
 };
 
 static inline int ew_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 16); }
@@ -472,6 +662,11 @@ static int run_gemm(Trainer *tr, cudaStream_t st, const float *A, long long a_ta
     p.M = M; p.K = K; p.L = tr->L; p.ntap = ntap;
     p.shift[0] = s0; p.shift[1] = s1; p.shift[2] = s2;
     p.alpha = alpha; p.bias_scale = bias_scale; p.beta = beta; p.relu = relu;
+    if (tr->mma && M >= 8 && K >= 8) {
+        dim3 grid(ceil_div(tr->L, MT_), ceil_div(M, MT_), tr->B);
+        TR_LAUNCH(tr, cgemm_mma_kernel<<<grid, NT, 0, st>>>(p));
+        return DWB_OK;
+    }
     // narrow outputs (the 1-channel head, tiny test models) keep the 64-wide tile
     const int W = (tile_w() == 2 && M > 64) ? 2 : 1, T = 64 * W;
     dim3 grid(ceil_div(tr->L, T), ceil_div(M, T), tr->B);
@@ -490,14 +685,17 @@ static int run_wgrad(Trainer *tr, cudaStream_t st, const float *dY, const float 
     p.M = M; p.K = K; p.L = tr->L; p.ntap = ntap;
     p.shift[0] = s0; p.shift[1] = s1; p.shift[2] = s2;
     p.alpha = alpha;
-    const int W = (tile_w() == 2 && M > 64 && K > 64) ? 2 : 1, T = 64 * W;
+    const bool mma = tr->mma && M >= 8 && K >= 8;
+    const int W = (mma || (tile_w() == 2 && M > 64 && K > 64)) ? 2 : 1, T = 64 * W;
     // time chunk per CTA: at least two waves of CTAs (2 resident per SM x 148 SMs) however few output tiles the weight has
     // (a 128 x 128 res_conv is ONE tile), at most 2048 samples so that the atomics stay a small share
     const int per_chunk = tr->B * ceil_div(M, T) * ceil_div(K, T) * ntap;
     const int want_chunks = std::max(1, ceil_div(592, per_chunk));
-    p.lchunk = std::min(2048, std::max(128, ceil_div(ceil_div(tr->L, want_chunks), TK) * TK));
+    p.lchunk = std::min(2048, std::max(128, ceil_div(ceil_div(tr->L, want_chunks), MK) * MK));
     dim3 grid(tr->B * ceil_div(tr->L, p.lchunk), ceil_div(M, T) * ceil_div(K, T), ntap);
-    if (W == 2)
+    if (mma)
+        TR_LAUNCH(tr, wgrad_mma_kernel<<<grid, NT, 0, st>>>(p));
+    else if (W == 2)
         TR_LAUNCH(tr, wgrad_kernel<2><<<grid, NT, 0, st>>>(p));
     else
         TR_LAUNCH(tr, wgrad_kernel<1><<<grid, NT, 0, st>>>(p));
@@ -550,6 +748,7 @@ int dwb_trainer_create(const dwb_config *cfg, int device, int B, int L, dwb_trai
     tr->B = B;
     tr->L = L;
     tr->lo = build_layout(cfg);
+    tr->mma = train_mma();
     const size_t C = cfg->res_channels, S = cfg->skip_channels, N = cfg->num_res_layers, BL = (size_t)B * L;
     const size_t Ei = cfg->embed_in, Em = cfg->embed_mid, Eo = cfg->embed_out, P = tr->lo.total;
     const size_t widest = std::max<size_t>(2 * C, S);
@@ -582,6 +781,13 @@ int dwb_trainer_destroy(dwb_trainer *t) {
     if (!tr) return DWB_OK;
     cudaFree(tr->ws);
     delete tr;
+    return DWB_OK;
+}
+
+int dwb_trainer_set_gemm(dwb_trainer *t, int tensor_cores) {
+    Trainer *tr = reinterpret_cast<Trainer *>(t);
+    DWB_REQUIRE(tr != nullptr, DWB_ERR_INVALID, "null trainer");
+    tr->mma = tensor_cores != 0;
     return DWB_OK;
 }
 

@@ -51,7 +51,8 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, betas=(0.9, 0.999), eps=1e
 class Trainer:
     """Optimizer + backward of one model for batches of exactly (batch_size, 1, audio_length)."""
 
-    def __init__(self, net, batch_size, audio_length, lr=2e-4, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, net, batch_size, audio_length, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, gemm=None):
+        """gemm: None = the library default (DWB_TRAIN_GEMM), "mma" = split-bf16 tensor cores, "simt" = exact fp32 tiles."""
         cfg = dict(net._cfg)
         named = list(net.named_parameters())
         if not named or not named[0][1].is_cuda:
@@ -80,6 +81,10 @@ class Trainer:
         c = config_struct(cfg)
         with torch.cuda.device(self.device):
             check(lib().dwb_trainer_create(ctypes.byref(c), self.device.index or 0, self.B, self.L, ctypes.byref(self._h)))
+        if gemm is not None:
+            if gemm not in ("mma", "simt"):
+                raise ValueError("gemm must be None, 'mma' or 'simt'")
+            check(lib().dwb_trainer_set_gemm(self._h, int(gemm == "mma")))
 
     # ---- loss + backward (train.py:198-222 + loss.backward()) ---------------------------------------------------
     def loss_backward(self, audio, diffusion_hyperparams, mel_spec=None, diffusion_steps=None, z=None, return_eps=False):

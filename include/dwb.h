@@ -226,6 +226,10 @@ int dwb_trainer_layout(const dwb_config *cfg, int index, char *name, int name_ca
 int dwb_trainer_create(const dwb_config *cfg, int device, int B, int L, dwb_trainer **out);
 int dwb_trainer_destroy(dwb_trainer *trainer);
 int dwb_trainer_info(dwb_trainer *trainer, int64_t *workspace_bytes, int64_t *launches);
+/* GEMM family of this trainer's convolutions and their gradients: 1 = split-bf16 tensor cores (three mma.sync per product,
+ * fp32 accumulation; the inference kernels' precision), 0 = exact fp32 SIMT tiles.  Default: DWB_TRAIN_GEMM=mma|simt, else the
+ * library's built-in choice. */
+int dwb_trainer_set_gemm(dwb_trainer *trainer, int tensor_cores);
 /* One loss + backward:  x_t = coef[b,0] audio + coef[b,1] z;  eps = net((x_t, steps));  loss = mean((eps - z)^2);
  * grads = d loss / d params (overwritten, not accumulated).
  *   params, grads  flat buffers (dwb_trainer_layout)      audio, z (B,1,L)      steps (B) f32 diffusion steps

@@ -13,7 +13,11 @@ from oracle import train_oracle as TO
 
 pytestmark = pytest.mark.gpu
 
-GRAD_TOL = 1e-4      # fp32 SIMT kernels against fp32 autograd: measured ~1e-6 (printed)
+# exact-fp32 SIMT tiles against fp32 autograd: measured ~1e-6 (printed); split-bf16 tensor-core GEMMs (three MMAs per
+# product, ~2^-17 each): measured values printed, bars well inside the north star's 1e-3
+GRAD_TOL = {"simt": 1e-4, "mma": 5e-4}
+LOSS_TOL = {"simt": 1e-5, "mma": 1e-4}
+GEMMS = ["simt", "mma"]
 
 
 def load(name):
@@ -44,34 +48,35 @@ def _dh(dwb, z):
     return dwb.calc_diffusion_hyperparams(int(z["T"]), float(z["beta_0"]), float(z["beta_T"]))
 
 
-def _check_grads(net, ref, label):
+def _check_grads(net, ref, label, gemm="simt"):
     gscale = max(float(g.norm()) for g in ref.values())
     worst = 0.0
     for k, p in net.named_parameters():
         g = ref[k].double()
         err = float((p.grad.cpu().double() - g).norm())
-        assert err <= GRAD_TOL * float(g.norm()) + 1e-6 * gscale, (label, k, err, float(g.norm()))
+        assert err <= GRAD_TOL[gemm] * float(g.norm()) + (1e-6 if gemm == "simt" else 1e-5) * gscale, (label, k, err, float(g.norm()))
         if float(g.norm()) > 1e-3 * gscale:
             worst = max(worst, err / float(g.norm()))
     return worst
 
 
+@pytest.mark.parametrize("gemm", GEMMS)
 @pytest.mark.parametrize("name", ["train_wnet_a", "train_wnet_b"])
-def test_loss_and_gradients_vs_reference(dwb, name):
+def test_loss_and_gradients_vs_reference(dwb, name, gemm):
     z, cfg = load(name)
     B, _, L = z["audio0"].shape
-    net, tr = _trainer(dwb, cfg, sub(z, "sd0/"), B, L)
+    net, tr = _trainer(dwb, cfg, sub(z, "sd0/"), B, L, gemm=gemm)
     loss, eps = tr.loss_backward(torch.from_numpy(z["audio0"]).cuda(), _dh(dwb, z), diffusion_steps=torch.from_numpy(z["steps0"]),
                                  z=torch.from_numpy(z["z0"]), return_eps=True)
     e = rel_l2(eps.cpu(), z["eps0"])
-    worst = _check_grads(net, sub(z, "grad0/"), name)
-    print(f"{name}: loss {float(loss):.6f} (ref {z['losses'][0]:.6f}) eps rel_l2 {e:.2e} worst gradient rel_l2 {worst:.2e}")
-    assert abs(float(loss) - z["losses"][0]) <= 1e-5 * z["losses"][0] and e < 1e-5
+    worst = _check_grads(net, sub(z, "grad0/"), name, gemm)
+    print(f"{name} [{gemm}]: loss {float(loss):.6f} (ref {z['losses'][0]:.6f}) eps rel_l2 {e:.2e} worst gradient rel_l2 {worst:.2e}")
+    assert abs(float(loss) - z["losses"][0]) <= LOSS_TOL[gemm] * z["losses"][0] and e < LOSS_TOL[gemm]
     # the gradients ARE the module's .grad tensors (views of the flat buffer), and a second call overwrites them
     loss2 = tr.loss_backward(torch.from_numpy(z["audio0"]).cuda(), _dh(dwb, z), diffusion_steps=torch.from_numpy(z["steps0"]),
                              z=torch.from_numpy(z["z0"]))
     assert abs(float(loss2) - float(loss)) <= 1e-6 * float(loss)
-    _check_grads(net, sub(z, "grad0/"), name + " (second call)")
+    _check_grads(net, sub(z, "grad0/"), name + " (second call)", gemm)
 
 
 @pytest.mark.parametrize("name", ["train_wnet_a", "train_wnet_b"])
@@ -109,7 +114,8 @@ def test_three_adam_steps_vs_reference(dwb, name):
     assert torch.equal(tr.exp_avg, m0) and tr.n_steps == 3
 
 
-def test_gradients_vs_fp64_oracle_other_batch(dwb):
+@pytest.mark.parametrize("gemm", GEMMS)
+def test_gradients_vs_fp64_oracle_other_batch(dwb, gemm):
     """Seeded inputs that no fixture holds (ragged length, per-clip steps incl. 0 and T-1) against the fp64 oracle."""
     z, cfg = load("train_wnet_b")
     sd = sub(z, "sd0/")
@@ -117,16 +123,17 @@ def test_gradients_vs_fp64_oracle_other_batch(dwb):
     g = torch.Generator().manual_seed(5)
     audio, zz = torch.rand(B, 1, L, generator=g) * 2 - 1, torch.randn(B, 1, L, generator=g)
     steps = torch.tensor([0, 49])
-    net, tr = _trainer(dwb, cfg, sd, B, L)
+    net, tr = _trainer(dwb, cfg, sd, B, L, gemm=gemm)
     dh = _dh(dwb, z)
     loss = tr.loss_backward(audio.cuda(), dh, diffusion_steps=steps, z=zz)
     lo, _, go = TO.loss_and_grads_manual(cfg, sd, audio, steps, zz, dh["Alpha_bar"].cpu())
-    assert abs(float(loss) - float(lo)) <= 1e-5 * float(lo)
-    worst = _check_grads(net, go, "oracle")
-    print(f"fp64 oracle, B={B} L={L}: worst gradient rel_l2 {worst:.2e}")
+    assert abs(float(loss) - float(lo)) <= LOSS_TOL[gemm] * float(lo)
+    worst = _check_grads(net, go, "oracle", gemm)
+    print(f"fp64 oracle [{gemm}], B={B} L={L}: worst gradient rel_l2 {worst:.2e}")
 
 
-def test_full_size_gradients_vs_reference(dwb):
+@pytest.mark.parametrize("gemm", GEMMS)
+def test_full_size_gradients_vs_reference(dwb, gemm):
     """BASELINE configs[0] (wnet h128/d30) at L = 16000: loss, the norm of every parameter gradient and six complete
     gradient tensors against the reference's autograd on the same seeded weights."""
     z, cfg = load("train_full_wnet_h128_d30")
@@ -135,10 +142,10 @@ def test_full_size_gradients_vs_reference(dwb):
     audio = torch.rand(1, 1, 16000, generator=g) * 2 - 1
     steps = torch.tensor([int(z["step"])])
     zz = torch.randn(1, 1, 16000, generator=g)
-    net, tr = _trainer(dwb, cfg, sd, 1, 16000)
+    net, tr = _trainer(dwb, cfg, sd, 1, 16000, gemm=gemm)
     dh = dwb.calc_diffusion_hyperparams(200, 1e-4, 0.02)
     loss = tr.loss_backward(audio.cuda(), dh, diffusion_steps=steps, z=zz)
-    assert abs(float(loss) - float(z["loss"])) <= 2e-5 * float(z["loss"]), (float(loss), float(z["loss"]))
+    assert abs(float(loss) - float(z["loss"])) <= 2 * LOSS_TOL[gemm] * float(z["loss"]), (float(loss), float(z["loss"]))
     names, norms = [str(n) for n in z["names"]], z["grad_norms"]
     grads = {k: p.grad for k, p in net.named_parameters()}
     gscale = norms.max()
@@ -157,7 +164,7 @@ def test_full_size_gradients_vs_reference(dwb):
             full = max(full, e)
             assert e < 1e-3, (k, e)
     info = tr.info()
-    print(f"wnet h128/d30 L=16000: loss {float(loss):.6f}, worst gradient-norm difference {worst:.2e}, worst full-tensor rel_l2 {full:.2e}, "
+    print(f"wnet h128/d30 L=16000 [{gemm}]: loss {float(loss):.6f}, worst gradient-norm difference {worst:.2e}, worst full-tensor rel_l2 {full:.2e}, "
           f"{info['launches']} launches, workspace {info['workspace_bytes'] / 2**20:.0f} MiB")
 
 
