@@ -194,6 +194,152 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs p) {
     }
 }
 
+// ---- software-pipelined forms (default): the global loads of reduction step i+1 are issued into registers before the FMAs of
+// step i run from shared memory.  profiles/ncu_r2_train.md: without this the 1x1 convolutions spend 3 issue slots waiting on
+// `long_scoreboard` per instruction issued (FMA pipe 33-35 % active) - load, barrier, compute, barrier with nothing in flight.
+// DWB_TRAIN_PREFETCH=0 keeps the plain forms above.
+static bool train_prefetch() {
+    static const bool on = [] { const char *e = getenv("DWB_TRAIN_PREFETCH"); return e ? atoi(e) != 0 : true; }();
+    return on;
+}
+
+template <int W>
+__global__ void __launch_bounds__(NT, 2) cgemm_pf_kernel(GemmArgs p) {
+    constexpr int T = 64 * W, NV = TK * T / NT;
+    __shared__ __align__(16) float As[TK][T + 4];
+    __shared__ __align__(16) float Bs[TK][T + 4];
+    const int b = blockIdx.z, m0 = blockIdx.y * T, l0 = blockIdx.x * T;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    float acc[4 * W][4 * W] = {};
+    const float *Xb = p.X + (size_t)b * p.K * p.L;
+    const float *ra = p.rowadd ? p.rowadd + (size_t)b * p.K : nullptr;
+    const int ksteps = (p.K + TK - 1) / TK, nsteps = p.ntap * ksteps;
+    float va[NV], vb[NV];
+    auto fetch = [&](int step) {
+        const int tap = step / ksteps, k0 = (step - tap * ksteps) * TK;
+        const int sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = tid + i * NT;
+            const int kk = e & (TK - 1), mm = e / TK, m = m0 + mm, k = k0 + kk;
+            va[i] = (m < p.M && k < p.K) ? p.A[tap * p.a_tap + m * p.a_m + k * p.a_k] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = tid + i * NT;
+            const int ll = e & (T - 1), kk = e / T, k = k0 + kk, l = l0 + ll + sh;
+            float v = 0.f;
+            if (k < p.K && l >= 0 && l < p.L) {
+                v = Xb[(size_t)k * p.L + l];
+                if (ra) v += ra[k];
+            }
+            vb[i] = v;
+        }
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = tid + i * NT;
+            As[e & (TK - 1)][e / TK] = va[i];
+            Bs[e / T][e & (T - 1)] = vb[i];
+        }
+    };
+    fetch(0);
+    stage();
+    __syncthreads();
+    for (int step = 0; step < nsteps; ++step) {
+        const bool more = step + 1 < nsteps;
+        if (more) fetch(step + 1);
+        tile_fma<W>(As, Bs, ty, tx, acc);
+        __syncthreads();
+        if (more) {
+            stage();
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4 * W; ++i) {
+        const int m = m0 + tile_pos(ty, i);
+        if (m >= p.M) continue;
+        const float bm = p.bias ? p.bias_scale * p.bias[m] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4 * W; ++j) {
+            const int l = l0 + tile_pos(tx, j);
+            if (l >= p.L) continue;
+            const size_t idx = ((size_t)b * p.M + m) * p.L + l;
+            float v = fmaf(p.alpha, acc[i][j], bm);
+            if (p.R) v = fmaf(p.beta, p.R[idx], v);
+            if (p.relu) v = fmaxf(v, 0.f);
+            p.Y[idx] = v;
+        }
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(NT, 2) wgrad_pf_kernel(WgradArgs p) {
+    constexpr int T = 64 * W, NV = TK * T / NT;
+    __shared__ __align__(16) float As[TK][T + 4];
+    __shared__ __align__(16) float Bs[TK][T + 4];
+    const int nchunk = (p.L + p.lchunk - 1) / p.lchunk;
+    const int b = blockIdx.x / nchunk, ch = blockIdx.x % nchunk;
+    const int tiles_k = (p.K + T - 1) / T;
+    const int m0 = (blockIdx.y / tiles_k) * T, k0 = (blockIdx.y % tiles_k) * T;
+    const int tap = blockIdx.z, sh = tap == 0 ? p.shift[0] : (tap == 1 ? p.shift[1] : p.shift[2]);
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int lbeg = ch * p.lchunk, lend = min(p.L, lbeg + p.lchunk);
+    const float *dYb = p.dY + (size_t)b * p.M * p.L;
+    const float *Xb = p.X + (size_t)b * p.K * p.L;
+    const float *ra = p.rowadd ? p.rowadd + (size_t)b * p.K : nullptr;
+    float acc[4 * W][4 * W] = {};
+    float va[NV], vb[NV];
+    auto fetch = [&](int l0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = tid + i * NT;
+            const int ll = e & (TK - 1), r = e / TK, l = l0 + ll, m = m0 + r, k = k0 + r, ls = l + sh;
+            va[i] = (m < p.M && l < lend) ? dYb[(size_t)m * p.L + l] : 0.f;
+            float v = 0.f;
+            if (k < p.K && l < lend && ls >= 0 && ls < p.L) {
+                v = Xb[(size_t)k * p.L + ls];
+                if (ra) v += ra[k];
+            }
+            vb[i] = v;
+        }
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = tid + i * NT;
+            As[e & (TK - 1)][e / TK] = va[i];
+            Bs[e & (TK - 1)][e / TK] = vb[i];
+        }
+    };
+    fetch(lbeg);
+    stage();
+    __syncthreads();
+    for (int l0 = lbeg; l0 < lend; l0 += TK) {
+        const bool more = l0 + TK < lend;
+        if (more) fetch(l0 + TK);
+        tile_fma<W>(As, Bs, ty, tx, acc);
+        __syncthreads();
+        if (more) {
+            stage();
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4 * W; ++i) {
+        const int m = m0 + tile_pos(ty, i);
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4 * W; ++j) {
+            const int k = k0 + tile_pos(tx, j);
+            if (k >= p.K) continue;
+            atomicAdd(&p.dW[tap * p.o_tap + m * p.o_m + k * p.o_k], p.alpha * acc[i][j]);
+        }
+    }
+}
+
 // ---- tensor-core forms of the two GEMM kernels ------------------------------------------------------------------
 // Same contracts as cgemm_kernel / wgrad_kernel.  fp32 operands are split x = hi + lo into bf16 halves while they are
 // staged into shared memory and every product is hi*hi + lo*hi + hi*lo on mma.sync.m16n8k16 with fp32 accumulation
@@ -670,7 +816,12 @@ static int run_gemm(Trainer *tr, cudaStream_t st, const float *A, long long a_ta
     // narrow outputs (the 1-channel head, tiny test models) keep the 64-wide tile
     const int W = (tile_w() == 2 && M > 64) ? 2 : 1, T = 64 * W;
     dim3 grid(ceil_div(tr->L, T), ceil_div(M, T), tr->B);
-    if (W == 2)
+    if (train_prefetch()) {
+        if (W == 2)
+            TR_LAUNCH(tr, cgemm_pf_kernel<2><<<grid, NT, 0, st>>>(p));
+        else
+            TR_LAUNCH(tr, cgemm_pf_kernel<1><<<grid, NT, 0, st>>>(p));
+    } else if (W == 2)
         TR_LAUNCH(tr, cgemm_kernel<2><<<grid, NT, 0, st>>>(p));
     else
         TR_LAUNCH(tr, cgemm_kernel<1><<<grid, NT, 0, st>>>(p));
@@ -695,7 +846,12 @@ static int run_wgrad(Trainer *tr, cudaStream_t st, const float *dY, const float 
     dim3 grid(tr->B * ceil_div(tr->L, p.lchunk), ceil_div(M, T) * ceil_div(K, T), ntap);
     if (mma)
         TR_LAUNCH(tr, wgrad_mma_kernel<<<grid, NT, 0, st>>>(p));
-    else if (W == 2)
+    else if (train_prefetch()) {
+        if (W == 2)
+            TR_LAUNCH(tr, wgrad_pf_kernel<2><<<grid, NT, 0, st>>>(p));
+        else
+            TR_LAUNCH(tr, wgrad_pf_kernel<1><<<grid, NT, 0, st>>>(p));
+    } else if (W == 2)
         TR_LAUNCH(tr, wgrad_kernel<2><<<grid, NT, 0, st>>>(p));
     else
         TR_LAUNCH(tr, wgrad_kernel<1><<<grid, NT, 0, st>>>(p));
