@@ -264,7 +264,7 @@ def measure_training(name, B, dev, steps=2, warmup=1):
            "ms_per_step": round(ms, 2), "value": round(B / ms * 1e3, 3), "unit": "clips/s per optimizer step", "steps": steps,
            "warmup": warmup, "dtype": "f32", "tflops_fp32": round(3 * fwd * B / ms / 1e9, 2), "loss": round(float(loss), 6),
            "finite": bool(torch.isfinite(loss)), "gpu_launches": (tr.info()["launches"] - n0) // steps + 1,
-           "note": "first correct path: exact-fp32 SIMT GEMM tiles, no tensor cores; not part of the headline metric"}
+           "note": "exact-fp32 software-pipelined SIMT GEMM tiles (tensor-core option measured slower); not part of the headline metric"}
     tr.close()
     return out
 
