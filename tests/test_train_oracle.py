@@ -106,3 +106,12 @@ def test_trainer_rejects_what_is_not_built():
     assert e.value.code == 5
     with pytest.raises(DwbError):
         trainer_layout(dict(_name_="wavenet", unconditional=False, res_channels=16, skip_channels=8, num_res_layers=3, dilation_cycle=2))
+
+
+def test_trainer_needs_a_gpu_model():
+    """No CPU path: a Trainer over CPU parameters raises before anything native is created."""
+    import diffwave_sashimi_b200 as dwb
+    from diffwave_sashimi_b200.training import Trainer
+    net = dwb.construct_model(dict(_name_="wavenet", unconditional=True, res_channels=16, skip_channels=8, num_res_layers=2, dilation_cycle=2))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Trainer(net, 2, 64)
