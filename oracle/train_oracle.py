@@ -3,7 +3,8 @@
 Restates, from the maths, what `train.py:137-143,198-222` does for `model._name_ = wavenet` (unconditional):
     x_t = sqrt(abar_t) x + sqrt(1 - abar_t) z;  loss = mean((net((x_t, t)) - z)^2);  loss.backward();  Adam.step()
 in two independent forms:
-  * `loss_and_grads_autograd`  torch autograd through the oracle's own forward (`diffwave_oracle.wavenet_forward`)
+  * `loss_and_grads_autograd`  torch autograd through the oracle's own forward (`diffwave_oracle.forward`; BOTH backbones - the
+                               SaShiMi form is the pinned oracle for the half of the training row whose kernels are not built)
   * `loss_and_grads_manual`    the hand-derived backward written out layer by layer - the derivation the CUDA
                                kernels of csrc/train_wavenet.cu implement (same shift conventions and scale factors)
 Pinned: tests/test_train_oracle.py checks both against tests/golden/train_wnet_*.npz, which
@@ -18,18 +19,21 @@ from . import diffwave_oracle as O
 
 
 def training_loss(cfg, sd, audio, steps, z, alpha_bar, dtype=torch.float64):
-    """train.py:198-222 with the draws passed in.  -> (loss, eps)"""
+    """train.py:198-222 with the draws passed in.  -> (loss, eps).  Either backbone (O.forward dispatches on cfg['_name_']):
+    the SaShiMi form regenerates every S4 kernel from the parameters inside the graph, as the reference does per step
+    (models/s4.py:674-807), so autograd reaches C, B, P, inv_w_real, w_imag and log_dt."""
     B = audio.shape[0]
     ab = alpha_bar[steps.reshape(B).long()].reshape(B, 1, 1)           # fp32 table lookups, like the reference
     x_t = (torch.sqrt(ab) * audio + torch.sqrt(1 - ab) * z) if dtype == torch.float32 else (
         torch.sqrt(ab).to(dtype) * audio.to(dtype) + torch.sqrt(1 - ab).to(dtype) * z.to(dtype))
-    eps = O.wavenet_forward(cfg, sd, x_t, steps.reshape(B, 1).to(dtype), None, dtype)
+    eps = O.forward(cfg, sd, x_t, steps.reshape(B, 1).to(dtype), None, dtype=dtype)
     return ((eps - z.to(dtype)) ** 2).mean(), eps
 
 
 def loss_and_grads_autograd(cfg, sd, audio, steps, z, alpha_bar, dtype=torch.float64):
     leaves = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
-    loss, eps = training_loss(cfg, leaves, audio, steps, z, alpha_bar, dtype)
+    full = {**sd, **leaves}          # integer buffers (SaShiMi's kernel.L) ride along untouched
+    loss, eps = training_loss(cfg, full, audio, steps, z, alpha_bar, dtype)
     loss.backward()
     return loss.detach(), eps.detach(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
 

@@ -223,6 +223,7 @@ def make_train(ns):
     """Training-step fixtures from the unmodified reference modules + torch autograd + torch.optim.Adam (train.py:84-143):
       train_wnet_{a,b}.npz     tiny WaveNets: start state_dict, three (audio, steps, z) batches, loss / eps / every
                                parameter gradient of batch 0, losses and the state_dict after three Adam steps (lr 2e-4)
+      train_unet_tiny.npz      tiny SaShiMi UNet: loss, eps and every parameter gradient (S4 parameters included) of one batch
       train_full_wnet_h128_d30 BASELINE configs[0] at B=1, L=16000 on our seeded weights: loss, the L2 norm of every
                                parameter gradient and a few complete gradient tensors
     """
@@ -255,6 +256,25 @@ def make_train(ns):
         arrs["losses"] = np.array(losses, dtype=np.float64)
         arrs.update({"sd3/" + k: v.detach().clone().numpy() for k, v in net.state_dict().items()})
         save(name, **arrs)
+
+    # SaShiMi (oracle pin for the half of the row without kernels): the tiny UNet of tiny_unet.npz with settled kernels
+    spec = TINY["tiny_unet"]
+    cfg, net = build(ns, spec["base"], spec["over"])
+    B, L = spec["B"], spec["L"]
+    g = torch.Generator().manual_seed(23)
+    audio = torch.rand(B, 1, L, generator=g) * 2 - 1
+    steps = torch.randint(50, size=(B,), generator=g)
+    z = torch.randn(B, 1, L, generator=g)
+    with torch.no_grad():
+        net((audio, steps.view(B, 1).float()))            # _setup_C (models/s4.py:525-551) before the weights are saved
+    net.train()
+    settled = np.load(os.path.join(HERE, "tiny_unet.npz"))         # the settled weights are input independent: stored once, there
+    assert all(np.array_equal(settled["sd/" + k], v.detach().numpy()) for k, v in net.state_dict().items())
+    loss, eps = ref_training_loss(net, audio, dh, steps, z)
+    loss.backward()
+    save("train_unet_tiny", cfg=np.array(repr(dict(cfg))), T=50, beta_0=1e-4, beta_T=0.05, audio0=audio.numpy(), steps0=steps.numpy(),
+         z0=z.numpy(), losses=np.array([float(loss)]), eps0=eps.detach().numpy(), weights=np.array("tiny_unet.npz sd/"),
+         **{"grad0/" + k: p.grad.numpy() for k, p in net.named_parameters()})
 
     base = "wnet_h128_d30"
     cfg = refshim.Cfg(refshim.MODEL_CFGS[base])

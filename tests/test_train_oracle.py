@@ -49,6 +49,25 @@ def test_loss_and_gradients_vs_reference(name, form):
         assert err <= 2e-5 * float(g.norm()) + 1e-7 * gscale, (k, err, float(g.norm()))
 
 
+def test_sashimi_loss_and_gradients_vs_reference():
+    """The oracle for the half of the training row without kernels: loss, eps and all 236 parameter gradients of a tiny
+    SaShiMi UNet - through the per-step S4 kernel generation, down to C, B, P, inv_w_real, w_imag, log_dt - against the
+    reference's own autograd (models/s4.py:674-807, models/sashimi.py:143-184)."""
+    z, cfg = load("train_unet_tiny")
+    w = np.load(os.path.join(GOLD, "tiny_unet.npz"))
+    sd = {k[3:]: torch.from_numpy(w[k]) for k in w.files if k.startswith("sd/")}
+    ref = sub(z, "grad0/")
+    loss, eps, grads = TO.loss_and_grads_autograd(cfg, sd, torch.from_numpy(z["audio0"]), torch.from_numpy(z["steps0"]),
+                                                  torch.from_numpy(z["z0"]), alpha_bar(z))
+    assert abs(float(loss) - z["losses"][0]) <= 1e-5 * z["losses"][0]
+    assert rel(eps, torch.from_numpy(z["eps0"])) < 1e-5
+    gscale = max(float(g.norm()) for g in ref.values())
+    assert len(ref) == 236 and any(k.endswith("kernel.kernel.log_dt") for k in ref)
+    for k, g in ref.items():
+        err = float((grads[k].double() - g.double()).norm())
+        assert err <= 1e-3 * float(g.norm()) + 1e-6 * gscale, (k, err, float(g.norm()))
+
+
 def test_manual_backward_equals_autograd_fp64():
     z, cfg = load("train_wnet_b")
     args = (cfg, sub(z, "sd0/"), torch.from_numpy(z["audio1"]), torch.from_numpy(z["steps1"]), torch.from_numpy(z["z1"]), alpha_bar(z))
