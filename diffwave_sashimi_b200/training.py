@@ -73,6 +73,7 @@ class Trainer:
                 view.copy_(p.data)
                 p.data = view                                  # the module now reads and writes the flat buffer
                 p.grad = self.grads[off:off + n].view(p.shape)
+        self._first, self._last = named[0][1], named[-1][1]
         self.n_steps = 0
         self.world_size = 1
         self._scale = 1.0
@@ -86,6 +87,15 @@ class Trainer:
                 raise ValueError("gemm must be None, 'mma' or 'simt'")
             check(lib().dwb_trainer_set_gemm(self._h, int(gemm == "mma")))
 
+    def _check_bound(self):
+        """The module's parameters must still be the views of the flat buffer made in __init__: `.cuda()` / `.to()` /
+        `p.data = ...` after construction would re-home them, and training would silently update memory the module no
+        longer reads."""
+        for (_, off, _), p in ((self.layout[0], self._first), (self.layout[-1], self._last)):
+            if p.data_ptr() != self.params.data_ptr() + 4 * off:
+                raise RuntimeError("the model's parameters were moved after Trainer(net, ...) was built (.cuda()/.to()/p.data=...): "
+                                   "build the Trainer after the last move")
+
     # ---- loss + backward (train.py:198-222 + loss.backward()) ---------------------------------------------------
     def loss_backward(self, audio, diffusion_hyperparams, mel_spec=None, diffusion_steps=None, z=None, return_eps=False):
         """Gradients are overwritten (an implicit optimizer.zero_grad()).  Returns the loss as a 0-dim CUDA tensor
@@ -93,6 +103,7 @@ class Trainer:
         reference's CPU-generator draws, in its order (train.py:217-218)."""
         if mel_spec is not None:
             raise _lib.DwbError(5, "mel-conditioned training is not implemented (unconditional WaveNet only)")
+        self._check_bound()
         B, C, L = audio.shape
         if (B, C, L) != (self.B, 1, self.L) or not audio.is_cuda:
             raise ValueError(f"this Trainer was built for CUDA batches of shape ({self.B}, 1, {self.L}), got {tuple(audio.shape)}")
@@ -129,6 +140,7 @@ class Trainer:
 
     # ---- optimizer.step() ---------------------------------------------------------------------------------------------
     def step(self):
+        self._check_bound()
         self.n_steps += 1
         with torch.cuda.device(self.device):
             adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.lr, self.betas, self.eps, self.n_steps, self._scale)
