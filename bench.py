@@ -265,6 +265,10 @@ def measure_training(name, B, dev, steps=2, warmup=1):
            "warmup": warmup, "dtype": "f32", "tflops_fp32": round(3 * fwd * B / ms / 1e9, 2), "loss": round(float(loss), 6),
            "finite": bool(torch.isfinite(loss)), "gpu_launches": (tr.info()["launches"] - n0) // steps + 1,
            "note": "exact-fp32 software-pipelined SIMT GEMM tiles (tensor-core option measured slower); not part of the headline metric"}
+    _, tf, src = peaks()
+    out["roofline"] = {"bound": "tensor", "achieved": out["tflops_fp32"], "peak": tf, "unit": "TFLOP/s",
+                       "frac": round(out["tflops_fp32"] / tf, 4), "peak_source": src,
+                       "note": "fp32-equivalent flops against the single-pass bf16 peak the WaveNet rows are judged by; this path runs on the FP32 pipe"}
     tr.close()
     return out
 
